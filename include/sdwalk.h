@@ -1,0 +1,118 @@
+/* sdwalk.h — C ABI of libsdwalk.so, the Blackwell-native (sm_100a) implementation of the
+ * latent-walk hot path of nateraw/stable-diffusion-videos.
+ *
+ * The reference has no FFI: its hot path sits behind the Python class
+ * StableDiffusionWalkPipeline (stable_diffusion_videos/stable_diffusion_pipeline.py:38).
+ * This header is the boundary a maintainer binds with ctypes; every entry
+ * point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, 1 = invalid argument, 2 = CUDA/driver failure,
+ *     3 = not initialised / wrong state. sdw_last_error() returns a thread-local message.
+ *   - all buffers are caller-owned DEVICE pointers (torch tensors' data_ptr()), sizes explicit.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - no entry point synchronises the device or allocates device memory, except
+ *     sdw_engine_create (records sizes only) — the arena is supplied by the caller.
+ *   - one engine per (process, device); an engine is not thread-safe (mirrors the reference:
+ *     mutable scheduler state, stable_diffusion_pipeline.py:394).
+ */
+#ifndef SDWALK_H_
+#define SDWALK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDW_ABI_VERSION 1
+
+const char* sdw_last_error(void);
+int sdw_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Interpolation inputs — replaces generate_inputs' per-frame torch.lerp + numpy slerp
+ * (stable_diffusion_pipeline.py:466-468, utils.py:42-66) with one batched fp32 kernel.
+ *   lat_a, lat_b : [n_lat] fp16 or fp32 (dtype_is_f16) keyframe latents
+ *   emb_a, emb_b : [n_emb] same dtype, keyframe text embeddings
+ *   t            : [n_frames] fp32 interpolation weights on device
+ *   out_lat      : [n_frames][n_lat], out_emb : [n_frames][n_emb], same dtype
+ *   dot_threshold: 0.9995 in the reference (utils.py:42)
+ * ---------------------------------------------------------------------------------------- */
+int sdw_slerp_lerp_batch(const void* lat_a, const void* lat_b, const void* emb_a, const void* emb_b,
+                         const float* t, int n_frames, int64_t n_lat, int64_t n_emb, int dtype_is_f16,
+                         float dot_threshold, void* out_lat, void* out_emb, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Classifier-free guidance + scheduler update — replaces stable_diffusion_pipeline.py:421-426
+ * (noise_pred chunk/combine and scheduler.step) and :414-415 (cat + scale_model_input) for
+ * every linear-multistep scheduler the reference accepts (PNDM/PLMS, DDIM, LMS).
+ *   eps_nhwc  : [2F][H][W][C] fp16 UNet output, first F = unconditional, last F = conditional
+ *               (or [F] when guidance is off: has_uncond = 0)
+ *   x         : [F][C][H][W] fp32 latents (updated in place)
+ *   x_base    : [F][C][H][W] fp32 PLMS `cur_sample` slot
+ *   hist      : [4][F][C][H][W] fp32 ring of previous combined eps, hist_slot[k] picks the slot
+ *   coef      : see sdw_step_coef
+ *   next_in   : [2F or F][H][W][Cpad] fp16 NHWC model input for the NEXT step (x * next_in_scale, duplicated
+ *               for the uncond/cond halves); may be null on the last step
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sdw_step_coef {
+  float guidance;      /* g in u + g (c - u) */
+  float c_x;           /* coefficient on the sample */
+  float c_e[5];        /* coefficients on {current eps, hist[slot0], hist[slot1], hist[slot2], hist[slot3]} */
+  int32_t hist_slot[4];
+  int32_t use_x_base;  /* 1: sample := x_base (PLMS second step) */
+  int32_t save_x_base; /* 1: x_base := sample before the update (PLMS first step) */
+  int32_t push_slot;   /* >=0: store the combined eps into hist[push_slot] */
+  float next_in_scale; /* scale_model_input factor for the next UNet call */
+} sdw_step_coef;
+
+int sdw_cfg_sched_step(const void* eps_nhwc, int has_uncond, float* x, float* x_base, float* hist,
+                       const sdw_step_coef* coef, int F, int C, int H, int W, void* next_in, int next_in_cpad,
+                       void* stream);
+
+/* latents [F][C][H][W] (fp16/fp32) -> fp32 state * sigma and the first NHWC fp16 model input */
+int sdw_latents_init(const void* latents, int dtype_is_f16, float init_noise_sigma, float in_scale, float* x,
+                     void* model_in, int model_in_cpad, int dup, int F, int C, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Low-level tensor-core op (tests / tooling): one implicit GEMM on the tcgen05 kernel.
+ * Covers Conv2d 3x3 (stride 1/2, nearest-up x2 fused), 1x1, Linear and batched matmul.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sdw_gemm_desc {
+  const void* A;             /* fp16 NHWC lattice base */
+  int32_t C, W, H, B;
+  int64_t sW, sH, sB;        /* element strides */
+  int32_t conv;              /* 0: 1x1; 1: 3x3 s1 p1; 2: 3x3 s2 p1; 3: nearest-up2 + 3x3 (one output parity) */
+  int32_t up_px, up_py;
+  const void* Wt;            /* fp16 [N][taps*Cp] K-major, Cp = ceil64(C) */
+  int32_t N;
+  int64_t ldb, Kb;
+  int32_t b_batched;
+  int64_t sBh, sBb;
+  const float* bias;
+  const float* rowvec;
+  int32_t rowvec_ld;
+  const void* resid;
+  int64_t ldr;
+  void* out;
+  int64_t ldc;
+  int64_t o_sW, o_sH, o_sB;
+  int32_t mode;              /* 0 plain, 1 GEGLU, 2 QKV with V^T scatter */
+  int32_t act;
+  float alpha;
+  int32_t vt_col0, vt_d, vt_heads, vt_ntok;
+  void* vt;
+  int64_t vt_ld;
+  int32_t bn;
+} sdw_gemm_desc;
+
+int sdw_gemm(const sdw_gemm_desc* desc, void* stream);
+
+/* pack an OIHW fp16 conv / [N][K] linear weight into the kernel's K-major [N][taps][Cp] layout */
+int sdw_pack_weight(const void* w_oihw, int N, int C, int kh, int kw, int geglu_interleave, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDWALK_H_ */

@@ -1,0 +1,67 @@
+// sdw_capi.cu — the extern "C" surface of libsdwalk.so (declared in include/sdwalk.h).
+#include "../../include/sdwalk.h"
+#include "sdw_internal.h"
+
+#include <cstring>
+
+namespace sdw {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error() { return g_err.c_str(); }
+}  // namespace sdw
+
+using namespace sdw;
+
+extern "C" {
+
+const char* sdw_last_error(void) { return sdw::last_error(); }
+int sdw_abi_version(void) { return SDW_ABI_VERSION; }
+
+int sdw_slerp_lerp_batch(const void* lat_a, const void* lat_b, const void* emb_a, const void* emb_b, const float* t,
+                         int n_frames, int64_t n_lat, int64_t n_emb, int dtype_is_f16, float dot_threshold,
+                         void* out_lat, void* out_emb, void* stream) {
+  return slerp_lerp_batch(lat_a, lat_b, emb_a, emb_b, t, n_frames, n_lat, n_emb, dtype_is_f16, dot_threshold,
+                          out_lat, out_emb, static_cast<cudaStream_t>(stream));
+}
+
+int sdw_cfg_sched_step(const void* eps_nhwc, int has_uncond, float* x, float* x_base, float* hist,
+                       const sdw_step_coef* coef, int F, int C, int H, int W, void* next_in, int next_in_cpad,
+                       void* stream) {
+  return cfg_sched_step(static_cast<const float*>(eps_nhwc), has_uncond, x, x_base, hist, coef, F, C, H, W, next_in,
+                        next_in_cpad, static_cast<cudaStream_t>(stream));
+}
+
+int sdw_latents_init(const void* latents, int dtype_is_f16, float init_noise_sigma, float in_scale, float* x,
+                     void* model_in, int model_in_cpad, int dup, int F, int C, int H, int W, void* stream) {
+  return latents_init(latents, dtype_is_f16, init_noise_sigma, in_scale, x, model_in, model_in_cpad, dup, F, C, H, W,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int sdw_gemm(const sdw_gemm_desc* c, void* stream) {
+  SDW_REQUIRE(c != nullptr, "null desc");
+  GemmDesc d;
+  d.A = static_cast<const __half*>(c->A);
+  d.C = c->C; d.W = c->W; d.H = c->H; d.B = c->B;
+  d.sW = c->sW; d.sH = c->sH; d.sB = c->sB;
+  d.conv = c->conv; d.up_px = c->up_px; d.up_py = c->up_py;
+  d.Wt = static_cast<const __half*>(c->Wt);
+  d.N = c->N; d.ldb = c->ldb; d.Kb = c->Kb;
+  d.b_batched = c->b_batched; d.sBh = c->sBh; d.sBb = c->sBb;
+  d.bias = c->bias; d.rowvec = c->rowvec; d.rowvec_ld = c->rowvec_ld;
+  d.resid = static_cast<const __half*>(c->resid); d.ldr = c->ldr;
+  d.out = static_cast<__half*>(c->out); d.ldc = c->ldc;
+  d.o_sW = c->o_sW; d.o_sH = c->o_sH; d.o_sB = c->o_sB;
+  d.mode = c->mode; d.act = c->act; d.alpha = c->alpha;
+  d.vt_col0 = c->vt_col0; d.vt_d = c->vt_d; d.vt_heads = c->vt_heads; d.vt_ntok = c->vt_ntok;
+  d.vt = static_cast<__half*>(c->vt); d.vt_ld = c->vt_ld;
+  d.bn = c->bn;
+  GemmLaunch L;
+  if (int e = plan_gemm(d, &L)) return e;
+  return launch_gemm(L, static_cast<cudaStream_t>(stream));
+}
+
+int sdw_pack_weight(const void* w_oihw, int N, int C, int kh, int kw, int geglu_interleave, void* out, void* stream) {
+  return pack_weight(w_oihw, N, C, kh, kw, geglu_interleave, out, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,510 @@
+// sdw_gemm.cu — the tcgen05 implicit-GEMM kernel behind every Conv2d 3x3 / 1x1,
+// Linear and batched matmul of the UNet2DCondition / AutoencoderKL-decoder hot path
+// (reference call sites: stable_diffusion_pipeline.py:418 `self.unet(...)`, :433 `self.vae.decode`).
+//
+// Shape of the kernel (one 128 x BN output tile per CTA, 2 CTAs co-resident per SM):
+//   warp 0    : TMA producer — per K block (tap, 64-channel chunk) one 4-D box load of the
+//               shifted NHWC activation tile (OOB halo = zero fill = conv padding) and one
+//               box of the K-major weight tile, SWIZZLE_128B, into a STAGES-deep smem ring.
+//   warp 1    : TMEM allocator + MMA issuer — one elected thread issues 4 x tcgen05.mma
+//               (M=128, N=BN, K=16) per K block, accumulating fp32 in TMEM; tcgen05.commit
+//               releases the smem stage / signals the epilogue.
+//   warps 2-5 : epilogue — tcgen05.ld the accumulator (thread = output row), fuse
+//               alpha / bias / time-embedding row vector / SiLU / residual / GEGLU /
+//               per-head V^T scatter, write fp16.
+#include "sdw_internal.h"
+#include "sdw_ptx.cuh"
+
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cstring>
+
+namespace sdw {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
+static constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGES = (BN <= 64) ? 4 : (BN <= 160 ? 3 : 4);
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void store8(__half* dst, const float* v, bool vec_ok, int nvalid) {
+  if (vec_ok && nvalid >= 8) {
+    uint4 u;
+    u.x = pack_h2(v[0], v[1]);
+    u.y = pack_h2(v[2], v[3]);
+    u.z = pack_h2(v[4], v[5]);
+    u.w = pack_h2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst) = u;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nvalid) dst[j] = __float2half_rn(v[j]);
+  }
+}
+__device__ __forceinline__ void load8(const __half* src, float* v, bool vec_ok, int nvalid) {
+  if (vec_ok && nvalid >= 8) {
+    uint4 u = *reinterpret_cast<const uint4*>(src);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __half22float2(h[j]);
+      v[2 * j] = f.x;
+      v[2 * j + 1] = f.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (j < nvalid) ? __half2float(src[j]) : 0.f;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * Cfg::B_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates -------------------------------------------------
+  const int m_tile = blockIdx.x;
+  const int tw = m_tile % p.tiles_w;
+  const int th = (m_tile / p.tiles_w) % p.tiles_h;
+  const int tb = m_tile / (p.tiles_w * p.tiles_h);
+  const int x0 = tw * p.bw, y0 = th * p.bh, b0 = tb * p.bb;
+  const int n0 = blockIdx.y * BN;
+  const int num_kb = p.ntaps * p.kchunks;
+
+  // ---- one-time setup -----------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.mapA[0]);
+    tma_prefetch_desc(&p.mapB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const int tap = kb / p.kchunks;
+        const int kc = kb - tap * p.kchunks;
+        mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
+        tma_load_4d(&p.mapA[p.tap_map[tap]], &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kc * BK,
+                    x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b0);
+        tma_load_4d(&p.mapB, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, kb * BK, n0,
+                    p.b_batched ? y0 : 0, p.b_batched ? b0 : 0);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t da = make_desc_k_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
+        const uint64_t db = make_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 fp16 = 32 B inside the 128-B swizzle row: +2 in the (>>4) address field
+          umma_f16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // =========================== epilogue ======================================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int r = quarter * 32 + lane;
+    const int lx = r % p.bw;
+    const int ly = (r / p.bw) % p.bh;
+    const int lb = r / (p.bw * p.bh);
+    const int x = x0 + lx, y = y0 + ly, b = b0 + lb;
+    const bool row_ok = (x < p.W) && (y < p.H) && (b < p.B);
+    const int64_t pix_in = (static_cast<int64_t>(b) * p.H + y) * p.W + x;  // lattice-linear index
+    const int oyy = y * p.os + p.oy, oxx = x * p.os + p.ox;
+    const int64_t out_off = static_cast<int64_t>(b) * p.o_sB + oyy * p.o_sH + oxx * p.o_sW;
+    const int64_t res_off = static_cast<int64_t>(b) * p.r_sB + oyy * p.r_sH + oxx * p.r_sW;
+    const bool vec_out = (((p.o_sW | p.o_sH | p.o_sB) & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    const bool vec_res = p.resid && (((p.r_sW | p.r_sH | p.r_sB) & 7) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0);
+    const float* rowvec = p.rowvec ? p.rowvec + static_cast<int64_t>(b) * p.rowvec_ld : nullptr;
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+
+    if (p.mode == GEMM_GEGLU) {
+      // packed columns: [32 value | 32 gate] pairs -> 32 outputs
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        const int n = n0 + c * 64;
+        if (n >= p.N) break;
+        uint32_t va[32], vg[32];
+        tmem_ld_32x32(taddr + c * 64, va);
+        tmem_ld_32x32(taddr + c * 64 + 32, vg);
+        tmem_ld_wait();
+        if (row_ok) {
+          __half* dst = p.out + out_off + n / 2;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int jj = j8 * 8 + j;
+              float a = __uint_as_float(va[jj]) * p.alpha;
+              float g = __uint_as_float(vg[jj]) * p.alpha;
+              if (p.bias) {
+                a += __ldg(&p.bias[n + jj]);
+                g += __ldg(&p.bias[n + 32 + jj]);
+              }
+              o[j] = a * gelu_erf_f(g);
+            }
+            store8(dst + j8 * 8, o, vec_out, 8);
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n = n0 + c * 32;
+        if (n >= p.N) break;
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        const bool to_vt = (p.mode == GEMM_QKV_VT) && (n >= p.vt_col0);
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          const int nn = n + j8 * 8;
+          const int nvalid = min(8, p.N - nn);
+          if (nvalid <= 0) break;
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a = __uint_as_float(v[j8 * 8 + j]) * p.alpha;
+            if (j < nvalid) {
+              if (p.bias) a += __ldg(&p.bias[nn + j]);
+              if (rowvec) a += __ldg(&rowvec[nn + j]);
+            }
+            if (p.act == 1) a = silu_f(a);
+            o[j] = a;
+          }
+          if (to_vt) {
+            const int64_t bq = pix_in / p.vt_ntok;
+            const int tok = static_cast<int>(pix_in - bq * p.vt_ntok);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j < nvalid) {
+                const int cc = nn + j - p.vt_col0;
+                const int head = cc / p.vt_d;
+                const int dd = cc - head * p.vt_d;
+                p.vt[((bq * p.vt_heads + head) * p.vt_d + dd) * p.vt_ld + tok] = __float2half_rn(o[j]);
+              }
+            }
+          } else {
+            if (p.resid) {
+              float rr[8];
+              load8(p.resid + res_off + nn, rr, vec_res, nvalid);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] += rr[j];
+            }
+            store8(p.out + out_off + nn, o, vec_out, nvalid);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown -------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, Cfg::TMEM_COLS);
+  }
+}
+
+// =============================================================================
+// host side
+// =============================================================================
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+template <int BN>
+static int set_attr() {
+  SDW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   GemmCfg<BN>::SMEM_BYTES));
+  return 0;
+}
+
+int gemm_init() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  SDW_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !fn) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return 2;
+  }
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  if (int e = set_attr<64>()) return e;
+  if (int e = set_attr<128>()) return e;
+  if (int e = set_attr<160>()) return e;
+  if (int e = set_attr<256>()) return e;
+  return 0;
+}
+
+// rank-`rank` fp16 tensor map, dim 0 contiguous, SWIZZLE_128B, zero OOB fill.
+int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+               const uint32_t* box) {
+  if (int e = gemm_init()) return e;
+  cuuint64_t gdim[5];
+  cuuint64_t gstride[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      gstride[i - 1] = strides_elems[i] * 2;
+      if (gstride[i - 1] % 16 != 0) {
+        set_error("TMA global stride must be a multiple of 16 bytes");
+        return 1;
+      }
+    }
+  }
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0) {
+    set_error("TMA global base must be 16-byte aligned");
+    return 1;
+  }
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstride, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return 2;
+  }
+  return 0;
+}
+
+static int pow2_floor(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
+  SDW_REQUIRE(d.A && d.Wt && d.out, "null operand");
+  SDW_REQUIRE(d.C > 0 && d.W > 0 && d.H > 0 && d.B > 0 && d.N > 0, "empty problem");
+  SDW_REQUIRE(d.C % 8 == 0, "channel count must be a multiple of 8 (TMA 16-byte rows)");
+  GemmKParams& p = L->p;
+  std::memset(&p, 0, sizeof(p));
+  const int kchunks = (d.C + BK - 1) / BK;
+  const int Cp = kchunks * BK;
+  p.kchunks = kchunks;
+  p.ntaps = d.conv == 0 ? 1 : 9;
+  // domain (lattice the M tiles walk over) and the tap table
+  int Wd = d.W, Hd = d.H;
+  int nmaps = 1;
+  p.os = 1;
+  p.ox = p.oy = 0;
+  if (d.conv == 0) {
+    p.tap_map[0] = 0;
+    p.tap_dx[0] = p.tap_dy[0] = 0;
+  } else if (d.conv == 1) {
+    for (int t = 0; t < 9; ++t) {
+      p.tap_map[t] = 0;
+      p.tap_dy[t] = static_cast<int8_t>(t / 3 - 1);
+      p.tap_dx[t] = static_cast<int8_t>(t % 3 - 1);
+    }
+  } else if (d.conv == 2) {
+    SDW_REQUIRE(d.W % 2 == 0 && d.H % 2 == 0, "stride-2 conv needs even extents");
+    Wd = d.W / 2;
+    Hd = d.H / 2;
+    nmaps = 4;
+    // in = 2*o + k - 1 : k=0 -> parity 1 shift -1 ; k=1 -> parity 0 shift 0 ; k=2 -> parity 1 shift 0
+    const int par[3] = {1, 0, 1};
+    const int sh[3] = {-1, 0, 0};
+    for (int t = 0; t < 9; ++t) {
+      const int ky = t / 3, kx = t % 3;
+      p.tap_map[t] = static_cast<int8_t>(par[ky] * 2 + par[kx]);
+      p.tap_dy[t] = static_cast<int8_t>(sh[ky]);
+      p.tap_dx[t] = static_cast<int8_t>(sh[kx]);
+    }
+  } else if (d.conv == 3) {
+    // nearest-up x2 then 3x3: output parity (py,px) reads low-res rows yo + floor((py+ky-1)/2)
+    const int sh0[3] = {-1, 0, 0};
+    const int sh1[3] = {0, 0, 1};
+    for (int t = 0; t < 9; ++t) {
+      const int ky = t / 3, kx = t % 3;
+      p.tap_map[t] = 0;
+      p.tap_dy[t] = static_cast<int8_t>(d.up_py ? sh1[ky] : sh0[ky]);
+      p.tap_dx[t] = static_cast<int8_t>(d.up_px ? sh1[kx] : sh0[kx]);
+    }
+    p.os = 2;
+    p.ox = d.up_px;
+    p.oy = d.up_py;
+  } else {
+    SDW_REQUIRE(false, "unknown conv kind");
+  }
+  p.W = Wd;
+  p.H = Hd;
+  p.B = d.B;
+  const int64_t OW = static_cast<int64_t>(Wd) * p.os, OH = static_cast<int64_t>(Hd) * p.os;
+  // tile geometry: bw*bh*bb = 128
+  int bw = std::min(pow2_floor(Wd), BM);
+  if (Wd > BM) bw = BM;
+  int bh = std::min(pow2_floor(Hd), BM / bw);
+  int bb = BM / (bw * bh);
+  if (d.b_batched) {
+    SDW_REQUIRE(d.conv == 0, "batched matmul is 1x1");
+    bw = BM;
+    bh = 1;
+    bb = 1;
+  }
+  p.bw = bw;
+  p.bh = bh;
+  p.bb = bb;
+  p.tiles_w = (Wd + bw - 1) / bw;
+  p.tiles_h = (Hd + bh - 1) / bh;
+  const int tiles_b = (d.B + bb - 1) / bb;
+  p.N = d.N;
+  p.b_batched = d.b_batched;
+  // BLOCK_N choice
+  int bn = d.bn;
+  if (bn == 0) {
+    if (d.mode == GEMM_GEGLU) bn = 128;
+    else if (d.N % 160 == 0 && d.N % 128 != 0) bn = 160;
+    else if (d.N <= 64) bn = 64;
+    else bn = 128;
+  }
+  SDW_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "unsupported BLOCK_N");
+  if (d.mode == GEMM_GEGLU) SDW_REQUIRE(bn % 64 == 0 && d.N % 64 == 0, "GEGLU needs 64-column pairs");
+  if (d.mode == GEMM_QKV_VT) SDW_REQUIRE(d.vt && d.vt_col0 % 32 == 0 && d.vt_d > 0, "bad V^T split");
+  L->bn = bn;
+  L->grid = dim3(p.tiles_w * p.tiles_h * tiles_b, (d.N + bn - 1) / bn, 1);
+  // tensor maps: A
+  for (int m = 0; m < nmaps; ++m) {
+    const __half* base = d.A;
+    uint64_t dims[4] = {static_cast<uint64_t>(d.C), static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H),
+                        static_cast<uint64_t>(d.B)};
+    uint64_t strides[4] = {1, static_cast<uint64_t>(d.sW), static_cast<uint64_t>(d.sH), static_cast<uint64_t>(d.sB)};
+    if (d.conv == 2) {
+      const int py = m / 2, px = m % 2;
+      base = d.A + py * d.sH + px * d.sW;
+      dims[1] = Wd;
+      dims[2] = Hd;
+      strides[1] = 2 * d.sW;
+      strides[2] = 2 * d.sH;
+    }
+    // degenerate extents still need a non-zero, 16B-multiple stride
+    for (int i = 1; i < 4; ++i)
+      if (strides[i] == 0) strides[i] = static_cast<uint64_t>(Cp);
+    uint32_t box[4] = {BK, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bb)};
+    if (int e = encode_map(&p.mapA[m], base, 4, dims, strides, box)) return e;
+  }
+  {
+    const int64_t ldb = d.ldb ? d.ldb : static_cast<int64_t>(p.ntaps) * Cp;
+    uint64_t dims[4] = {static_cast<uint64_t>(d.Kb ? d.Kb : static_cast<int64_t>(p.ntaps) * Cp),
+                        static_cast<uint64_t>(d.N), static_cast<uint64_t>(d.b_batched ? Hd : 1),
+                        static_cast<uint64_t>(d.b_batched ? d.B : 1)};
+    uint64_t strides[4] = {1, static_cast<uint64_t>(ldb), static_cast<uint64_t>(d.b_batched ? d.sBh : 0),
+                           static_cast<uint64_t>(d.b_batched ? d.sBb : 0)};
+    for (int i = 2; i < 4; ++i)
+      if (strides[i] == 0) strides[i] = static_cast<uint64_t>(ldb);
+    uint32_t box[4] = {BK, static_cast<uint32_t>(bn), 1, 1};
+    if (int e = encode_map(&p.mapB, d.Wt, 4, dims, strides, box)) return e;
+  }
+  p.bias = d.bias;
+  p.rowvec = d.rowvec;
+  p.rowvec_ld = d.rowvec_ld;
+  p.resid = d.resid;
+  p.out = d.out;
+  if (d.o_sW || d.o_sH || d.o_sB) {
+    p.o_sW = d.o_sW; p.o_sH = d.o_sH; p.o_sB = d.o_sB;
+  } else {
+    p.o_sW = d.ldc; p.o_sH = OW * d.ldc; p.o_sB = OH * OW * d.ldc;
+  }
+  if (d.r_sW || d.r_sH || d.r_sB) {
+    p.r_sW = d.r_sW; p.r_sH = d.r_sH; p.r_sB = d.r_sB;
+  } else {
+    const int64_t ldr = d.ldr ? d.ldr : d.ldc;
+    p.r_sW = ldr; p.r_sH = OW * ldr; p.r_sB = OH * OW * ldr;
+  }
+  p.mode = d.mode;
+  p.act = d.act;
+  p.alpha = d.alpha;
+  p.vt_col0 = d.vt_col0;
+  p.vt_d = d.vt_d;
+  p.vt_heads = d.vt_heads;
+  p.vt_ntok = d.vt_ntok > 0 ? d.vt_ntok : 1;
+  p.vt = d.vt;
+  p.vt_ld = d.vt_ld;
+  return 0;
+}
+
+int launch_gemm(const GemmLaunch& l, cudaStream_t stream) {
+  switch (l.bn) {
+    case 64:
+      gemm_tc_kernel<64><<<l.grid, GEMM_THREADS, GemmCfg<64>::SMEM_BYTES, stream>>>(l.p);
+      break;
+    case 128:
+      gemm_tc_kernel<128><<<l.grid, GEMM_THREADS, GemmCfg<128>::SMEM_BYTES, stream>>>(l.p);
+      break;
+    case 160:
+      gemm_tc_kernel<160><<<l.grid, GEMM_THREADS, GemmCfg<160>::SMEM_BYTES, stream>>>(l.p);
+      break;
+    case 256:
+      gemm_tc_kernel<256><<<l.grid, GEMM_THREADS, GemmCfg<256>::SMEM_BYTES, stream>>>(l.p);
+      break;
+    default:
+      set_error("bad BLOCK_N");
+      return 1;
+  }
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sdw

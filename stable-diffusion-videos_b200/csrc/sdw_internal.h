@@ -1,0 +1,129 @@
+// sdw_internal.h — host-side internal API shared by the kernels' launchers, the
+// engine (sdw_engine.cu) and the C-ABI (sdw_capi.cu).  Not part of the public ABI.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace sdw {
+
+// ---------------------------------------------------------------------------
+// error plumbing: every launcher returns 0 on success; message in thread-local
+// ---------------------------------------------------------------------------
+void set_error(const std::string& msg);
+const char* last_error();
+#define SDW_CUDA_OK(expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ::sdw::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+      return 2;                                                                                \
+    }                                                                                          \
+  } while (0)
+#define SDW_REQUIRE(cond, msg)                                                                 \
+  do {                                                                                         \
+    if (!(cond)) {                                                                             \
+      ::sdw::set_error(std::string("invalid argument: ") + (msg) + " [" #cond "]");            \
+      return 1;                                                                                \
+    }                                                                                          \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// tcgen05 implicit-GEMM (conv3x3 / conv1x1 / linear / batched matmul)
+// ---------------------------------------------------------------------------
+// out[pix, n] = epi( sum_{tap, c} A[lattice(tap)][pix shifted by (dx,dy)][c] * Wt[n][tap*Cp + c] )
+// A is an NHWC fp16 lattice (C, W, H, B) read through up to four TMA maps (one
+// per input sub-lattice; >1 only for stride-2 convs), Wt is K-major [N][ntaps*Cp].
+enum GemmMode : int {
+  GEMM_PLAIN = 0,   // out[pix*ldc + n]
+  GEMM_GEGLU = 1,   // packed (value|gate) 32-column pairs -> out[pix*ldc + n/2]
+  GEMM_QKV_VT = 2,  // cols < vt_col0 plain; cols >= vt_col0 written transposed per head (V^T)
+};
+
+struct alignas(64) GemmKParams {
+  CUtensorMap mapA[4];
+  CUtensorMap mapB;
+  int8_t tap_map[12], tap_dx[12], tap_dy[12];
+  int ntaps, kchunks;       // K blocks = ntaps * kchunks, each 64 wide
+  int W, H, B;              // tile-grid domain (the A lattice extents)
+  int bw, bh, bb;           // M tile = bw*bh*bb = 128 lattice points
+  int tiles_w, tiles_h;     // tiles per (w,h); tiles along b = gridDim.x / (tiles_w*tiles_h)
+  int N;                    // GEMM N (packed columns)
+  int b_batched;            // 1: weight map coords (.., y0, b0) = lattice (h, b) (batched matmul)
+  // epilogue
+  const float* bias;        // [N] or null
+  const float* rowvec;      // [B][rowvec_ld] per-sample vector added per column (time-embedding proj) or null
+  int rowvec_ld;
+  const __half* resid;      // residual or null; element offset = b*r_sB + oy'*r_sH + ox'*r_sW + n
+  int64_t r_sW, r_sH, r_sB;
+  __half* out;              // element offset = b*o_sB + (y*os+oy)*o_sH + (x*os+ox)*o_sW + n
+  int64_t o_sW, o_sH, o_sB;
+  int os, ox, oy;
+  int mode;
+  int act;                  // 0 none, 1 SiLU
+  float alpha;              // scale on the accumulator (before bias)
+  // GEMM_QKV_VT
+  int vt_col0, vt_d, vt_heads, vt_ntok;
+  __half* vt;               // [b][head][d][vt_ld]
+  int64_t vt_ld;
+};
+
+struct GemmLaunch {
+  GemmKParams p;
+  dim3 grid;
+  int bn;  // BLOCK_N variant
+};
+
+// Describes one implicit GEMM in host terms; plan_gemm() turns it into a launch.
+struct GemmDesc {
+  const __half* A = nullptr;       // lattice base
+  int C = 0, W = 0, H = 1, B = 1;  // input lattice extents (elements)
+  int64_t sW = 0, sH = 0, sB = 0;  // element strides of the input lattice (channel stride is 1)
+  int conv = 0;                    // 0: 1x1 / linear; 1: 3x3 stride 1 pad 1; 2: 3x3 stride 2 pad 1; 3: nearest-up2 + 3x3 (parity in up_px/up_py)
+  int up_px = 0, up_py = 0;
+  const __half* Wt = nullptr;      // [N][ntaps*Cp] (Cp = C rounded up to 64) K-major
+  int N = 0;
+  int64_t ldb = 0;                 // weight row pitch in elements (0 -> ntaps*Cp)
+  int64_t Kb = 0;                  // valid K extent of the weight rows (0 -> ntaps*Cp); beyond it reads as zero
+  int b_batched = 0;               // weights indexed by lattice (h, b): batched matmul
+  int64_t sBh = 0, sBb = 0;        // weight strides (elements) along lattice h and b when b_batched
+  const float* bias = nullptr;
+  const float* rowvec = nullptr;
+  int rowvec_ld = 0;
+  const __half* resid = nullptr;
+  int64_t ldr = 0;                 // residual pixel pitch (0 -> ldc); or explicit strides below
+  int64_t r_sW = 0, r_sH = 0, r_sB = 0;
+  __half* out = nullptr;
+  int64_t ldc = 0;                 // output pixel pitch; NHWC-contiguous output unless o_s* are given
+  int64_t o_sW = 0, o_sH = 0, o_sB = 0;
+  int mode = GEMM_PLAIN;
+  int act = 0;
+  float alpha = 1.f;
+  int vt_col0 = 0, vt_d = 0, vt_heads = 0, vt_ntok = 0;
+  __half* vt = nullptr;
+  int64_t vt_ld = 0;
+  int bn = 0;  // 0 = auto
+};
+
+int plan_gemm(const GemmDesc& d, GemmLaunch* out);
+int launch_gemm(const GemmLaunch& l, cudaStream_t stream);
+int gemm_init();  // resolves the driver entry point, sets smem attributes
+int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+               const uint32_t* box);
+
+// ---------------------------------------------------------------------------
+// fp32 helper kernels (sdw_elem.cu)
+// ---------------------------------------------------------------------------
+int slerp_lerp_batch(const void* lat_a, const void* lat_b, const void* emb_a, const void* emb_b, const float* t,
+                     int n_frames, int64_t n_lat, int64_t n_emb, int is_f16, float thr, void* out_lat, void* out_emb,
+                     cudaStream_t stream);
+int cfg_sched_step(const float* eps, int has_uncond, float* x, float* x_base, float* hist, const void* coef, int F,
+                   int C, int H, int W, void* next_in, int cpad, cudaStream_t stream);
+int latents_init(const void* latents, int is_f16, float sigma, float in_scale, float* x, void* model_in, int cpad,
+                 int dup, int F, int C, int H, int W, cudaStream_t stream);
+int pack_weight(const void* w, int N, int C, int kh, int kw, int geglu, void* out, cudaStream_t stream);
+
+}  // namespace sdw

@@ -1,0 +1,227 @@
+"""GPU parity tests of the tcgen05 implicit-GEMM kernel (sdw_gemm) against torch fp32 references.
+
+Tolerance: inputs are fp16, accumulation fp32, output rounded once to fp16 -> |err| <= 2^-9 * max|ref| + 1e-3
+(the per-kernel bound of SURVEY.md §8d).
+"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as Fn
+
+pytestmark = pytest.mark.gpu
+
+
+def _native():
+    from stable_diffusion_videos_b200 import _native as n
+    return n
+
+
+def _tol(ref):
+    return float(ref.abs().max()) * 2.0 ** -9 + 1e-3
+
+
+def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None):
+    """x: [B,H,W,C] fp16 cuda; returns NHWC fp16 output computed by the native kernel."""
+    n = _native()
+    B, H, W, Cc = x_nhwc.shape
+    N = w_oihw.shape[0]
+    wp = n.pack_weight(w_oihw, geglu=(mode == 1))
+    if conv == 2:
+        OH, OW = H // 2, W // 2
+    elif conv == 3:
+        OH, OW = 2 * H, 2 * W
+    else:
+        OH, OW = H, W
+    ncols = N // 2 if mode == 1 else N
+    out = torch.full((B, OH, OW, ncols), float("nan"), dtype=torch.float16, device="cuda")
+    parities = [(0, 0), (0, 1), (1, 0), (1, 1)] if conv == 3 else [(0, 0)]
+    for (py, px) in parities:
+        d = n.GemmDesc()
+        d.A = x_nhwc.data_ptr()
+        d.C, d.W, d.H, d.B = Cc, W, H, B
+        d.sW, d.sH, d.sB = x_nhwc.stride(2), x_nhwc.stride(1), x_nhwc.stride(0)
+        d.conv = conv
+        d.up_px, d.up_py = px, py
+        d.Wt = wp.data_ptr()
+        d.N = N
+        d.bias = bias.data_ptr() if bias is not None else None
+        if rowvec is not None:
+            d.rowvec = rowvec.data_ptr()
+            d.rowvec_ld = rowvec.shape[1]
+        if resid is not None:
+            d.resid = resid.data_ptr()
+            d.ldr = resid.shape[-1]
+        d.out = out.data_ptr()
+        d.ldc = ncols
+        d.mode = mode
+        d.act = act
+        d.alpha = 1.0
+        d.bn = bn
+        n.gemm(d)
+    torch.cuda.synchronize()
+    return out
+
+
+def ref_conv(x_nhwc, w, conv, bias=None, rowvec=None, resid=None, act=0):
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    wf = w.float()
+    if conv == 0:
+        y = Fn.conv2d(x, wf.reshape(wf.shape[0], wf.shape[1], 1, 1))
+    elif conv == 1:
+        y = Fn.conv2d(x, wf, padding=1)
+    elif conv == 2:
+        y = Fn.conv2d(x, wf, stride=2, padding=1)
+    else:
+        y = Fn.conv2d(Fn.interpolate(x, scale_factor=2.0, mode="nearest"), wf, padding=1)
+    if bias is not None:
+        y = y + bias.float()[None, :, None, None]
+    if rowvec is not None:
+        y = y + rowvec.float()[:, :, None, None]
+    if act == 1:
+        y = Fn.silu(y)
+    y = y.permute(0, 2, 3, 1)
+    if resid is not None:
+        y = y + resid.float()
+    return y
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.float16).cuda()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (300, 320, 320, 0), (77 * 2, 640, 768, 128),
+                                       (2, 1280, 320, 0), (1024, 64, 128, 64), (512, 512, 512, 256),
+                                       (8192, 320, 2880, 160)])
+def test_linear(M, N, K, bn):
+    x = _rand(1, 1, M, K, seed=1)
+    w = _rand(N, K, scale=K ** -0.5, seed=2)
+    bias = _rand(N, seed=3).float()
+    out = run_conv(x, w, 0, bias=bias, bn=bn)
+    ref = ref_conv(x, w, 0, bias=bias)
+    err = (out.float() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all()
+    assert err <= _tol(ref), (err, _tol(ref))
+
+
+@pytest.mark.parametrize("B,H,W,Cc,N", [(2, 16, 16, 64, 128), (2, 8, 8, 320, 320), (1, 64, 64, 320, 320),
+                                         (3, 4, 4, 128, 64), (2, 32, 32, 192, 160), (4, 2, 2, 64, 64),
+                                         (2, 1, 1, 64, 64), (1, 24, 24, 64, 64)])
+def test_conv3x3(B, H, W, Cc, N):
+    x = _rand(B, H, W, Cc, seed=4)
+    w = _rand(N, Cc, 3, 3, scale=(9 * Cc) ** -0.5, seed=5)
+    bias = _rand(N, seed=6).float()
+    rowvec = _rand(B, N, seed=7).float()
+    out = run_conv(x, w, 1, bias=bias, rowvec=rowvec)
+    ref = ref_conv(x, w, 1, bias=bias, rowvec=rowvec)
+    err = (out.float() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all()
+    assert err <= _tol(ref), (err, _tol(ref))
+
+
+def test_conv3x3_residual_silu():
+    x = _rand(2, 16, 16, 128, seed=8)
+    w = _rand(128, 128, 3, 3, scale=(9 * 128) ** -0.5, seed=9)
+    resid = _rand(2, 16, 16, 128, seed=10)
+    out = run_conv(x, w, 1, resid=resid, act=1)
+    ref = ref_conv(x, w, 1, resid=resid, act=1)
+    assert (out.float() - ref).abs().max().item() <= _tol(ref)
+
+
+@pytest.mark.parametrize("B,H,W,Cc,N", [(2, 16, 16, 64, 128), (1, 64, 64, 320, 320), (2, 2, 2, 64, 64)])
+def test_conv3x3_stride2(B, H, W, Cc, N):
+    x = _rand(B, H, W, Cc, seed=11)
+    w = _rand(N, Cc, 3, 3, scale=(9 * Cc) ** -0.5, seed=12)
+    bias = _rand(N, seed=13).float()
+    out = run_conv(x, w, 2, bias=bias)
+    ref = ref_conv(x, w, 2, bias=bias)
+    assert (out.float() - ref).abs().max().item() <= _tol(ref)
+
+
+@pytest.mark.parametrize("B,H,W,Cc,N", [(2, 8, 8, 64, 128), (1, 32, 32, 128, 128), (2, 1, 1, 64, 64)])
+def test_upsample_conv3x3(B, H, W, Cc, N):
+    x = _rand(B, H, W, Cc, seed=14)
+    w = _rand(N, Cc, 3, 3, scale=(9 * Cc) ** -0.5, seed=15)
+    bias = _rand(N, seed=16).float()
+    out = run_conv(x, w, 3, bias=bias)
+    ref = ref_conv(x, w, 3, bias=bias)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() <= _tol(ref)
+
+
+def test_geglu():
+    M, K, Ch = 256, 128, 256  # Linear(K -> 2*Ch), out = a * gelu(g)
+    x = _rand(1, 1, M, K, seed=17)
+    w = _rand(2 * Ch, K, scale=K ** -0.5, seed=18)
+    bias = _rand(2 * Ch, seed=19).float()
+    n = _native()
+    # bias must follow the same row interleave as the packed weight
+    blk = torch.arange(2 * Ch, device="cuda")
+    b64, within = blk // 64, blk % 64
+    src = torch.where(within < 32, b64 * 32 + within, Ch + b64 * 32 + within - 32)
+    out = run_conv(x, w, 0, bias=bias[src].contiguous(), mode=1)
+    h = x.float().reshape(M, K) @ w.float().t() + bias
+    a, g = h.chunk(2, dim=-1)
+    ref = (a * Fn.gelu(g)).reshape(1, 1, M, Ch)
+    assert (out.float() - ref).abs().max().item() <= _tol(ref)
+
+
+def test_qkv_vt_and_batched_attention_matmuls():
+    """QKV projection with V^T scatter, then S = Q K^T and O = P V as head-batched matmuls."""
+    n = _native()
+    Bn, Ntok, Cc, heads = 2, 256, 128, 4
+    d = Cc // heads
+    x = _rand(Bn, 1, Ntok, Cc, seed=20)
+    wqkv = _rand(3 * Cc, Cc, scale=Cc ** -0.5, seed=21)
+    wp = n.pack_weight(wqkv)
+    qk = torch.zeros((Bn, Ntok, 2 * Cc), dtype=torch.float16, device="cuda")
+    vt = torch.zeros((Bn, heads, d, Ntok), dtype=torch.float16, device="cuda")
+    g = n.GemmDesc()
+    g.A = x.data_ptr(); g.C, g.W, g.H, g.B = Cc, Ntok, 1, Bn
+    g.sW, g.sH, g.sB = Cc, Ntok * Cc, Ntok * Cc
+    g.Wt = wp.data_ptr(); g.N = 3 * Cc
+    g.out = qk.data_ptr(); g.ldc = 2 * Cc
+    g.mode = 2; g.alpha = 1.0
+    g.vt_col0, g.vt_d, g.vt_heads, g.vt_ntok = 2 * Cc, d, heads, Ntok
+    g.vt = vt.data_ptr(); g.vt_ld = Ntok
+    n.gemm(g)
+    torch.cuda.synchronize()
+    ref = x.float().reshape(Bn, Ntok, Cc) @ wqkv.float().t()
+    q_ref, k_ref, v_ref = ref.split(Cc, dim=-1)
+    assert (qk.float() - torch.cat([q_ref, k_ref], -1)).abs().max().item() <= _tol(ref)
+    vt_ref = v_ref.reshape(Bn, Ntok, heads, d).permute(0, 2, 3, 1)
+    assert (vt.float() - vt_ref).abs().max().item() <= _tol(ref)
+
+    # S[b,h] = Q[b,:,h,:] K[b,:,h,:]^T * d^-0.5 : lattice (C=d, W=tok, H=heads, B=b)
+    S = torch.zeros((Bn, heads, Ntok, Ntok), dtype=torch.float16, device="cuda")
+    g = n.GemmDesc()
+    g.A = qk.data_ptr(); g.C, g.W, g.H, g.B = d, Ntok, heads, Bn
+    g.sW, g.sH, g.sB = 2 * Cc, d, Ntok * 2 * Cc
+    g.Wt = qk.data_ptr() + Cc * 2; g.N = Ntok; g.ldb = 2 * Cc; g.Kb = d
+    g.b_batched = 1; g.sBh = d; g.sBb = Ntok * 2 * Cc
+    g.out = S.data_ptr(); g.ldc = Ntok
+    g.o_sW, g.o_sH, g.o_sB = Ntok, Ntok * Ntok, heads * Ntok * Ntok
+    g.alpha = d ** -0.5
+    n.gemm(g)
+    torch.cuda.synchronize()
+    q = qk[..., :Cc].float().reshape(Bn, Ntok, heads, d).permute(0, 2, 1, 3)
+    k = qk[..., Cc:].float().reshape(Bn, Ntok, heads, d).permute(0, 2, 1, 3)
+    S_ref = q @ k.transpose(-1, -2) * d ** -0.5
+    assert (S.float() - S_ref).abs().max().item() <= _tol(S_ref)
+
+    # O[b, tok, h*d + :] = P[b,h] V[b,h]  with P = softmax(S) (torch), V^T from the scatter above
+    P = torch.softmax(S.float(), -1).to(torch.float16).contiguous()
+    O = torch.zeros((Bn, Ntok, Cc), dtype=torch.float16, device="cuda")
+    g = n.GemmDesc()
+    g.A = P.data_ptr(); g.C, g.W, g.H, g.B = Ntok, Ntok, heads, Bn
+    g.sW, g.sH, g.sB = Ntok, Ntok * Ntok, heads * Ntok * Ntok
+    g.Wt = vt.data_ptr(); g.N = d; g.ldb = Ntok; g.Kb = Ntok
+    g.b_batched = 1; g.sBh = d * Ntok; g.sBb = heads * d * Ntok
+    g.out = O.data_ptr(); g.ldc = Cc
+    g.o_sW, g.o_sH, g.o_sB = Cc, d, Ntok * Cc
+    g.alpha = 1.0; g.bn = 64
+    n.gemm(g)
+    torch.cuda.synchronize()
+    O_ref = (P.float() @ vt.float().transpose(-1, -2)).permute(0, 2, 1, 3).reshape(Bn, Ntok, Cc)
+    assert (O.float() - O_ref).abs().max().item() <= _tol(O_ref)
