@@ -47,7 +47,7 @@ int sdw_slerp_lerp_batch(const void* lat_a, const void* lat_b, const void* emb_a
  * Classifier-free guidance + scheduler update — replaces stable_diffusion_pipeline.py:421-426
  * (noise_pred chunk/combine and scheduler.step) and :414-415 (cat + scale_model_input) for
  * every linear-multistep scheduler the reference accepts (PNDM/PLMS, DDIM, LMS).
- *   eps_nhwc  : [2F][H][W][C] fp16 UNet output, first F = unconditional, last F = conditional
+ *   eps_nhwc  : [2F][H][W][C] fp32 UNet output, first F = unconditional, last F = conditional
  *               (or [F] when guidance is off: has_uncond = 0)
  *   x         : [F][C][H][W] fp32 latents (updated in place)
  *   x_base    : [F][C][H][W] fp32 PLMS `cur_sample` slot
@@ -66,6 +66,9 @@ typedef struct sdw_step_coef {
   int32_t push_slot;   /* >=0: store the combined eps into hist[push_slot] */
   float next_in_scale; /* scale_model_input factor for the next UNet call */
 } sdw_step_coef;
+/* update: e = u + g (c - u);  s = use_x_base ? x_base : x;  x' = c_x s + c_e[0] e + sum_j c_e[1+j] hist[hist_slot[j]];
+ * covers PNDM/PLMS (warm-up, cur_sample step, 4-term Adams-Bashforth), DDIM eps / v-prediction (eta = 0) and
+ * LMS (epsilon) exactly; coefficients are computed on the host in fp64 (see schedulers.py). */
 
 int sdw_cfg_sched_step(const void* eps_nhwc, int has_uncond, float* x, float* x_base, float* hist,
                        const sdw_step_coef* coef, int F, int C, int H, int W, void* next_in, int next_in_cpad,
@@ -74,6 +77,61 @@ int sdw_cfg_sched_step(const void* eps_nhwc, int has_uncond, float* x, float* x_
 /* latents [F][C][H][W] (fp16/fp32) -> fp32 state * sigma and the first NHWC fp16 model input */
 int sdw_latents_init(const void* latents, int dtype_is_f16, float init_noise_sigma, float in_scale, float* x,
                      void* model_in, int model_in_cpad, int dup, int F, int C, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Engine: the whole per-frame sampler (stable_diffusion_pipeline.py:412-438, 450) for `frames` frames per call.
+ * Life cycle: create(cfg) -> arena_bytes -> bind(arena) -> load_param xN -> set_schedule -> sample xN -> destroy.
+ * Parameter names are the diffusers state-dict keys of the UNet; VAE decoder keys carry a "vae." prefix
+ * ("vae.decoder.conv_in.weight", "vae.post_quant_conv.weight", attention as to_q/to_k/to_v/to_out.0).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sdw_engine sdw_engine;
+
+typedef struct sdw_engine_config {
+  /* UNet2DConditionModel (config.json of the checkpoint) */
+  int32_t in_channels, out_channels;
+  int32_t num_levels;
+  int32_t block_out_channels[4];
+  int32_t layers_per_block;
+  int32_t attention_heads[4];      /* diffusers' `attention_head_dim` = NUMBER of heads per level */
+  int32_t cross_attention_dim, ctx_tokens;
+  int32_t norm_num_groups;
+  float norm_eps;
+  /* AutoencoderKL decoder */
+  int32_t vae_num_levels;
+  int32_t vae_block_out_channels[4];
+  int32_t vae_layers_per_block;
+  int32_t vae_norm_num_groups;
+  int32_t vae_out_channels;
+  int32_t vae_scale;               /* 2^(vae_num_levels-1) = pipeline.vae_scale_factor */
+  float vae_scaling_factor;        /* 0.18215, hard-coded at stable_diffusion_pipeline.py:432 */
+  /* problem */
+  int32_t latent_h, latent_w;
+  int32_t frames;                  /* frames per sample call (the reference's batch_size) */
+  int32_t guidance;                /* 1: classifier-free guidance -> UNet batch 2*frames (P:414) */
+  int32_t max_steps;
+} sdw_engine_config;
+
+int sdw_engine_create(const sdw_engine_config* cfg, sdw_engine** out);
+void sdw_engine_destroy(sdw_engine* e);
+int sdw_engine_arena_bytes(const sdw_engine* e, uint64_t* bytes);
+int sdw_engine_bind(sdw_engine* e, void* arena, uint64_t bytes);
+int sdw_engine_num_params(const sdw_engine* e);
+int sdw_engine_param_info(const sdw_engine* e, int index, const char** name, int64_t* numel);
+/* src: fp16 device tensor in the checkpoint's own layout (OIHW conv / [out,in] linear / vectors) */
+int sdw_engine_load_param(sdw_engine* e, const char* name, const void* src_f16, int64_t numel, void* stream);
+int sdw_engine_missing_params(const sdw_engine* e, const char** first_missing);
+/* timesteps: host fp32 [n_steps]; coefs: host [n_steps] */
+int sdw_engine_set_schedule(sdw_engine* e, int n_steps, const float* timesteps, const sdw_step_coef* coefs,
+                            float init_noise_sigma, float first_in_scale, void* stream);
+/* latents fp32 [F][4][h][w] (already interpolated, unscaled), cond fp16 [F][tokens][D], uncond fp16 [1][tokens][D]
+ * -> out_u8 [F][8h][8w][3] uint8 NHWC; out_latents (optional) fp32 [F][4][h][w] final latents. */
+int sdw_engine_sample(sdw_engine* e, const float* latents_f32, const void* cond_f16, const void* uncond_f16,
+                      uint8_t* out_u8, float* out_latents, int use_graph, void* stream);
+int sdw_engine_launches(const sdw_engine* e, int* prologue, int* unet_per_step, int* vae);
+/* parity hooks: one UNet forward on an explicit [Bn] batch / one VAE decode */
+int sdw_engine_debug_unet(sdw_engine* e, const float* x_nchw, int step, const void* ctx_f16, float* eps_nhwc_out,
+                          void* stream);
+int sdw_engine_debug_vae(sdw_engine* e, const float* latents_nchw, uint8_t* out_u8, float* out_f32_nhwc, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Low-level tensor-core op (tests / tooling): one implicit GEMM on the tcgen05 kernel.

@@ -126,4 +126,24 @@ int latents_init(const void* latents, int is_f16, float sigma, float in_scale, f
                  int dup, int F, int C, int H, int W, cudaStream_t stream);
 int pack_weight(const void* w, int N, int C, int kh, int kw, int geglu, void* out, cudaStream_t stream);
 
+// ---------------------------------------------------------------------------
+// norm / softmax / small-channel layers (sdw_norm.cu)
+// ---------------------------------------------------------------------------
+int gn_chunks(int64_t P);
+int groupnorm(const __half* x, int64_t ldx, int B, int64_t P, int C, int G, const float* gamma, const float* beta,
+              float eps, int silu, __half* y, int64_t ldy, float2* partial_ws, cudaStream_t stream);
+int layernorm(const __half* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+              __half* y, int64_t ldy, cudaStream_t stream);
+int softmax_rows(__half* s, int64_t ld, int64_t rows, int n, cudaStream_t stream);
+int conv_in_small(const __half* x, int64_t ldx, int B, int H, int W, int Cin, const __half* w, const float* bias,
+                  int N, __half* y, int64_t ldy, cudaStream_t stream);
+int conv_out_small(const __half* x, int64_t ldx, int B, int H, int W, int C, const __half* w, const float* bias,
+                   int nout, float* out_f32, uint8_t* out_u8, cudaStream_t stream);
+int vae_in(const float* x, float inv_scale, const __half* w, const float* bias, int F, int C, int H, int W, __half* z,
+           cudaStream_t stream);
+int linear_f32(const float* in, int64_t ldi, const __half* w, const float* bias, int M, int N, int K, int silu_in,
+               int silu_out, float* out, int64_t ldo, cudaStream_t stream);
+int timestep_embed(const float* t, int n, int dim, int round_f16, float* out, cudaStream_t stream);
+int half_to_float(const __half* in, float* out, int64_t n, int geglu_N, cudaStream_t stream);
+
 }  // namespace sdw

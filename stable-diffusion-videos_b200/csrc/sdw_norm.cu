@@ -1,0 +1,538 @@
+// sdw_norm.cu — the HBM-bound layers between the tensor-core kernels (all fp32 math, fp16 NHWC I/O):
+//   GroupNorm(+SiLU), LayerNorm, row softmax, the tiny-channel direct convolutions (conv_in: 4 -> C,
+//   conv_out: C -> 4 / 3 with the VAE post-process fused), post_quant_conv, fp32 small linear layers
+//   (time-embedding MLP and the per-ResBlock time projections) and the sinusoidal timestep embedding.
+// Reference call sites: the layers inside `self.unet(...)` (stable_diffusion_pipeline.py:418) and
+// `self.vae.decode(...)` (:433); post-process = :435-438 + numpy_to_pil (:450).
+#include "sdw_internal.h"
+#include "sdw_ptx.cuh"
+
+namespace sdw {
+
+// =============================================================================================
+// GroupNorm: two deterministic kernels.
+//   gn_partial : grid (nchunks, B). Each block sums x and x^2 per group over its pixel chunk (all channels,
+//                coalesced 16-byte loads, fixed reduction order) -> partial[b][chunk][g] = (sum, sumsq).
+//   gn_apply   : grid (pixel tiles, B). Reduces the <=32 partials per group in a fixed order, then
+//                y = (x - mean) * rstd * gamma + beta (optionally SiLU), fp16 out.
+// =============================================================================================
+static constexpr int GN_MAX_CHUNKS = 32;
+static constexpr int GN_MAX_GROUPS = 64;
+
+// per-thread partials go to shared memory and are reduced in index order (bit-reproducible).
+__global__ void __launch_bounds__(256) gn_partial_det_kernel(const __half* __restrict__ x, int64_t ld, int C, int G,
+                                                             int64_t P, int pix_per_chunk,
+                                                             float2* __restrict__ part) {
+  extern __shared__ float sm[];  // [rows][C] sums then [rows][C] squares
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int cg = C / G;
+  const int vecs = C / 8;
+  const int rows = max(1, min(min(static_cast<int>(blockDim.x) / vecs, 16), 6144 / C));
+  const int64_t p0 = static_cast<int64_t>(chunk) * pix_per_chunk;
+  const int64_t p1 = min(P, p0 + pix_per_chunk);
+  const __half* xb = x + static_cast<int64_t>(b) * P * ld;
+  float* ssum = sm;
+  float* ssq = sm + rows * C;
+  for (int item = threadIdx.x; item < rows * vecs; item += blockDim.x) {
+    const int v = item % vecs, prow = item / vecs;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    for (int64_t p = p0 + prow; p < p1; p += rows) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xb + p * ld + v * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        s[2 * j] += f.x;
+        q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
+        s[2 * j + 1] += f.y;
+        q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ssum[prow * C + v * 8 + j] = s[j];
+      ssq[prow * C + v * 8 + j] = q[j];
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float a = 0.f, c = 0.f;
+    for (int r = 0; r < rows; ++r)
+      for (int j = 0; j < cg; ++j) {
+        a += ssum[r * C + g * cg + j];
+        c += ssq[r * C + g * cg + j];
+      }
+    part[(static_cast<int64_t>(b) * gridDim.x + chunk) * G + g] = make_float2(a, c);
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, int64_t ldx, int C, int G,
+                                                       int64_t P, int nchunks, const float2* __restrict__ part,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps, int silu,
+                                                       __half* __restrict__ y, int64_t ldy, int pix_per_block) {
+  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  const int b = blockIdx.y;
+  const int cg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float a = 0.f, c = 0.f;
+    for (int k = 0; k < nchunks; ++k) {
+      const float2 pr = part[(static_cast<int64_t>(b) * nchunks + k) * G + g];
+      a += pr.x;
+      c += pr.y;
+    }
+    const float n = static_cast<float>(P) * cg;
+    const float mean = a / n;
+    const float var = fmaxf(c / n - mean * mean, 0.f);
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int vecs = C / 8;
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * pix_per_block;
+  const int64_t p1 = min(P, p0 + pix_per_block);
+  const int64_t items = (p1 - p0) * vecs;
+  const __half* xb = x + static_cast<int64_t>(b) * P * ldx;
+  __half* yb = y + static_cast<int64_t>(b) * P * ldy;
+  for (int64_t it = threadIdx.x; it < items; it += blockDim.x) {
+    const int v = static_cast<int>(it % vecs);
+    const int64_t p = p0 + it / vecs;
+    const uint4 u = *reinterpret_cast<const uint4*>(xb + p * ldx + v * 8);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      o[2 * j] = f.x;
+      o[2 * j + 1] = f.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = v * 8 + j;
+      const int g = c / cg;
+      float t = (o[j] - s_mean[g]) * s_rstd[g] * __ldg(&gamma[c]) + __ldg(&beta[c]);
+      if (silu) t = silu_f(t);
+      o[j] = t;
+    }
+    uint4 w;
+    w.x = pack_h2(o[0], o[1]);
+    w.y = pack_h2(o[2], o[3]);
+    w.z = pack_h2(o[4], o[5]);
+    w.w = pack_h2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(yb + p * ldy + v * 8) = w;
+  }
+}
+
+int gn_chunks(int64_t P) {
+  int64_t n = P / 64;
+  if (n < 1) n = 1;
+  if (n > GN_MAX_CHUNKS) n = GN_MAX_CHUNKS;
+  return static_cast<int>(n);
+}
+
+int groupnorm(const __half* x, int64_t ldx, int B, int64_t P, int C, int G, const float* gamma, const float* beta,
+              float eps, int silu, __half* y, int64_t ldy, float2* partial_ws, cudaStream_t stream) {
+  SDW_REQUIRE(C % 8 == 0 && C % G == 0 && G <= GN_MAX_GROUPS, "GroupNorm: C % 8, C % G, G <= 64");
+  SDW_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, "GroupNorm: row pitch must be a multiple of 8");
+  const int nchunks = gn_chunks(P);
+  const int ppc = static_cast<int>((P + nchunks - 1) / nchunks);
+  const int vecs = C / 8;
+  const int rows = std::max(1, std::min(std::min(256 / vecs, 16), 6144 / C));
+  const size_t smem = static_cast<size_t>(2) * rows * C * sizeof(float);
+  SDW_REQUIRE(smem <= 48 * 1024, "GroupNorm: channel count too large for the stats kernel");
+  gn_partial_det_kernel<<<dim3(nchunks, B), 256, smem, stream>>>(x, ldx, C, G, P, ppc, partial_ws);
+  SDW_CUDA_OK(cudaGetLastError());
+  int ppb = static_cast<int>(std::max<int64_t>(1, 4096 / C));  // ~4K elements per block pass
+  ppb *= 8;
+  const unsigned tiles = static_cast<unsigned>((P + ppb - 1) / ppb);
+  gn_apply_kernel<<<dim3(tiles, B), 256, 0, stream>>>(x, ldx, C, G, P, nchunks, partial_ws, gamma, beta, eps, silu, y,
+                                                      ldy, ppb);
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// LayerNorm over the channel dim: one warp per token row, fp32 two-pass in registers.
+// =============================================================================================
+template <int MAXV>  // 16-byte vectors per lane
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int64_t ldx, int64_t rows,
+                                                        int C, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps,
+                                                        __half* __restrict__ y, int64_t ldy) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int vecs = C / 8;
+  float v[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < vecs) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + row * ldx + vi * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        v[i][2 * j] = f.x;
+        v[i][2 * j + 1] = f.y;
+        sum += f.x + f.y;
+      }
+    }
+  }
+  sum = warp_sum(sum);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < vecs) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+  }
+  sq = warp_sum(sq);
+  const float rstd = rsqrtf(sq / C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < vecs) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = vi * 8 + j;
+        o[j] = (v[i][j] - mean) * rstd * __ldg(&gamma[c]) + __ldg(&beta[c]);
+      }
+      uint4 w;
+      w.x = pack_h2(o[0], o[1]);
+      w.y = pack_h2(o[2], o[3]);
+      w.z = pack_h2(o[4], o[5]);
+      w.w = pack_h2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(y + row * ldy + vi * 8) = w;
+    }
+  }
+}
+
+int layernorm(const __half* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+              __half* y, int64_t ldy, cudaStream_t stream) {
+  SDW_REQUIRE(C % 8 == 0 && C <= 8 * 32 * 8, "LayerNorm: C % 8 == 0 and C <= 2048");
+  const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+  const int vecs = C / 8;
+  if (vecs <= 64)
+    layernorm_kernel<2><<<blocks, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, y, ldy);
+  else if (vecs <= 160)
+    layernorm_kernel<5><<<blocks, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, y, ldy);
+  else
+    layernorm_kernel<8><<<blocks, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, y, ldy);
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// row softmax in place (scores already scaled by the QK^T epilogue): one warp per row for n <= 1024,
+// one 256-thread block per row otherwise.  fp32 math, fp16 storage.
+// =============================================================================================
+__global__ void __launch_bounds__(256) softmax_warp_kernel(__half* __restrict__ s, int64_t ld, int64_t rows, int n) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  __half* r = s + row * ld;
+  float v[32];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + i * 32;
+    v[i] = c < n ? __half2float(r[c]) : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + i * 32;
+    v[i] = c < n ? __expf(v[i] - m) : 0.f;
+    sum += v[i];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + i * 32;
+    if (c < n) r[c] = __float2half_rn(v[i] * inv);
+  }
+}
+
+__global__ void __launch_bounds__(256) softmax_block_kernel(__half* __restrict__ s, int64_t ld, int n) {
+  __shared__ float red[32];
+  __half* r = s + static_cast<int64_t>(blockIdx.x) * ld;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) m = fmaxf(m, __half2float(r[c]));
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = lane < (blockDim.x >> 5) ? red[lane] : -INFINITY;
+  m = warp_max(m);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) sum += __expf(__half2float(r[c]) - m);
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) r[c] = __float2half_rn(__expf(__half2float(r[c]) - m) * inv);
+}
+
+int softmax_rows(__half* s, int64_t ld, int64_t rows, int n, cudaStream_t stream) {
+  SDW_REQUIRE(n > 0 && rows > 0, "softmax: empty");
+  if (n <= 1024)
+    softmax_warp_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(s, ld, rows, n);
+  else
+    softmax_block_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(s, ld, n);
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// conv_in: 3x3 pad 1, tiny Cin (4) -> N channels.  Block = N threads (one output channel each, weights in
+// registers), loops over a tile of pixels whose 3x3xCin patches sit in shared memory.
+// w layout: [N][Cin][3][3] fp16 (the checkpoint's OIHW), bias fp32.
+// =============================================================================================
+template <int CIN>
+__global__ void __launch_bounds__(1024) conv_in_kernel(const __half* __restrict__ x, int64_t ldx, int B, int H, int W,
+                                                       const __half* __restrict__ w, const float* __restrict__ bias,
+                                                       int N, __half* __restrict__ y, int64_t ldy,
+                                                       int pix_per_block) {
+  extern __shared__ float patch[];  // [pix_per_block][9*CIN]
+  const int64_t P = static_cast<int64_t>(B) * H * W;
+  const int64_t p0 = static_cast<int64_t>(blockIdx.x) * pix_per_block;
+  const int np = static_cast<int>(min(static_cast<int64_t>(pix_per_block), P - p0));
+  for (int i = threadIdx.x; i < np * 9 * CIN; i += blockDim.x) {
+    const int c = i % CIN;
+    const int tap = (i / CIN) % 9;
+    const int lp = i / (9 * CIN);
+    const int64_t p = p0 + lp;
+    const int xw = static_cast<int>(p % W), yh = static_cast<int>((p / W) % H);
+    const int64_t b = p / (static_cast<int64_t>(W) * H);
+    const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+    float v = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __half2float(x[((b * H + yy) * W + xx) * ldx + c]);
+    patch[lp * 9 * CIN + tap * CIN + c] = v;
+  }
+  __syncthreads();
+  const int n = threadIdx.x;
+  if (n >= N) return;
+  float wr[9 * CIN];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) wr[tap * CIN + c] = __half2float(w[(static_cast<int64_t>(n) * CIN + c) * 9 + tap]);
+  const float bn = bias ? bias[n] : 0.f;
+  for (int lp = 0; lp < np; ++lp) {
+    float acc = bn;
+#pragma unroll
+    for (int k = 0; k < 9 * CIN; ++k) acc = fmaf(patch[lp * 9 * CIN + k], wr[k], acc);
+    y[(p0 + lp) * ldy + n] = __float2half_rn(acc);
+  }
+}
+
+int conv_in_small(const __half* x, int64_t ldx, int B, int H, int W, int Cin, const __half* w, const float* bias,
+                  int N, __half* y, int64_t ldy, cudaStream_t stream) {
+  SDW_REQUIRE(Cin == 4, "conv_in: latent channel count must be 4");
+  SDW_REQUIRE(N <= 1024, "conv_in: N <= 1024");
+  const int ppb = 16;
+  const int64_t P = static_cast<int64_t>(B) * H * W;
+  const int threads = (N + 31) / 32 * 32;
+  conv_in_kernel<4><<<static_cast<unsigned>((P + ppb - 1) / ppb), threads, ppb * 36 * sizeof(float), stream>>>(
+      x, ldx, B, H, W, w, bias, N, y, ldy, ppb);
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// conv_out: 3x3 pad 1, C -> NOUT (<= 4) channels, one warp per output pixel; lanes split the channels.
+// Input is the already normalised + SiLU'd fp16 NHWC tensor.  w layout: OIHW fp16 [NOUT][C][3][3].
+//   out_f32  : fp32 NHWC [P][NOUT] (UNet eps)          — optional
+//   out_u8   : uint8 NHWC [P][NOUT] = round(clamp(v/2+0.5,0,1)*255) (VAE frame; P:435-438 + numpy_to_pil) — optional
+// =============================================================================================
+template <int NOUT>
+__global__ void __launch_bounds__(256) conv_out_kernel(const __half* __restrict__ x, int64_t ldx, int B, int H, int W,
+                                                       int C, const __half* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out_f32,
+                                                       uint8_t* __restrict__ out_u8) {
+  extern __shared__ __half ws[];  // [NOUT][9][C]
+  for (int i = threadIdx.x; i < NOUT * 9 * C; i += blockDim.x) {
+    const int c = i % C, tap = (i / C) % 9, n = i / (9 * C);
+    ws[i] = w[(static_cast<int64_t>(n) * C + c) * 9 + tap];
+  }
+  __syncthreads();
+  const int64_t P = static_cast<int64_t>(B) * H * W;
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * warps + (threadIdx.x >> 5); p < P;
+       p += static_cast<int64_t>(gridDim.x) * warps) {
+    const int xw = static_cast<int>(p % W), yh = static_cast<int>((p / W) % H);
+    const int64_t b = p / (static_cast<int64_t>(W) * H);
+    float acc[NOUT];
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) acc[n] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const __half* xp = x + ((b * H + yy) * W + xx) * ldx;
+      for (int c = lane * 2; c < C; c += 64) {
+        const float2 xv = __half22float2(*reinterpret_cast<const __half2*>(xp + c));
+#pragma unroll
+        for (int n = 0; n < NOUT; ++n) {
+          const float2 wv = __half22float2(*reinterpret_cast<const __half2*>(&ws[(n * 9 + tap) * C + c]));
+          acc[n] = fmaf(xv.x, wv.x, acc[n]);
+          acc[n] = fmaf(xv.y, wv.y, acc[n]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) acc[n] = warp_sum(acc[n]);
+    if (lane == 0) {
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n) {
+        const float v = acc[n] + (bias ? bias[n] : 0.f);
+        if (out_f32) out_f32[p * NOUT + n] = v;
+        if (out_u8) {
+          const float q = fminf(fmaxf(v * 0.5f + 0.5f, 0.f), 1.f);
+          out_u8[p * NOUT + n] = static_cast<uint8_t>(rintf(q * 255.f));
+        }
+      }
+    }
+  }
+}
+
+int conv_out_small(const __half* x, int64_t ldx, int B, int H, int W, int C, const __half* w, const float* bias,
+                   int nout, float* out_f32, uint8_t* out_u8, cudaStream_t stream) {
+  SDW_REQUIRE(nout == 3 || nout == 4, "conv_out: 3 or 4 output channels");
+  SDW_REQUIRE(C % 2 == 0, "conv_out: even channel count");
+  const int64_t P = static_cast<int64_t>(B) * H * W;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((P + 7) / 8, 148 * 8));
+  const size_t smem = static_cast<size_t>(nout) * 9 * C * sizeof(__half);
+  if (nout == 4)
+    conv_out_kernel<4><<<blocks, 256, smem, stream>>>(x, ldx, B, H, W, C, w, bias, out_f32, out_u8);
+  else
+    conv_out_kernel<3><<<blocks, 256, smem, stream>>>(x, ldx, B, H, W, C, w, bias, out_f32, out_u8);
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// VAE input: z = post_quant_conv(latents / scaling) ; latents fp32 NCHW [F][C][H][W] -> fp16 NHWC [F][H][W][C]
+// (stable_diffusion_pipeline.py:432 `1 / 0.18215 * latents`, then AutoencoderKL.decode's post_quant_conv 1x1)
+// =============================================================================================
+__global__ void vae_in_kernel(const float* __restrict__ x, float inv_scale, const __half* __restrict__ w,
+                              const float* __restrict__ bias, int F, int C, int H, int W, __half* __restrict__ z) {
+  const int64_t P = static_cast<int64_t>(F) * H * W;
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int64_t hw = static_cast<int64_t>(H) * W;
+  const int64_t f = p / hw, r = p % hw;
+  float in[8];
+  for (int c = 0; c < C; ++c) in[c] = x[(f * C + c) * hw + r] * inv_scale;
+  for (int n = 0; n < C; ++n) {
+    float acc = bias ? bias[n] : 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(in[c], __half2float(w[n * C + c]), acc);
+    z[p * C + n] = __float2half_rn(acc);
+  }
+}
+
+int vae_in(const float* x, float inv_scale, const __half* w, const float* bias, int F, int C, int H, int W, __half* z,
+           cudaStream_t stream) {
+  SDW_REQUIRE(C <= 8, "latent channels <= 8");
+  const int64_t P = static_cast<int64_t>(F) * H * W;
+  vae_in_kernel<<<static_cast<unsigned>((P + 255) / 256), 256, 0, stream>>>(x, inv_scale, w, bias, F, C, H, W, z);
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// fp32 small linear: out[m][n] = act_out( bias[n] + sum_k act_in(in[m][k]) * W[n][k] ), W fp16 [N][K].
+// One warp per output element.  Used for the time-embedding MLP and the 22 ResBlock time projections,
+// evaluated once per schedule for ALL timesteps (they depend on t only — SURVEY.md K8).
+// =============================================================================================
+__global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict__ in, int64_t ldi,
+                                                         const __half* __restrict__ w, const float* __restrict__ bias,
+                                                         int M, int N, int K, int silu_in, int silu_out,
+                                                         float* __restrict__ out, int64_t ldo) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (idx >= static_cast<int64_t>(M) * N) return;
+  const int m = static_cast<int>(idx / N), n = static_cast<int>(idx % N);
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float a = in[m * ldi + k];
+    if (silu_in) a = silu_f(a);
+    acc = fmaf(a, __half2float(w[static_cast<int64_t>(n) * K + k]), acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    acc += bias ? bias[n] : 0.f;
+    if (silu_out) acc = silu_f(acc);
+    out[m * ldo + n] = acc;
+  }
+}
+
+int linear_f32(const float* in, int64_t ldi, const __half* w, const float* bias, int M, int N, int K, int silu_in,
+               int silu_out, float* out, int64_t ldo, cudaStream_t stream) {
+  const int64_t total = static_cast<int64_t>(M) * N;
+  linear_f32_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, stream>>>(in, ldi, w, bias, M, N, K, silu_in,
+                                                                                 silu_out, out, ldo);
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// sinusoidal timestep embedding, flip_sin_to_cos = True, freq_shift = 0: out[s] = cat[cos(t f), sin(t f)]
+// rounded to fp16 like the reference's `.to(dtype=self.dtype)` cast before time_embedding.
+__global__ void timestep_embed_kernel(const float* __restrict__ t, int n, int dim, int round_f16,
+                                      float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * dim) return;
+  const int s = i / dim, j = i % dim;
+  const int half = dim / 2;
+  const int k = j % half;
+  const float freq = expf(-logf(10000.f) * static_cast<float>(k) / static_cast<float>(half));
+  const float a = t[s] * freq;
+  float v = j < half ? cosf(a) : sinf(a);
+  if (round_f16) v = __half2float(__float2half_rn(v));
+  out[i] = v;
+}
+
+int timestep_embed(const float* t, int n, int dim, int round_f16, float* out, cudaStream_t stream) {
+  timestep_embed_kernel<<<(n * dim + 255) / 256, 256, 0, stream>>>(t, n, dim, round_f16, out);
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// fp16 -> fp32 vector conversion (biases, norm affine parameters)
+__global__ void h2f_kernel(const __half* __restrict__ in, float* __restrict__ out, int64_t n, const int* perm_geglu,
+                           int N) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t src = i;
+  if (N > 0) {  // GEGLU bias interleave, same row permutation as pack_weight
+    const int r = static_cast<int>(i);
+    const int blk = r >> 6, within = r & 63;
+    src = within < 32 ? blk * 32 + within : N / 2 + blk * 32 + (within - 32);
+  }
+  out[i] = __half2float(in[src]);
+}
+
+int half_to_float(const __half* in, float* out, int64_t n, int geglu_N, cudaStream_t stream) {
+  h2f_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(in, out, n, nullptr, geglu_N);
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sdw
