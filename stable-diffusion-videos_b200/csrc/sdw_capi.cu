@@ -16,6 +16,7 @@ extern "C" {
 
 const char* sdw_last_error(void) { return sdw::last_error(); }
 int sdw_abi_version(void) { return SDW_ABI_VERSION; }
+void sdw_debug_plan_only(int on) { sdw::set_plan_only(on != 0); }
 
 int sdw_slerp_lerp_batch(const void* lat_a, const void* lat_b, const void* emb_a, const void* emb_b, const float* t,
                          int n_frames, int64_t n_lat, int64_t n_emb, int dtype_is_f16, float dot_threshold,

@@ -806,7 +806,7 @@ static int run_all(Engine* E, cudaStream_t st) {
 }
 
 int sdw_engine_sample(sdw_engine* e, const float* latents_f32, const void* cond_f16, const void* uncond_f16,
-                      uint8_t* out_u8, float* out_latents, int use_graph, void* stream) {
+                      uint8_t* out_u8, float* out_latents, float* out_raw_f32, int use_graph, void* stream) {
   Engine* E = reinterpret_cast<Engine*>(e);
   SDW_REQUIRE(E && latents_f32 && cond_f16 && out_u8, "null");
   SDW_REQUIRE(!E->dry && E->n_steps > 0, "engine not bound or schedule not set");
@@ -846,6 +846,8 @@ int sdw_engine_sample(sdw_engine* e, const float* latents_f32, const void* cond_
   const size_t out_bytes = static_cast<size_t>(F) * H * c.vae_scale * W * c.vae_scale * c.vae_out_channels;
   SDW_CUDA_OK(cudaMemcpyAsync(out_u8, E->out_u8, out_bytes, cudaMemcpyDeviceToDevice, st));
   if (out_latents) SDW_CUDA_OK(cudaMemcpyAsync(out_latents, E->x, nlat * 4, cudaMemcpyDeviceToDevice, st));
+  if (out_raw_f32)
+    SDW_CUDA_OK(cudaMemcpyAsync(out_raw_f32, E->out_img_f32, out_bytes * 4, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 

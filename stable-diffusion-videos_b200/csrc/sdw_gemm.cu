@@ -271,6 +271,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
 // host side
 // =============================================================================
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static bool g_plan_only = false;  // validate plans without a driver (CPU-side tests); nothing can be launched
+void set_plan_only(bool on) { g_plan_only = on; }
 
 template <int BN>
 static int set_attr() {
@@ -280,7 +282,7 @@ static int set_attr() {
 }
 
 int gemm_init() {
-  if (g_encode) return 0;
+  if (g_encode || g_plan_only) return 0;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   SDW_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -319,6 +321,13 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
     set_error("TMA global base must be 16-byte aligned");
     return 1;
   }
+  for (int i = 0; i < rank; ++i) {
+    if (bx[i] == 0 || bx[i] > 256 || gdim[i] == 0) {
+      set_error("TMA box dims must be in 1..256 and tensor dims non-zero");
+      return 1;
+    }
+  }
+  if (g_plan_only) return 0;
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstride, bx, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -338,7 +347,6 @@ static int pow2_floor(int v) {
 int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
   SDW_REQUIRE(d.A && d.Wt && d.out, "null operand");
   SDW_REQUIRE(d.C > 0 && d.W > 0 && d.H > 0 && d.B > 0 && d.N > 0, "empty problem");
-  SDW_REQUIRE(d.C % 8 == 0, "channel count must be a multiple of 8 (TMA 16-byte rows)");
   GemmKParams& p = L->p;
   std::memset(&p, 0, sizeof(p));
   const int kchunks = (d.C + BK - 1) / BK;

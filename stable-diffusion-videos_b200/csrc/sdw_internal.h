@@ -110,6 +110,7 @@ struct GemmDesc {
 
 int plan_gemm(const GemmDesc& d, GemmLaunch* out);
 int launch_gemm(const GemmLaunch& l, cudaStream_t stream);
+void set_plan_only(bool on);
 int gemm_init();  // resolves the driver entry point, sets smem attributes
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                const uint32_t* box);

@@ -152,7 +152,7 @@ class Engine:
         return a.value, b.value, c.value
 
     # ------------------------------------------------------------------------------------------
-    def sample(self, latents, cond, uncond=None, use_graph=True, return_latents=False):
+    def sample(self, latents, cond, uncond=None, use_graph=True, return_latents=False, return_raw=False):
         """latents [F,4,h,w] (any float dtype), cond [F,tokens,D], uncond [1,tokens,D] -> uint8 [F,8h,8w,3] (CUDA)."""
         F = self.frames
         h, w = self.latent_hw
@@ -166,9 +166,12 @@ class Engine:
         out = torch.empty((F, h * self.vae_scale, w * self.vae_scale, self.vae_cfg.out_channels), dtype=torch.uint8,
                           device=self.device)
         fin = torch.empty_like(lat) if return_latents else None
+        raw = torch.empty(out.shape, dtype=torch.float32, device=self.device) if return_raw else None
         with torch.cuda.device(self.device):
             N.check(N.lib().sdw_engine_sample(self._h, N.ptr(lat), N.ptr(cnd), N.ptr(unc), N.ptr(out), N.ptr(fin),
-                                              int(use_graph), N.stream_ptr()))
+                                              N.ptr(raw), int(use_graph), N.stream_ptr()))
+        if return_raw:
+            return out, raw
         return (out, fin) if return_latents else out
 
     def debug_unet(self, x_nchw, step, ctx):
