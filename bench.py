@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py — frames/sec of the latent-walk hot path (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus 1 --steps K --warmup W             native arm (libsdwalk.so)
+  python bench.py --impl reference ...                       the reference's CPU path (oracle restatement), rank 0
+  torchrun --nproc-per-node N bench.py --gpus N ...          one rank per GPU, frames sharded, NCCL gather
+
+Workload (config.workload): BASELINE.json configs[1] — SD-1.4 architecture, 512x512, fp16, PNDM 50 steps
+(51 UNet calls), classifier-free guidance 7.5, frames interpolated between 2 synthetic prompts; random-init weights
+and synthetic prompt embeddings (no network).  A *step* = one sample call of F frames through
+slerp/lerp inputs -> 51 x {UNet, CFG, scheduler step} -> VAE decode -> uint8 frames.  Frames are independent and
+cost-identical, so frames/s on K*F frames is the throughput of the 60-frame clip.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_FRAME = {"sd14": 2 * 51 * 0.8033e12 + 2.5145e12}  # SURVEY.md §8d algorithmic FLOPs (84.45 T)
+UNET_FLOP_B1 = 0.8033e12
+VAE_FLOP = 2.5145e12
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1440.7), d.get("hbm_gbs", 6564.5), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = max((int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=0)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_leg(steps, warmup, threads=None):
+    """time the oracle (restated diffusers CPU path, fp32) on a bounded sample: `steps` batch-2 UNet forwards at the
+    64x64 latent + ONE VAE decode; frame time = 51 * t_unet + t_vae (frames are cost-identical)."""
+    import torch
+
+    from oracle.unet import UNet2DConditionModel, UNetConfig
+    from oracle.vae import AutoencoderKLDecoder, VAEConfig
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel(UNetConfig.sd14()).eval()
+    vae = AutoencoderKLDecoder(VAEConfig()).eval()
+    x = torch.randn(2, 4, 64, 64)
+    ctx = torch.randn(2, 77, 768)
+    z = torch.randn(1, 4, 64, 64)
+    with torch.no_grad():
+        for _ in range(max(1, warmup)):
+            unet(x, torch.tensor(981), ctx)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            unet(x, torch.tensor(981), ctx)
+        t_unet = (time.perf_counter() - t0) / steps
+        t0 = time.perf_counter()
+        vae.decode(z)
+        t_vae = time.perf_counter() - t0
+    spf = 51 * t_unet + t_vae
+    return {"value": 1.0 / spf, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} timed batch-2 UNet forwards (64x64 latent, fp32) + 1 VAE decode on {threads} threads; "
+                      f"s/frame = 51*{t_unet:.3f} + {t_vae:.3f} = {spf:.1f}",
+            "s_per_frame": spf, "t_unet_s": t_unet, "t_vae_s": t_vae}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--frames-per-call", type=int, default=int(os.environ.get("SDW_BENCH_F", "4")))
+    ap.add_argument("--inference-steps", type=int, default=50)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = ("SD-1.4 UNet+VAE, 512x512, fp16, PNDM 50 steps (51 UNet calls), CFG 7.5, 2 prompts x 60 interp "
+                "frames (BASELINE configs[1]); random-init weights, synthetic embeddings")
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        leg = cpu_reference_leg(max(1, a.steps), a.warmup)
+        print(json.dumps({
+            "impl": "reference", "metric": "frames/sec at 512x512 50-step SD-1.4", "value": leg["value"],
+            "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": leg["t_unet_s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": workload, "reference_arm": leg["sample"]},
+            "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": leg["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from stable_diffusion_videos_b200 import _native
+    from stable_diffusion_videos_b200.configs import UNetConfig, VAEConfig
+    from stable_diffusion_videos_b200.parallel import broadcast_state_dict, gather_frames, init_distributed
+    from stable_diffusion_videos_b200.pipeline import StableDiffusionWalkPipeline
+
+    rank, world, local = init_distributed()
+    assert world == a.gpus or world == 1, f"--gpus {a.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    F, K, W = a.frames_per_call, a.steps, a.warmup
+
+    # ---- model: random-init SD-1.4; rank 0 generates, one NCCL broadcast ships the weights -------------------
+    from stable_diffusion_videos_b200.configs import random_state_dict, unet_param_shapes, vae_param_shapes
+    from stable_diffusion_videos_b200.pipeline import NativeUNet, NativeVAE, SyntheticTextEncoder, SyntheticTokenizer
+    from stable_diffusion_videos_b200.schedulers import PNDMScheduler
+
+    ucfg, vcfg = UNetConfig.sd14(), VAEConfig()
+    if rank == 0 or world == 1:
+        usd = {k: v.to(dev) for k, v in random_state_dict(unet_param_shapes(ucfg), 0).items()}
+        vsd = {k: v.to(dev) for k, v in random_state_dict(vae_param_shapes(vcfg), 1).items()}
+    else:
+        usd = {k: torch.empty(s, dtype=torch.float16, device=dev) for k, s in unet_param_shapes(ucfg).items()}
+        vsd = {k: torch.empty(s, dtype=torch.float16, device=dev) for k, s in vae_param_shapes(vcfg).items()}
+    usd, vsd = broadcast_state_dict(usd), broadcast_state_dict(vsd)
+    pipe = StableDiffusionWalkPipeline(NativeVAE(vcfg, vsd), SyntheticTextEncoder(768), SyntheticTokenizer(),
+                                       NativeUNet(ucfg, usd), PNDMScheduler()).to(dev)
+    h = w = 64
+    eng = pipe._engine(h, w, F, True)
+    del usd, vsd
+    pipe.unet.state, pipe.vae.state = None, None
+    eng.set_scheduler(pipe.scheduler, a.inference_steps, 7.5)
+    eng._plan_key = (type(pipe.scheduler).__name__, a.inference_steps, 7.5)
+    n_unet_calls = eng.n_steps
+
+    # ---- inputs: one clip's worth of interpolated (embedding, latent) pairs, resident on the device ------------
+    n_clip = max(F * (K + W), 60)
+    ea, eb = pipe.embed_text("0"), pipe.embed_text("1")
+    la, lb = pipe.init_noise(42, (1, 4, h, w), ea.dtype), pipe.init_noise(1337, (1, 4, h, w), ea.dtype)
+    T = torch.linspace(0, 1, n_clip, device=dev)
+    lat_all, emb_all = _native.slerp_lerp_batch(la, lb, ea, eb, T)
+    unc = pipe._uncond([""])
+    # per-rank offset so ranks render different frames (weak scaling: per-GPU work fixed)
+    def batch(i):
+        j = ((rank * 7 + i) * F) % (n_clip - F + 1)
+        return lat_all[j:j + F], emb_all[j:j + F]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_step(i, gather=True):
+        lat, emb = batch(i)
+        u8 = eng.sample(lat, emb, unc, use_graph=not a.no_graph)
+        if world > 1 and gather:
+            gather_frames(u8, F * world)  # decoded frames to rank 0 over NCCL
+        return u8
+
+    for i in range(W):
+        run_step(i)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(K):
+        run_step(W + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    clk = clocks.stop() if rank == 0 else None
+    frames_total = K * F * world
+    value = frames_total / (ms / 1e3)
+
+    # ---- e2e: the public call (pipeline.__call__) with HOST inputs: H2D of latents+embeddings, D2H of frames ------
+    lat_h = [batch(i)[0].cpu().pin_memory() for i in range(K + 1)]
+    emb_h = [batch(i)[1].cpu().pin_memory() for i in range(K + 1)]
+    pipe(latents=lat_h[K], text_embeddings=emb_h[K], num_inference_steps=a.inference_steps, guidance_scale=7.5, output_type="pil")
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        out = pipe(latents=lat_h[i], text_embeddings=emb_h[i], num_inference_steps=a.inference_steps,
+                   guidance_scale=7.5, output_type="pil")
+        assert len(out["images"]) == F
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_val = frames_total / e2e_s
+    h2d = F * (4 * h * w + 77 * 768) * 2
+    d2h = F * 512 * 512 * 3
+
+    if rank != 0:
+        return
+    peak_tf, peak_gbs, peak_src = _peaks()
+    achieved_tf = value * FLOP_PER_FRAME["sd14"] / 1e12 / world
+    pro, per_step, vae_l = eng.launches()
+    launches_per_call = pro + 1 + n_unet_calls * (per_step + 1) + vae_l
+    res = {
+        "metric": "frames/sec at 512x512 50-step SD-1.4", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": workload, "frames_per_step": F, "unet_calls_per_frame": n_unet_calls,
+                   "unet_batch": 2 * F, "parallelism": f"frame-dp{world}", "cuda_graph": not a.no_graph,
+                   "l2": "working set per step (1.8 GB weights + activations) exceeds the 126 MB L2"},
+        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved_tf / peak_tf, "traffic": None,
+                     "note": f"whole sampler: frames x 84.45 TFLOP / time / gpus, vs {peak_src} sustained bf16/fp16 peak"},
+        "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches_per_call * K,
+        "clocks": clk,
+    }
+    if not a.no_cpu_baseline and world == 1:
+        res["cpu_baseline"] = {k: v for k, v in cpu_reference_leg(2, 1).items()
+                               if k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -129,7 +129,8 @@ int sdw_engine_set_schedule(sdw_engine* e, int n_steps, const float* timesteps, 
  * -> out_u8 [F][8h][8w][3] uint8 NHWC; out_latents (optional) fp32 [F][4][h][w] final latents. */
 int sdw_engine_sample(sdw_engine* e, const float* latents_f32, const void* cond_f16, const void* uncond_f16,
                       uint8_t* out_u8, float* out_latents, float* out_raw_f32, int use_graph, void* stream);
-/* out_raw_f32 (optional): fp32 [F][8h][8w][3] decoder output BEFORE (x/2+0.5).clamp(0,1) — the float image of P:435 */
+/* use_graph = 1 captures the whole call into a CUDA graph on first use: `stream` must then be a real stream, not
+ * the legacy default stream 0.  out_raw_f32 (optional): fp32 [F][8h][8w][3] decoder output BEFORE (x/2+0.5).clamp(0,1) — the float image of P:435 */
 int sdw_engine_launches(const sdw_engine* e, int* prologue, int* unet_per_step, int* vae);
 /* parity hooks: one UNet forward on an explicit [Bn] batch / one VAE decode */
 int sdw_engine_debug_unet(sdw_engine* e, const float* x_nchw, int step, const void* ctx_f16, float* eps_nhwc_out,

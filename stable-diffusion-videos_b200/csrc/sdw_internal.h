@@ -19,6 +19,7 @@ const char* last_error();
   do {                                                                                         \
     cudaError_t _e = (expr);                                                                   \
     if (_e != cudaSuccess) {                                                                   \
+      (void)cudaGetLastError(); /* do not leave the error latched for the caller's next CUDA call */ \
       ::sdw::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
       return 2;                                                                                \
     }                                                                                          \

@@ -71,6 +71,8 @@ class Engine:
             N.check(lib.sdw_engine_bind(self._h, C.c_void_p(base), C.c_uint64(self.arena_bytes)))
         self.n_steps = 0
         self._plan_key = None
+        # graph capture is illegal on the legacy default stream: the engine runs on its own stream, fenced both ways
+        self._stream = torch.cuda.Stream(device=self.device)
 
     def __del__(self):
         try:
@@ -168,8 +170,12 @@ class Engine:
         fin = torch.empty_like(lat) if return_latents else None
         raw = torch.empty(out.shape, dtype=torch.float32, device=self.device) if return_raw else None
         with torch.cuda.device(self.device):
-            N.check(N.lib().sdw_engine_sample(self._h, N.ptr(lat), N.ptr(cnd), N.ptr(unc), N.ptr(out), N.ptr(fin),
-                                              N.ptr(raw), int(use_graph), N.stream_ptr()))
+            cur = torch.cuda.current_stream()
+            self._stream.wait_stream(cur)
+            with torch.cuda.stream(self._stream):
+                N.check(N.lib().sdw_engine_sample(self._h, N.ptr(lat), N.ptr(cnd), N.ptr(unc), N.ptr(out), N.ptr(fin),
+                                                  N.ptr(raw), int(use_graph), N.stream_ptr()))
+            cur.wait_stream(self._stream)
         if return_raw:
             return out, raw
         return (out, fin) if return_latents else out

@@ -1,0 +1,77 @@
+"""Frame-level data parallelism: one process per GPU, frames of a clip split into contiguous
+per-rank blocks, weights broadcast once, decoded uint8 frames gathered to rank 0 over NCCL (NVLink / NVSwitch).
+
+The reference's torch path is single-device; its only multi-device precedent is the Flax twin's `pmap` over the
+frame axis with padding (flax_stable_diffusion_pipeline.py:546, 568-578, 594-597, 898-902) — a pure map with no
+collective inside, which is what this is.  Works with the `gloo` backend on CPU tensors (tests) and `nccl` on GPU.
+"""
+import math
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def frame_block(n, world, rank):
+    """contiguous block [lo, hi) of rank `rank` out of n frames (ceil split; trailing ranks may get fewer / none)."""
+    per = math.ceil(n / world) if n > 0 else 0
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def init_distributed():
+    """(rank, world, local_rank) from the torchrun environment; initialises the process group when WORLD_SIZE > 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def broadcast_state_dict(sd, src=0):
+    """broadcast every tensor of a state dict from `src` as ONE flat fp16 buffer (1.8 GB for SD-1.4: one NCCL call)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return sd
+    names = sorted(sd)
+    dev = sd[names[0]].device
+    flat = torch.cat([sd[k].reshape(-1).to(torch.float16) for k in names])
+    dist.broadcast(flat, src=src)
+    out, off = {}, 0
+    for k in names:
+        n = sd[k].numel()
+        out[k] = flat[off:off + n].view(sd[k].shape).to(dev)
+        off += n
+    return out
+
+
+def gather_frames(local_frames, n_total, dst=0):
+    """gather per-rank uint8 frame blocks [k_r, H, W, 3] (contiguous frame_block split of n_total) to rank `dst`.
+
+    Returns the [n_total, H, W, 3] tensor on `dst`, None elsewhere.  Uniform collective: every rank pads its block
+    to ceil(n_total / world) frames, one all_gather_into_tensor (NCCL) / all_gather (gloo), trim on dst."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local_frames
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per = math.ceil(n_total / world)
+    shape = tuple(local_frames.shape[1:])
+    buf = torch.zeros((per,) + shape, dtype=local_frames.dtype, device=local_frames.device)
+    buf[: local_frames.shape[0]] = local_frames
+    if local_frames.is_cuda:
+        out = torch.empty((world * per,) + shape, dtype=buf.dtype, device=buf.device)
+        dist.all_gather_into_tensor(out, buf)
+    else:
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf)
+        out = torch.cat(parts)
+    if rank != dst:
+        return None
+    keep = []
+    for r in range(world):
+        lo, hi = frame_block(n_total, world, r)
+        keep.append(out[r * per: r * per + (hi - lo)])
+    return torch.cat(keep)
