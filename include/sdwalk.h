@@ -171,6 +171,12 @@ typedef struct sdw_gemm_desc {
 
 int sdw_gemm(const sdw_gemm_desc* desc, void* stream);
 
+/* fused attention on tcgen05 (tests / tooling): O = softmax(Q K^T d^-1/2) V per (batch, head).
+ * q [B][Nq][q_ld], k [B][Nk][k_ld] with head h at columns h*d; vt [B][heads][d][vt_ld] = V transposed;
+ * out [B][Nq][out_ld]; all fp16; d a multiple of 8 in 8..160. */
+int sdw_attention(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* vt, int64_t vt_ld, int B,
+                  int Nq, int Nk, int heads, int d, void* out, int64_t out_ld, void* stream);
+
 /* pack an OIHW fp16 conv / [N][K] linear weight into the kernel's K-major [N][taps][Cp] layout */
 int sdw_pack_weight(const void* w_oihw, int N, int C, int kh, int kw, int geglu_interleave, void* out, void* stream);
 

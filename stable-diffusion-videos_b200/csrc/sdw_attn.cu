@@ -1,0 +1,378 @@
+// sdw_attn.cu — fused (flash) attention on tcgen05 for the UNet's self- and cross-attention
+// (the SDPA inside `BasicTransformerBlock`, reached from stable_diffusion_pipeline.py:418).
+//
+//   O[b, q, h*d:(h+1)*d] = softmax(Q_h K_h^T * d^-1/2) V_h          per (batch b, head h), fp16 in / fp16 out
+//
+// One CTA = one 128-query tile of one (b, h).  Nothing but Q, K, V^T tiles and the O tile touches HBM:
+//   warp 0    : TMA producer.  Q tile once; per KV tile a K box [BKV x dk] and a V^T box [dv x BKV]
+//               (SWIZZLE_128B, head dim zero-filled up to 64*DKA by TMA OOB) into a STAGES-deep ring.
+//   warp 1    : MMA issuer.  S_j = Q K_j^T  (M=128, N=BKV, fp32 in TMEM, double-buffered) and
+//               O += P_j V_j (A = P_j fp16 from shared memory, N = DVP, fp32 in TMEM).
+//   warps 2-5 : online softmax, thread = query row.  tcgen05.ld S_j, running max / sum in fp32
+//               (ex2.approx on pre-scaled scores), rescale O in TMEM only when a row max moved,
+//               write P_j to shared memory in the UMMA K-major 128B-swizzled layout, finally O / l -> fp16.
+// Ordering is carried by mbarriers only (s_full, p_ready, pv_done, kv_full/empty).
+#include "sdw_internal.h"
+#include "sdw_ptx.cuh"
+
+#include <cmath>
+#include <cstring>
+
+namespace sdw {
+
+static constexpr int ATT_THREADS = 192;
+static constexpr int ATT_BQ = 128;
+
+struct alignas(64) AttnKParams {
+  CUtensorMap mapQ, mapK, mapV;
+  int Nq, Nk, d, heads;
+  int dk_steps;          // ceil(d / 16)
+  float scale_log2e;     // d^-1/2 * log2(e)
+  __half* out;
+  int64_t out_ld;
+};
+
+template <int DKA, int DVP, int BKV, int ST>
+struct AttnCfg {
+  static constexpr int Q_BYTES = DKA * ATT_BQ * 128;
+  static constexpr int K_STAGE = DKA * BKV * 128;
+  static constexpr int V_STAGE = (BKV / 64) * DVP * 128;
+  static constexpr int P_BYTES = (BKV / 64) * ATT_BQ * 128;
+  static constexpr int SMEM = Q_BYTES + P_BYTES + ST * (K_STAGE + V_STAGE) + 1024 + 256;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int O_COL = 2 * BKV;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int DKA, int DVP, int BKV, int ST>
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnKParams p) {
+  using Cfg = AttnCfg<DKA, DVP, BKV, ST>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* p_smem = q_smem + Cfg::Q_BYTES;
+  uint8_t* k_smem = p_smem + Cfg::P_BYTES;
+  uint8_t* v_smem = k_smem + ST * Cfg::K_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + ST * Cfg::V_STAGE);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + ST;
+  uint64_t* s_full = kv_empty + ST;  // [2]
+  uint64_t* p_ready = s_full + 2;
+  uint64_t* pv_done = p_ready + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int ntiles = (p.Nk + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.mapQ);
+    tma_prefetch_desc(&p.mapK);
+    tma_prefetch_desc(&p.mapV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(p_ready, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int a = 0; a < DKA; ++a) tma_load_4d(&p.mapQ, q_full, q_smem + a * (ATT_BQ * 128), a * 64, q0, head, b);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % ST;
+        mbar_wait(&kv_empty[s], ((j / ST) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], Cfg::K_STAGE + Cfg::V_STAGE);
+        const int kv0 = j * BKV;
+#pragma unroll
+        for (int a = 0; a < DKA; ++a)
+          tma_load_4d(&p.mapK, &kv_full[s], k_smem + s * Cfg::K_STAGE + a * (BKV * 128), a * 64, kv0, head, b);
+#pragma unroll
+        for (int a = 0; a < BKV / 64; ++a)
+          tma_load_4d(&p.mapV, &kv_full[s], v_smem + s * Cfg::V_STAGE + a * (DVP * 128), kv0 + a * 64, 0, head, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_f16(ATT_BQ, BKV);
+      constexpr uint32_t idesc_o = make_idesc_f16(ATT_BQ, DVP);
+      const uint32_t q_addr = smem_u32(q_smem);
+      const uint32_t p_addr = smem_u32(p_smem);
+      auto issue_s = [&](int j) {
+        const int s = j % ST;
+        mbar_wait(&kv_full[s], (j / ST) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(k_smem + s * Cfg::K_STAGE);
+        const uint32_t ts = tmem + (j & 1) * BKV;
+        for (int ks = 0; ks < p.dk_steps; ++ks) {
+          const uint64_t da = make_desc_k_sw128(q_addr + (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32);
+          const uint64_t db = make_desc_k_sw128(k_addr + (ks >> 2) * (BKV * 128) + (ks & 3) * 32);
+          umma_f16_ss(ts, da, db, idesc_s, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      if (ntiles > 1) issue_s(1);
+      for (int j = 0; j < ntiles; ++j) {
+        mbar_wait(p_ready, j & 1);
+        tc_fence_after();
+        const int s = j % ST;
+        const uint32_t v_addr = smem_u32(v_smem + s * Cfg::V_STAGE);
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          const uint64_t da = make_desc_k_sw128(p_addr + (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32);
+          const uint64_t db = make_desc_k_sw128(v_addr + (ks >> 2) * (DVP * 128) + (ks & 3) * 32);
+          umma_f16_ss(tmem + Cfg::O_COL, da, db, idesc_o, (j | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(pv_done);
+        umma_commit(&kv_empty[s]);
+        if (j + 2 < ntiles) issue_s(j + 2);
+      }
+    }
+  } else {
+    // ============================ softmax / correction / epilogue ============================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_o = tmem + lane_base + Cfg::O_COL;
+    float m_run = -INFINITY, l_run = 0.f;
+    const float sl2 = p.scale_log2e;
+    uint8_t* p_row = p_smem + r * 128;
+    const int sw = r & 7;
+
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_s = tmem + lane_base + (j & 1) * BKV;
+      float v[BKV];
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t tmp[32];
+        tmem_ld_32x32(t_s + c * 32, tmp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[c * 32 + i] = __uint_as_float(tmp[i]);
+      }
+      const int kv0 = j * BKV;
+      if (kv0 + BKV > p.Nk) {
+#pragma unroll
+        for (int i = 0; i < BKV; ++i)
+          if (kv0 + i >= p.Nk) v[i] = -INFINITY;
+      }
+      float m_t = v[0];
+#pragma unroll
+      for (int i = 1; i < BKV; ++i) m_t = fmaxf(m_t, v[i]);
+      const float m_new = fmaxf(m_run, m_t);
+      const float alpha = ex2f((m_run - m_new) * sl2);
+      const float mb = m_new * sl2;
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < BKV; ++i) {
+        v[i] = ex2f(fmaf(v[i], sl2, -mb));
+        sum += v[i];
+      }
+      l_run = fmaf(l_run, alpha, sum);
+      m_run = m_new;
+      if (j > 0) {
+        // P smem and the O accumulator are free once PV_{j-1} has completed
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+          for (int c = 0; c < DVP / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_32x16(t_o + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x16(t_o + c * 16, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // P_j -> shared memory, K-major SWIZZLE_128B: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
+#pragma unroll
+      for (int c8 = 0; c8 < BKV / 8; ++c8) {
+        uint4 u;
+        u.x = pack_h2(v[c8 * 8 + 0], v[c8 * 8 + 1]);
+        u.y = pack_h2(v[c8 * 8 + 2], v[c8 * 8 + 3]);
+        u.z = pack_h2(v[c8 * 8 + 4], v[c8 * 8 + 5]);
+        u.w = pack_h2(v[c8 * 8 + 6], v[c8 * 8 + 7]);
+        *reinterpret_cast<uint4*>(p_row + (c8 >> 3) * (ATT_BQ * 128) + (((c8 & 7) ^ sw) << 4)) = u;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+    }
+    // ---- epilogue: O / l -> fp16 ------------------------------------------------------------
+    mbar_wait(pv_done, (ntiles - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l_run;
+    const int row = q0 + r;
+    __half* orow = p.out + (static_cast<int64_t>(b) * p.Nq + row) * p.out_ld + head * p.d;
+    const bool vec_ok = ((p.out_ld & 7) == 0) && ((p.d & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+#pragma unroll
+    for (int c = 0; c < DVP / 16; ++c) {
+      uint32_t o[16];
+      tmem_ld_32x16(t_o + c * 16, o);
+      tmem_ld_wait();
+      if (row < p.Nq) {
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          const int dd = c * 16 + h8 * 8;
+          if (dd >= p.d) break;
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[h8 * 8 + i]) * inv_l;
+          if (vec_ok && dd + 8 <= p.d) {
+            uint4 u;
+            u.x = pack_h2(f[0], f[1]);
+            u.y = pack_h2(f[2], f[3]);
+            u.z = pack_h2(f[4], f[5]);
+            u.w = pack_h2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(orow + dd) = u;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (dd + i < p.d) orow[dd + i] = __float2half_rn(f[i]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, Cfg::TMEM_COLS);
+  }
+}
+
+// =============================================================================================
+// host
+// =============================================================================================
+struct AttnLaunchImpl {
+  AttnKParams p;
+  dim3 grid;
+  int variant;
+};
+
+template <int DKA, int DVP, int BKV, int ST>
+static int attn_set_attr() {
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<DKA, DVP, BKV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   AttnCfg<DKA, DVP, BKV, ST>::SMEM));
+  return 0;
+}
+
+static bool g_attn_init = false;
+static int attn_init() {
+  if (g_attn_init) return 0;
+  if (int e = attn_set_attr<1, 16, 128, 2>()) return e;
+  if (int e = attn_set_attr<1, 32, 128, 2>()) return e;
+  if (int e = attn_set_attr<1, 48, 128, 2>()) return e;
+  if (int e = attn_set_attr<1, 64, 128, 2>()) return e;
+  if (int e = attn_set_attr<2, 80, 128, 2>()) return e;
+  if (int e = attn_set_attr<3, 160, 64, 3>()) return e;
+  g_attn_init = true;
+  return 0;
+}
+
+bool attn_supported(int d) { return d % 8 == 0 && d >= 8 && d <= 160; }
+
+static int variant_for(int d) {
+  if (d <= 16) return 0;
+  if (d <= 32) return 1;
+  if (d <= 48) return 2;
+  if (d <= 64) return 3;
+  if (d <= 80) return 4;
+  return 5;
+}
+
+int plan_attention(const AttnDesc& a, AttnLaunch* L) {
+  SDW_REQUIRE(attn_supported(a.d), "flash attention supports head dims 8..160 (multiples of 8)");
+  SDW_REQUIRE(a.q && a.k && a.vt && a.out, "null operand");
+  SDW_REQUIRE(a.Nq > 0 && a.Nk > 0 && a.heads > 0 && a.B > 0, "empty attention");
+  static_assert(sizeof(AttnLaunchImpl) <= sizeof(AttnLaunch::storage), "AttnLaunch storage too small");
+  AttnLaunchImpl* I = reinterpret_cast<AttnLaunchImpl*>(L->storage);
+  std::memset(I, 0, sizeof(*I));
+  I->variant = variant_for(a.d);
+  const int bkv = I->variant == 5 ? 64 : 128;
+  const int dvp_tab[6] = {16, 32, 48, 64, 80, 160};
+  const int dvp = dvp_tab[I->variant];
+  AttnKParams& p = I->p;
+  p.Nq = a.Nq; p.Nk = a.Nk; p.d = a.d; p.heads = a.heads;
+  p.dk_steps = (a.d + 15) / 16;
+  p.scale_log2e = (1.f / std::sqrt(static_cast<float>(a.d))) * 1.4426950408889634f;
+  p.out = a.out; p.out_ld = a.out_ld;
+  I->grid = dim3((a.Nq + ATT_BQ - 1) / ATT_BQ, a.heads, a.B);
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(a.d), static_cast<uint64_t>(a.Nq), static_cast<uint64_t>(a.heads),
+                        static_cast<uint64_t>(a.B)};
+    uint64_t str[4] = {1, static_cast<uint64_t>(a.q_ld), static_cast<uint64_t>(a.d),
+                       static_cast<uint64_t>(a.Nq) * a.q_ld};
+    uint32_t box[4] = {64, ATT_BQ, 1, 1};
+    if (int e = encode_map(&p.mapQ, a.q, 4, dims, str, box)) return e;
+  }
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(a.d), static_cast<uint64_t>(a.Nk), static_cast<uint64_t>(a.heads),
+                        static_cast<uint64_t>(a.B)};
+    uint64_t str[4] = {1, static_cast<uint64_t>(a.k_ld), static_cast<uint64_t>(a.d),
+                       static_cast<uint64_t>(a.Nk) * a.k_ld};
+    uint32_t box[4] = {64, static_cast<uint32_t>(bkv), 1, 1};
+    if (int e = encode_map(&p.mapK, a.k, 4, dims, str, box)) return e;
+  }
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(a.Nk), static_cast<uint64_t>(a.d), static_cast<uint64_t>(a.heads),
+                        static_cast<uint64_t>(a.B)};
+    uint64_t str[4] = {1, static_cast<uint64_t>(a.vt_ld), static_cast<uint64_t>(a.d) * a.vt_ld,
+                       static_cast<uint64_t>(a.heads) * a.d * a.vt_ld};
+    uint32_t box[4] = {64, static_cast<uint32_t>(dvp), 1, 1};
+    if (int e = encode_map(&p.mapV, a.vt, 4, dims, str, box)) return e;
+  }
+  return 0;
+}
+
+int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
+  if (int e = attn_init()) return e;
+  const AttnLaunchImpl* I = reinterpret_cast<const AttnLaunchImpl*>(L.storage);
+  switch (I->variant) {
+    case 0: attn_fwd_kernel<1, 16, 128, 2><<<I->grid, ATT_THREADS, AttnCfg<1, 16, 128, 2>::SMEM, stream>>>(I->p); break;
+    case 1: attn_fwd_kernel<1, 32, 128, 2><<<I->grid, ATT_THREADS, AttnCfg<1, 32, 128, 2>::SMEM, stream>>>(I->p); break;
+    case 2: attn_fwd_kernel<1, 48, 128, 2><<<I->grid, ATT_THREADS, AttnCfg<1, 48, 128, 2>::SMEM, stream>>>(I->p); break;
+    case 3: attn_fwd_kernel<1, 64, 128, 2><<<I->grid, ATT_THREADS, AttnCfg<1, 64, 128, 2>::SMEM, stream>>>(I->p); break;
+    case 4: attn_fwd_kernel<2, 80, 128, 2><<<I->grid, ATT_THREADS, AttnCfg<2, 80, 128, 2>::SMEM, stream>>>(I->p); break;
+    case 5: attn_fwd_kernel<3, 160, 64, 3><<<I->grid, ATT_THREADS, AttnCfg<3, 160, 64, 3>::SMEM, stream>>>(I->p); break;
+    default: set_error("bad attention variant"); return 1;
+  }
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sdw

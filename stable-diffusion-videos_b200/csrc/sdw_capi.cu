@@ -61,6 +61,19 @@ int sdw_gemm(const sdw_gemm_desc* c, void* stream) {
   return launch_gemm(L, static_cast<cudaStream_t>(stream));
 }
 
+int sdw_attention(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* vt, int64_t vt_ld, int B,
+                  int Nq, int Nk, int heads, int d, void* out, int64_t out_ld, void* stream) {
+  AttnDesc a;
+  a.q = static_cast<const __half*>(q); a.q_ld = q_ld;
+  a.k = static_cast<const __half*>(k); a.k_ld = k_ld;
+  a.vt = static_cast<const __half*>(vt); a.vt_ld = vt_ld;
+  a.B = B; a.Nq = Nq; a.Nk = Nk; a.heads = heads; a.d = d;
+  a.out = static_cast<__half*>(out); a.out_ld = out_ld;
+  AttnLaunch L;
+  if (int e = plan_attention(a, &L)) return e;
+  return launch_attention(L, static_cast<cudaStream_t>(stream));
+}
+
 int sdw_pack_weight(const void* w_oihw, int N, int C, int kh, int kw, int geglu_interleave, void* out, void* stream) {
   return pack_weight(w_oihw, N, C, kh, kw, geglu_interleave, out, static_cast<cudaStream_t>(stream));
 }

@@ -15,6 +15,7 @@
 #include "sdw_internal.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -202,10 +203,25 @@ struct Engine {
     emit([=](cudaStream_t st, int) { return layernorm(x.p, x.ld, x.pixels(), x.C, g, b, 1e-5f, out.p, out.ld, st); });
   }
   int cfg_groups = 32;
+  bool use_flash = true;
 
   // unfused attention: S = alpha Q K^T (head-batched tcgen05 GEMM) ; softmax rows ; O = P V
   int attention(const __half* q, int64_t q_ld, const __half* k, int64_t k_ld, const __half* vt, int64_t vt_ld, int Bq,
                 int Nq, int Nk, int heads, int d, const T& out) {
+    if (use_flash && attn_supported(d)) {
+      if (dry) {
+        *cur_count += 1;
+        return 0;
+      }
+      AttnDesc a;
+      a.q = q; a.q_ld = q_ld; a.k = k; a.k_ld = k_ld; a.vt = vt; a.vt_ld = vt_ld;
+      a.B = Bq; a.Nq = Nq; a.Nk = Nk; a.heads = heads; a.d = d;
+      a.out = out.p; a.out_ld = out.ld;
+      auto L = std::make_shared<AttnLaunch>();
+      if (int e = plan_attention(a, L.get())) return e;
+      emit([L](cudaStream_t st, int) { return launch_attention(*L, st); });
+      return 0;
+    }
     const int64_t Nkp = (Nk + 7) / 8 * 8;
     GemmDesc g;
     g.A = q; g.C = d; g.W = Nq; g.H = heads; g.B = Bq;
@@ -672,6 +688,7 @@ int sdw_engine_create(const sdw_engine_config* cfg, sdw_engine** out) {
   if (int e = validate(cfg)) return e;
   Engine* E = new Engine();
   E->cfg = *cfg;
+  if (const char* nf = std::getenv("SDW_NO_FLASH")) E->use_flash = !(nf[0] == '1');
   if (int e = E->build(true, nullptr)) {
     delete E;
     return e;

@@ -117,6 +117,27 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
                const uint32_t* box);
 
 // ---------------------------------------------------------------------------
+// fused attention (sdw_attn.cu)
+// ---------------------------------------------------------------------------
+struct AttnDesc {
+  const __half* q = nullptr;   // [B][Nq][q_ld], head h at columns h*d
+  int64_t q_ld = 0;
+  const __half* k = nullptr;   // [B][Nk][k_ld], head h at columns h*d
+  int64_t k_ld = 0;
+  const __half* vt = nullptr;  // [B][heads][d][vt_ld]  (V transposed, written by the QKV GEMM epilogue)
+  int64_t vt_ld = 0;
+  int B = 0, Nq = 0, Nk = 0, heads = 0, d = 0;
+  __half* out = nullptr;       // [B][Nq][out_ld], head h at columns h*d
+  int64_t out_ld = 0;
+};
+struct AttnLaunch {
+  alignas(64) unsigned char storage[704];
+};
+bool attn_supported(int d);
+int plan_attention(const AttnDesc& a, AttnLaunch* L);
+int launch_attention(const AttnLaunch& L, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
 // fp32 helper kernels (sdw_elem.cu)
 // ---------------------------------------------------------------------------
 int slerp_lerp_batch(const void* lat_a, const void* lat_b, const void* emb_a, const void* emb_b, const float* t,

@@ -312,8 +312,8 @@ class StableDiffusionWalkPipeline:
             eng.set_scheduler(self.scheduler, num_inference_steps, guidance_scale)
             eng._plan_key = plan_key
         want_float = output_type != "pil"
-        frames_u8, raw = eng.sample(latents, text_embeddings.to(self.device), uncond, use_graph=True,
-                                    return_raw=want_float)
+        res = eng.sample(latents, text_embeddings.to(self.device), uncond, use_graph=True, return_raw=want_float)
+        frames_u8, raw = res if want_float else (res, None)
         if output_type == "pil":
             from PIL import Image
 
