@@ -195,7 +195,7 @@ struct Engine {
     float2* ws = gn_ws;
     emit([=](cudaStream_t st, int) {
       return groupnorm(x.p, x.ld, x.B, static_cast<int64_t>(x.H) * x.W, x.C, G, g, b, eps, silu, out.p, out.ld, ws, st);
-    }, 2);
+    }, 3);
   }
   void ln(const T& x, const std::string& name, const T& out) {
     const float* g = vec(name + ".weight", x.C);
@@ -609,7 +609,7 @@ struct Engine {
     const int OH = H * cfg.vae_scale, OW = W * cfg.vae_scale;
     out_u8 = static_cast<uint8_t*>(alloc(static_cast<size_t>(F) * OH * OW * cfg.vae_out_channels));
     out_img_f32 = static_cast<float*>(alloc(static_cast<size_t>(F) * OH * OW * cfg.vae_out_channels * 4));
-    gn_ws = static_cast<float2*>(alloc(static_cast<size_t>(std::max(Bn, F)) * 32 * 64 * sizeof(float2)));
+    gn_ws = static_cast<float2*>(alloc(gn_workspace_bytes(std::max(Bn, F))));
     // attention score scratch: largest of UNet level-0 self attention and the VAE mid attention
     {
       const int64_t n0 = static_cast<int64_t>(H) * W;

@@ -152,7 +152,8 @@ int pack_weight(const void* w, int N, int C, int kh, int kw, int geglu, void* ou
 // ---------------------------------------------------------------------------
 // norm / softmax / small-channel layers (sdw_norm.cu)
 // ---------------------------------------------------------------------------
-int gn_chunks(int64_t P);
+int gn_chunks(int64_t P, int B);
+size_t gn_workspace_bytes(int B);
 int groupnorm(const __half* x, int64_t ldx, int B, int64_t P, int C, int G, const float* gamma, const float* beta,
               float eps, int silu, __half* y, int64_t ldy, float2* partial_ws, cudaStream_t stream);
 int layernorm(const __half* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,

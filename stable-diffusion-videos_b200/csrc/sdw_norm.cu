@@ -10,13 +10,13 @@
 namespace sdw {
 
 // =============================================================================================
-// GroupNorm: two deterministic kernels.
+// GroupNorm: three small deterministic kernels.
 //   gn_partial : grid (nchunks, B). Each block sums x and x^2 per group over its pixel chunk (all channels,
 //                coalesced 16-byte loads, fixed reduction order) -> partial[b][chunk][g] = (sum, sumsq).
-//   gn_apply   : grid (pixel tiles, B). Reduces the <=32 partials per group in a fixed order, then
-//                y = (x - mean) * rstd * gamma + beta (optionally SiLU), fp16 out.
+//   gn_finalize: one warp per (b, g) reduces the chunk partials in a fixed order -> (mean, rstd).
+//   gn_apply   : grid (pixel tiles, B): y = (x - mean) * rstd * gamma + beta (optionally SiLU), fp16 out.
 // =============================================================================================
-static constexpr int GN_MAX_CHUNKS = 32;
+static constexpr int GN_MAX_CHUNKS = 1024;
 static constexpr int GN_MAX_GROUPS = 64;
 
 // per-thread partials go to shared memory and are reduced in index order (bit-reproducible).
@@ -38,7 +38,26 @@ __global__ void __launch_bounds__(256) gn_partial_det_kernel(const __half* __res
     float s[8], q[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-    for (int64_t p = p0 + prow; p < p1; p += rows) {
+    int64_t p = p0 + prow;
+    // 4 independent 16-byte loads in flight per thread
+    for (; p + 3 * rows < p1; p += 4 * rows) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (p + k * rows) * ld + v * 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          s[2 * j] += f.x;
+          q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
+          s[2 * j + 1] += f.y;
+          q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
+        }
+      }
+    }
+    for (; p < p1; p += rows) {
       const uint4 u = *reinterpret_cast<const uint4*>(xb + p * ld + v * 8);
       const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -68,26 +87,40 @@ __global__ void __launch_bounds__(256) gn_partial_det_kernel(const __half* __res
   }
 }
 
+// one warp per (b, g): fixed-order reduction of the chunk partials -> (mean, rstd)
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float2* __restrict__ part, int nchunks, int G, int BG,
+                                                          float count, float eps, float2* __restrict__ stats) {
+  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (idx >= BG) return;
+  const int lane = threadIdx.x & 31;
+  const int b = idx / G, g = idx % G;
+  float a = 0.f, c = 0.f;
+  for (int k = lane; k < nchunks; k += 32) {
+    const float2 pr = part[(static_cast<int64_t>(b) * nchunks + k) * G + g];
+    a += pr.x;
+    c += pr.y;
+  }
+  a = warp_sum(a);
+  c = warp_sum(c);
+  if (lane == 0) {
+    const float mean = a / count;
+    const float var = fmaxf(c / count - mean * mean, 0.f);
+    stats[idx] = make_float2(mean, rsqrtf(var + eps));
+  }
+}
+
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, int64_t ldx, int C, int G,
-                                                       int64_t P, int nchunks, const float2* __restrict__ part,
+                                                       int64_t P, const float2* __restrict__ stats,
                                                        const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, float eps, int silu,
+                                                       const float* __restrict__ beta, int silu,
                                                        __half* __restrict__ y, int64_t ldy, int pix_per_block) {
   __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
   const int b = blockIdx.y;
   const int cg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    float a = 0.f, c = 0.f;
-    for (int k = 0; k < nchunks; ++k) {
-      const float2 pr = part[(static_cast<int64_t>(b) * nchunks + k) * G + g];
-      a += pr.x;
-      c += pr.y;
-    }
-    const float n = static_cast<float>(P) * cg;
-    const float mean = a / n;
-    const float var = fmaxf(c / n - mean * mean, 0.f);
-    s_mean[g] = mean;
-    s_rstd[g] = rsqrtf(var + eps);
+    const float2 st = stats[b * G + g];
+    s_mean[g] = st.x;
+    s_rstd[g] = st.y;
   }
   __syncthreads();
   const int vecs = C / 8;
@@ -125,30 +158,39 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
   }
 }
 
-int gn_chunks(int64_t P) {
-  int64_t n = P / 64;
+// chunks per sample: enough blocks to fill the machine (B * nchunks >= ~4 waves) while keeping >= 16 pixels each
+int gn_chunks(int64_t P, int B) {
+  int64_t want = (148 * 4 + B - 1) / B;
+  int64_t n = std::min<int64_t>(want, P / 16);
   if (n < 1) n = 1;
   if (n > GN_MAX_CHUNKS) n = GN_MAX_CHUNKS;
   return static_cast<int>(n);
 }
 
+// workspace: partials [B][nchunks][G] float2 followed by stats [B][G] float2
+size_t gn_workspace_bytes(int B) { return (static_cast<size_t>(B) * GN_MAX_CHUNKS * GN_MAX_GROUPS + B * GN_MAX_GROUPS) * sizeof(float2); }
+
 int groupnorm(const __half* x, int64_t ldx, int B, int64_t P, int C, int G, const float* gamma, const float* beta,
               float eps, int silu, __half* y, int64_t ldy, float2* partial_ws, cudaStream_t stream) {
   SDW_REQUIRE(C % 8 == 0 && C % G == 0 && G <= GN_MAX_GROUPS, "GroupNorm: C % 8, C % G, G <= 64");
   SDW_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, "GroupNorm: row pitch must be a multiple of 8");
-  const int nchunks = gn_chunks(P);
+  const int nchunks = gn_chunks(P, B);
   const int ppc = static_cast<int>((P + nchunks - 1) / nchunks);
   const int vecs = C / 8;
   const int rows = std::max(1, std::min(std::min(256 / vecs, 16), 6144 / C));
   const size_t smem = static_cast<size_t>(2) * rows * C * sizeof(float);
   SDW_REQUIRE(smem <= 48 * 1024, "GroupNorm: channel count too large for the stats kernel");
+  float2* stats = partial_ws + static_cast<size_t>(B) * nchunks * G;
   gn_partial_det_kernel<<<dim3(nchunks, B), 256, smem, stream>>>(x, ldx, C, G, P, ppc, partial_ws);
+  SDW_CUDA_OK(cudaGetLastError());
+  const int BG = B * G;
+  gn_finalize_kernel<<<(BG + 7) / 8, 256, 0, stream>>>(partial_ws, nchunks, G, BG, static_cast<float>(P) * (C / G), eps,
+                                                       stats);
   SDW_CUDA_OK(cudaGetLastError());
   int ppb = static_cast<int>(std::max<int64_t>(1, 4096 / C));  // ~4K elements per block pass
   ppb *= 8;
   const unsigned tiles = static_cast<unsigned>((P + ppb - 1) / ppb);
-  gn_apply_kernel<<<dim3(tiles, B), 256, 0, stream>>>(x, ldx, C, G, P, nchunks, partial_ws, gamma, beta, eps, silu, y,
-                                                      ldy, ppb);
+  gn_apply_kernel<<<dim3(tiles, B), 256, 0, stream>>>(x, ldx, C, G, P, stats, gamma, beta, silu, y, ldy, ppb);
   SDW_CUDA_OK(cudaGetLastError());
   return 0;
 }
