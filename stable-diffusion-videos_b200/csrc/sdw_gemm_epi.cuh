@@ -38,110 +38,211 @@ __device__ __forceinline__ void load8(const __half* src, float* v, bool vec_ok, 
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// fast paths: everything column-uniform is hoisted, 16-byte vector I/O only (the first version of this
+// epilogue spent ~750 SASS instructions per 32-column chunk on generic address / predicate math and was
+// the bottleneck of every short-K GEMM — see profiles/r01_ncu_gemm_linear_v1.txt).
+// FLAGS: 1 bias, 2 per-sample row vector (time embedding), 4 residual, 8 SiLU, 16 alpha != 1
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void add8(float* o, const float* __restrict__ src) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+  o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+  o[4] += b.x; o[5] += b.y; o[6] += b.z; o[7] += b.w;
+}
+
+// V^T scatter of one 32-column chunk (columns >= vt_col0): out element (b, head, dd, tok)
+__device__ __forceinline__ void epi_vt_chunk(const GemmKParams& p, const uint32_t (&v)[32], int n, int64_t pix_in) {
+  const int64_t bq = pix_in / p.vt_ntok;
+  const int tok = static_cast<int>(pix_in - bq * p.vt_ntok);
+  int cc = n - p.vt_col0;
+  int head = cc / p.vt_d;
+  int dd = cc - head * p.vt_d;
+  __half* base = p.vt + (bq * p.vt_heads) * p.vt_d * p.vt_ld + tok;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (n + j < p.N) {
+      float a = __uint_as_float(v[j]) * p.alpha;
+      if (p.bias) a += __ldg(&p.bias[n + j]);
+      base[(static_cast<int64_t>(head) * p.vt_d + dd) * p.vt_ld] = __float2half_rn(a);
+    }
+    if (++dd == p.vt_d) {
+      dd = 0;
+      ++head;
+    }
+  }
+}
+
+template <int BN, int FLAGS>
+__device__ __forceinline__ void epi_fast(const GemmKParams& p, uint32_t taddr, int n0, bool row_ok, int64_t pix_in,
+                                         __half* out_row, const __half* res_row, const float* rowvec) {
+  const int nmax = min(BN, p.N - n0);  // valid columns of this tile (multiple of 8)
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    if (c * 32 >= nmax) break;
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+    const int n = n0 + c * 32;
+    if (p.mode == GEMM_QKV_VT && n >= p.vt_col0) {
+      epi_vt_chunk(p, v, n, pix_in);
+      continue;
+    }
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      if (c * 32 + j8 * 8 < nmax) {
+        const int nn = n + j8 * 8;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = __uint_as_float(v[j8 * 8 + j]);
+          if (FLAGS & 16) o[j] *= p.alpha;
+        }
+        if (FLAGS & 1) add8(o, p.bias + nn);
+        if (FLAGS & 2) add8(o, rowvec + nn);
+        if (FLAGS & 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = silu_f(o[j]);
+        }
+        if (FLAGS & 4) {
+          const uint4 u = *reinterpret_cast<const uint4*>(res_row + nn);
+          const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            o[2 * j] += f.x;
+            o[2 * j + 1] += f.y;
+          }
+        }
+        uint4 w;
+        w.x = pack_h2(o[0], o[1]);
+        w.y = pack_h2(o[2], o[3]);
+        w.z = pack_h2(o[4], o[5]);
+        w.w = pack_h2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(out_row + nn) = w;
+      }
+    }
+  }
+}
+
+// GEGLU: packed columns [32 value | 32 gate] pairs -> 32 outputs a * gelu(g)
+template <int BN>
+__device__ __forceinline__ void epi_geglu(const GemmKParams& p, uint32_t taddr, int n0, bool row_ok, __half* out_row,
+                                          bool vec_out) {
+#pragma unroll 1
+  for (int c = 0; c < BN / 64; ++c) {
+    const int n = n0 + c * 64;
+    if (n >= p.N) break;
+    uint32_t va[32], vg[32];
+    tmem_ld_32x32(taddr + c * 64, va);
+    tmem_ld_32x32(taddr + c * 64 + 32, vg);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+    __half* dst = out_row + n / 2;
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      float a[8], g[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[j] = __uint_as_float(va[j8 * 8 + j]) * p.alpha;
+        g[j] = __uint_as_float(vg[j8 * 8 + j]) * p.alpha;
+      }
+      if (p.bias) {
+        add8(a, p.bias + n + j8 * 8);
+        add8(g, p.bias + n + 32 + j8 * 8);
+      }
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = a[j] * gelu_erf_f(g[j]);
+      store8(dst + j8 * 8, o, vec_out, 8);
+    }
+  }
+}
+
 // warp = absolute warp index of an epilogue warp (its TMEM lane quarter is warp & 3); tmem_acc = accumulator base.
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, uint32_t tmem_acc, int warp, int lane, int x0,
-                                              int y0, int b0, int n0, uint64_t* tmem_full_bar) {
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
-    const int r = quarter * 32 + lane;
-    const int lx = r % p.bw;
-    const int ly = (r / p.bw) % p.bh;
-    const int lb = r / (p.bw * p.bh);
-    const int x = x0 + lx, y = y0 + ly, b = b0 + lb;
-    const bool row_ok = (x < p.W) && (y < p.H) && (b < p.B);
-    const int64_t pix_in = (static_cast<int64_t>(b) * p.H + y) * p.W + x;  // lattice-linear index
-    const int oyy = y * p.os + p.oy, oxx = x * p.os + p.ox;
-    const int64_t out_off = static_cast<int64_t>(b) * p.o_sB + oyy * p.o_sH + oxx * p.o_sW;
-    const int64_t res_off = static_cast<int64_t>(b) * p.r_sB + oyy * p.r_sH + oxx * p.r_sW;
-    const bool vec_out = (((p.o_sW | p.o_sH | p.o_sB) & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
-    const bool vec_res = p.resid && (((p.r_sW | p.r_sH | p.r_sB) & 7) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0);
-    const float* rowvec = p.rowvec ? p.rowvec + static_cast<int64_t>(b) * p.rowvec_ld : nullptr;
+                                              int y0, int b0, int n0, uint64_t* tmem_full_bar, uint32_t full_parity = 0) {
+  const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+  const int r = quarter * 32 + lane;
+  const int lx = r % p.bw;
+  const int ly = (r / p.bw) % p.bh;
+  const int lb = r / (p.bw * p.bh);
+  const int x = x0 + lx, y = y0 + ly, b = b0 + lb;
+  const bool row_ok = (x < p.W) && (y < p.H) && (b < p.B);
+  const int64_t pix_in = (static_cast<int64_t>(b) * p.H + y) * p.W + x;  // lattice-linear index
+  const int oyy = y * p.os + p.oy, oxx = x * p.os + p.ox;
+  const int64_t out_off = static_cast<int64_t>(b) * p.o_sB + oyy * p.o_sH + oxx * p.o_sW;
+  const int64_t res_off = static_cast<int64_t>(b) * p.r_sB + oyy * p.r_sH + oxx * p.r_sW;
+  const bool vec_out = (((p.o_sW | p.o_sH | p.o_sB) & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+  const bool vec_res = p.resid && (((p.r_sW | p.r_sH | p.r_sB) & 7) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0);
+  const float* rowvec = p.rowvec ? p.rowvec + static_cast<int64_t>(b) * p.rowvec_ld : nullptr;
+  __half* out_row = p.out + out_off;
+  const __half* res_row = p.resid ? p.resid + res_off : nullptr;
 
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+  mbar_wait(tmem_full_bar, full_parity);
+  tc_fence_after();
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
 
-    if (p.mode == GEMM_GEGLU) {
-      // packed columns: [32 value | 32 gate] pairs -> 32 outputs
-#pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        const int n = n0 + c * 64;
-        if (n >= p.N) break;
-        uint32_t va[32], vg[32];
-        tmem_ld_32x32(taddr + c * 64, va);
-        tmem_ld_32x32(taddr + c * 64 + 32, vg);
-        tmem_ld_wait();
-        if (row_ok) {
-          __half* dst = p.out + out_off + n / 2;
-#pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int jj = j8 * 8 + j;
-              float a = __uint_as_float(va[jj]) * p.alpha;
-              float g = __uint_as_float(vg[jj]) * p.alpha;
-              if (p.bias) {
-                a += __ldg(&p.bias[n + jj]);
-                g += __ldg(&p.bias[n + 32 + jj]);
-              }
-              o[j] = a * gelu_erf_f(g);
-            }
-            store8(dst + j8 * 8, o, vec_out, 8);
-          }
-        }
-      }
-    } else {
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n = n0 + c * 32;
-        if (n >= p.N) break;
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        const bool to_vt = (p.mode == GEMM_QKV_VT) && (n >= p.vt_col0);
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          const int nn = n + j8 * 8;
-          const int nvalid = min(8, p.N - nn);
-          if (nvalid <= 0) break;
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float a = __uint_as_float(v[j8 * 8 + j]) * p.alpha;
-            if (j < nvalid) {
-              if (p.bias) a += __ldg(&p.bias[nn + j]);
-              if (rowvec) a += __ldg(&rowvec[nn + j]);
-            }
-            if (p.act == 1) a = silu_f(a);
-            o[j] = a;
-          }
-          if (to_vt) {
-            const int64_t bq = pix_in / p.vt_ntok;
-            const int tok = static_cast<int>(pix_in - bq * p.vt_ntok);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (j < nvalid) {
-                const int cc = nn + j - p.vt_col0;
-                const int head = cc / p.vt_d;
-                const int dd = cc - head * p.vt_d;
-                p.vt[((bq * p.vt_heads + head) * p.vt_d + dd) * p.vt_ld + tok] = __float2half_rn(o[j]);
-              }
-            }
-          } else {
-            if (p.resid) {
-              float rr[8];
-              load8(p.resid + res_off + nn, rr, vec_res, nvalid);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] += rr[j];
-            }
-            store8(p.out + out_off + nn, o, vec_out, nvalid);
-          }
-        }
-      }
+  if (p.mode == GEMM_GEGLU) {
+    epi_geglu<BN>(p, taddr, n0, row_ok, out_row, vec_out);
+    return;
+  }
+  const bool fast = vec_out && (!p.resid || vec_res) && ((p.N & 7) == 0) &&
+                    (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
+                    (!p.rowvec || ((reinterpret_cast<uintptr_t>(p.rowvec) & 15) == 0 && (p.rowvec_ld & 3) == 0));
+  if (fast) {
+    const int flags = (p.bias ? 1 : 0) | (p.rowvec ? 2 : 0) | (p.resid ? 4 : 0) | (p.act == 1 ? 8 : 0) |
+                      (p.alpha != 1.f ? 16 : 0);
+    switch (flags) {
+      case 0: epi_fast<BN, 0>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec); return;
+      case 1: epi_fast<BN, 1>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec); return;
+      case 3: epi_fast<BN, 3>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec); return;
+      case 5: epi_fast<BN, 5>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec); return;
+      case 16: epi_fast<BN, 16>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec); return;
+      default: break;
     }
+  }
+  // ---- generic path (unaligned views, odd N, rarely used flag combinations) --------------------
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int n = n0 + c * 32;
+    if (n >= p.N) break;
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+    if (p.mode == GEMM_QKV_VT && n >= p.vt_col0) {
+      epi_vt_chunk(p, v, n, pix_in);
+      continue;
+    }
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      const int nn = n + j8 * 8;
+      const int nvalid = min(8, p.N - nn);
+      if (nvalid <= 0) continue;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = __uint_as_float(v[j8 * 8 + j]) * p.alpha;
+        if (j < nvalid) {
+          if (p.bias) a += __ldg(&p.bias[nn + j]);
+          if (rowvec) a += __ldg(&rowvec[nn + j]);
+        }
+        if (p.act == 1) a = silu_f(a);
+        o[j] = a;
+      }
+      if (p.resid) {
+        float rr[8];
+        load8(res_row + nn, rr, vec_res, nvalid);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += rr[j];
+      }
+      store8(out_row + nn, o, vec_out, nvalid);
+    }
+  }
 }
 
 }  // namespace sdw
