@@ -166,7 +166,8 @@ typedef struct sdw_gemm_desc {
   int32_t vt_col0, vt_d, vt_heads, vt_ntok;
   void* vt;
   int64_t vt_ld;
-  int32_t bn;
+  int32_t bn;                /* BLOCK_N: 0 auto, 64/128/160/256 */
+  int32_t ver;               /* 0 auto, 1: one CTA per 128xBN tile, 2: persistent CTA pairs (256xBN) */
 } sdw_gemm_desc;
 
 int sdw_gemm(const sdw_gemm_desc* desc, void* stream);

@@ -56,6 +56,7 @@ int sdw_gemm(const sdw_gemm_desc* c, void* stream) {
   d.vt_col0 = c->vt_col0; d.vt_d = c->vt_d; d.vt_heads = c->vt_heads; d.vt_ntok = c->vt_ntok;
   d.vt = static_cast<__half*>(c->vt); d.vt_ld = c->vt_ld;
   d.bn = c->bn;
+  d.ver = c->ver;
   GemmLaunch L;
   if (int e = plan_gemm(d, &L)) return e;
   return launch_gemm(L, static_cast<cudaStream_t>(stream));

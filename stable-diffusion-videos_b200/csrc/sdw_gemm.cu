@@ -19,6 +19,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace sdw {
@@ -292,8 +293,34 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
   const int tiles_b = (d.B + bb - 1) / bb;
   p.N = d.N;
   p.b_batched = d.b_batched;
+  // kernel version: CTA pairs need >= 2 M tiles and a wide-enough N; batched matmuls must pair within one (h, b)
+  const int m_tiles = p.tiles_w * p.tiles_h * tiles_b;
+  int ver = d.ver;
+  if (ver == 0) {
+    static const bool force_v1 = [] { const char* e = std::getenv("SDW_GEMM_V1"); return e && e[0] == '1'; }();
+    ver = (!force_v1 && m_tiles >= 2 && d.N >= 128 && (!d.b_batched || p.tiles_w % 2 == 0)) ? 2 : 1;
+  }
+  if (ver == 2) SDW_REQUIRE(!d.b_batched || p.tiles_w % 2 == 0, "2-CTA batched matmul needs an even tile count per row");
   // BLOCK_N choice
   int bn = d.bn;
+  if (bn == 0 && ver == 2) {
+    // largest of {256, 160, 128} wasting < 10 % of the padded N (GEGLU needs 64-column pairs)
+    const int cand[3] = {256, 160, 128};
+    int best = 128;
+    double best_cost = 1e30;
+    for (int c : cand) {
+      if (d.mode == GEMM_GEGLU && c % 64 != 0) continue;
+      const int tiles = (d.N + c - 1) / c;
+      const double waste = static_cast<double>(tiles) * c / d.N;
+      const double eff = c == 256 ? 1.0 : (c == 160 ? 1.12 : 1.2);  // smaller tiles pay more L2 bytes per FLOP
+      const double cost = waste * eff;
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = c;
+      }
+    }
+    bn = best;
+  }
   if (bn == 0) {
     if (d.mode == GEMM_GEGLU) bn = 128;
     else if (d.N % 160 == 0 && d.N % 128 != 0) bn = 160;
@@ -301,10 +328,18 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
     else bn = 128;
   }
   SDW_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "unsupported BLOCK_N");
+  if (ver == 2) SDW_REQUIRE(bn != 64, "the 2-CTA kernel needs BLOCK_N >= 128");
+  L->ver = ver;
   if (d.mode == GEMM_GEGLU) SDW_REQUIRE(bn % 64 == 0 && d.N % 64 == 0, "GEGLU needs 64-column pairs");
   if (d.mode == GEMM_QKV_VT) SDW_REQUIRE(d.vt && d.vt_col0 % 32 == 0 && d.vt_d > 0, "bad V^T split");
   L->bn = bn;
-  L->grid = dim3(p.tiles_w * p.tiles_h * tiles_b, (d.N + bn - 1) / bn, 1);
+  L->grid = dim3(m_tiles, (d.N + bn - 1) / bn, 1);
+  if (ver == 2) {
+    p.m_pairs = (m_tiles + 1) / 2;
+    p.n_tiles = (d.N + bn - 1) / bn;
+    const int clusters = std::min(p.m_pairs * p.n_tiles, 74);
+    L->grid = dim3(2 * clusters, 1, 1);
+  }
   // tensor maps: A
   for (int m = 0; m < nmaps; ++m) {
     const __half* base = d.A;
@@ -334,7 +369,7 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
                            static_cast<uint64_t>(d.b_batched ? d.sBb : 0)};
     for (int i = 2; i < 4; ++i)
       if (strides[i] == 0) strides[i] = static_cast<uint64_t>(ldb);
-    uint32_t box[4] = {BK, static_cast<uint32_t>(bn), 1, 1};
+    uint32_t box[4] = {BK, static_cast<uint32_t>(ver == 2 ? bn / 2 : bn), 1, 1};
     if (int e = encode_map(&p.mapB, d.Wt, 4, dims, strides, box)) return e;
   }
   p.bias = d.bias;
@@ -366,6 +401,7 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
 }
 
 int launch_gemm(const GemmLaunch& l, cudaStream_t stream) {
+  if (l.ver == 2) return launch_gemm2(l, stream);
   switch (l.bn) {
     case 64:
       gemm_tc_kernel<64><<<l.grid, GEMM_THREADS, GemmCfg<64>::SMEM_BYTES, stream>>>(l.p);

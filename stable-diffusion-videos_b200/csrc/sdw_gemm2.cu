@@ -1,0 +1,204 @@
+// sdw_gemm2.cu — persistent 2-CTA (cta_group::2) variant of the implicit-GEMM kernel.
+//
+// Why: a 128 x BN tile moves (128 + BN) * 128 B of operands per 64-deep K block for 2 * 128 * BN * 64 FLOP —
+// 64-71 FLOP per L2 byte, which caps the whole chip near 40 % of tensor peak (profiles/r01_ncu_gemm_v1.md: LTS 33 % at
+// tensor 34 %).  A CTA pair computes a 256 x BN tile with ONE tcgen05.mma.cta_group::2 (M = 256): each CTA stages its
+// own 128 activation rows and only HALF of the weight tile, so operand bytes per FLOP drop by ~1.6-2x, and the
+// accumulators of two consecutive tiles double-buffer in TMEM so the epilogue of tile i overlaps the mainloop of
+// tile i+1 (persistent grid: one cluster per SM pair, static round-robin over tiles, M fastest for weight reuse in L2).
+//
+//   warp 0 (both CTAs)  : TMA producer — own A tile [128 x 64] + own half of B [BN/2 x 64]; completion bytes are
+//                         signalled on the LEADER's full barrier (cta_group::2 TMA, mapa'd barrier address).
+//   warp 1 (leader)     : MMA issuer, 4 x UMMA(M=256, N=BN, K=16) per K block; tcgen05.commit multicast frees the
+//                         smem stage in both CTAs / publishes the accumulator to both epilogues.
+//   warps 2-5 (both)    : epilogue on the CTA's own 128 rows (sdw_gemm_epi.cuh), then a remote arrive on the
+//                         leader's tmem_empty barrier.
+#include "sdw_gemm_epi.cuh"
+#include "sdw_internal.h"
+#include "sdw_ptx.cuh"
+
+namespace sdw {
+
+static constexpr int G2_THREADS = 192;
+static constexpr int G2_A_STAGE = 128 * 64 * 2;
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int BH = BN / 2;
+  static constexpr int B_STAGE = BH * 128;
+  static constexpr int STAGES = BN == 256 ? 6 : (BN == 160 ? 7 : 8);
+  static constexpr int TMEM_COLS = BN <= 128 ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * (G2_A_STAGE + B_STAGE) + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+    gemm2_tc_kernel(const __grid_constant__ GemmKParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * G2_A_STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * Cfg::B_STAGE);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]  (leader's copy is the one in use)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int nclusters = gridDim.x >> 1;
+  const int total_tiles = p.m_pairs * p.n_tiles;
+  const int num_kb = p.ntaps * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.mapA[0]);
+    tma_prefetch_desc(&p.mapB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 8);  // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto tile_coords = [&](int t, int& x0, int& y0, int& b0, int& n0) {
+    const int m_pair = t % p.m_pairs;
+    const int n_tile = t / p.m_pairs;
+    const int m_tile = m_pair * 2 + static_cast<int>(rank);
+    const int tw = m_tile % p.tiles_w;
+    const int th = (m_tile / p.tiles_w) % p.tiles_h;
+    const int tb = m_tile / (p.tiles_w * p.tiles_h);
+    x0 = tw * p.bw;
+    y0 = th * p.bh;
+    b0 = tb * p.bb;
+    n0 = n_tile * BN;
+  };
+
+  if (warp == 0) {
+    // =========================== TMA producer (both CTAs) ==========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < total_tiles; t += nclusters) {
+        int x0, y0, b0, n0;
+        tile_coords(t, x0, y0, b0, n0);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int tap = kb / p.kchunks;
+          const int kc = kb - tap * p.kchunks;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (G2_A_STAGE + Cfg::B_STAGE));
+          const uint32_t bar = mapa_rank(smem_u32(&full_bar[stage]), 0);
+          tma_load_4d_2sm(&p.mapA[p.tap_map[tap]], bar, smem_a + stage * G2_A_STAGE, kc * 64, x0 + p.tap_dx[tap],
+                          y0 + p.tap_dy[tap], b0);
+          tma_load_4d_2sm(&p.mapB, bar, smem_b + stage * Cfg::B_STAGE, kb * 64, n0 + static_cast<int>(rank) * Cfg::BH,
+                          p.b_batched ? y0 : 0, p.b_batched ? b0 : 0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (leader CTA only) =======================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(256, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = cluster_id; t < total_tiles; t += nclusters, ++it) {
+        const int a = it & 1;
+        mbar_wait(&tmem_empty[a], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + a * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_desc_k_sw128(smem_u32(smem_a + stage * G2_A_STAGE));
+          const uint64_t db = make_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss_2cta(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2cta(&empty_bar[stage], 0b11);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2cta(&tmem_full[a], 0b11);
+      }
+    }
+  } else {
+    // =========================== epilogue (both CTAs, own 128 rows) ==================
+    int it = 0;
+    for (int t = cluster_id; t < total_tiles; t += nclusters, ++it) {
+      int x0, y0, b0, n0;
+      tile_coords(t, x0, y0, b0, n0);
+      const int a = it & 1;
+      gemm_epilogue<BN>(p, tmem_base + a * BN, warp, lane, x0, y0, b0, n0, &tmem_full[a], (it >> 1) & 1);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[a]), 0));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int set_attr2() {
+  SDW_CUDA_OK(cudaFuncSetAttribute(gemm2_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Gemm2Cfg<BN>::SMEM_BYTES));
+  return 0;
+}
+
+static bool g_init2 = false;
+int gemm2_init() {
+  if (g_init2) return 0;
+  if (int e = set_attr2<128>()) return e;
+  if (int e = set_attr2<160>()) return e;
+  if (int e = set_attr2<256>()) return e;
+  g_init2 = true;
+  return 0;
+}
+
+int launch_gemm2(const GemmLaunch& l, cudaStream_t stream) {
+  if (int e = gemm2_init()) return e;
+  switch (l.bn) {
+    case 128:
+      gemm2_tc_kernel<128><<<l.grid, G2_THREADS, Gemm2Cfg<128>::SMEM_BYTES, stream>>>(l.p);
+      break;
+    case 160:
+      gemm2_tc_kernel<160><<<l.grid, G2_THREADS, Gemm2Cfg<160>::SMEM_BYTES, stream>>>(l.p);
+      break;
+    case 256:
+      gemm2_tc_kernel<256><<<l.grid, G2_THREADS, Gemm2Cfg<256>::SMEM_BYTES, stream>>>(l.p);
+      break;
+    default:
+      set_error("bad BLOCK_N for the 2-CTA kernel");
+      return 1;
+  }
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sdw

@@ -54,6 +54,7 @@ struct alignas(64) GemmKParams {
   int tiles_w, tiles_h;     // tiles per (w,h); tiles along b = gridDim.x / (tiles_w*tiles_h)
   int N;                    // GEMM N (packed columns)
   int b_batched;            // 1: weight map coords (.., y0, b0) = lattice (h, b) (batched matmul)
+  int m_pairs, n_tiles;     // 2-CTA persistent kernel: tile grid (pairs of 128-row M tiles x BN-wide N tiles)
   // epilogue
   const float* bias;        // [N] or null
   const float* rowvec;      // [B][rowvec_ld] per-sample vector added per column (time-embedding proj) or null
@@ -75,7 +76,8 @@ struct alignas(64) GemmKParams {
 struct GemmLaunch {
   GemmKParams p;
   dim3 grid;
-  int bn;  // BLOCK_N variant
+  int bn;   // BLOCK_N variant
+  int ver;  // 1: one 128xBN tile per CTA (sdw_gemm.cu); 2: persistent CTA pairs, 256xBN tiles (sdw_gemm2.cu)
 };
 
 // Describes one implicit GEMM in host terms; plan_gemm() turns it into a launch.
@@ -106,11 +108,13 @@ struct GemmDesc {
   int vt_col0 = 0, vt_d = 0, vt_heads = 0, vt_ntok = 0;
   __half* vt = nullptr;
   int64_t vt_ld = 0;
-  int bn = 0;  // 0 = auto
+  int bn = 0;   // 0 = auto
+  int ver = 0;  // 0 = auto, 1 / 2 force a kernel version
 };
 
 int plan_gemm(const GemmDesc& d, GemmLaunch* out);
 int launch_gemm(const GemmLaunch& l, cudaStream_t stream);
+int launch_gemm2(const GemmLaunch& l, cudaStream_t stream);
 void set_plan_only(bool on);
 int gemm_init();  // resolves the driver entry point, sets smem attributes
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,

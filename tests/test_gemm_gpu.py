@@ -21,7 +21,7 @@ def _tol(ref):
     return float(ref.abs().max()) * 2.0 ** -9 + 1e-3
 
 
-def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None):
+def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None, ver=0):
     """x: [B,H,W,C] fp16 cuda; returns NHWC fp16 output computed by the native kernel."""
     n = _native()
     B, H, W, Cc = x_nhwc.shape
@@ -58,6 +58,7 @@ def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn
         d.act = act
         d.alpha = 1.0
         d.bn = bn
+        d.ver = ver
         n.gemm(d)
     torch.cuda.synchronize()
     return out
@@ -225,3 +226,61 @@ def test_qkv_vt_and_batched_attention_matmuls():
     torch.cuda.synchronize()
     O_ref = (P.float() @ vt.float().transpose(-1, -2)).permute(0, 2, 1, 3).reshape(Bn, Ntok, Cc)
     assert (O.float() - O_ref).abs().max().item() <= _tol(O_ref)
+
+
+# ---- the persistent 2-CTA (cta_group::2) kernel, forced ------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 64, 256), (300, 320, 320, 160), (8192, 320, 2880, 160),
+                                       (128, 128, 128, 128), (4096, 2560, 320, 0), (1000, 640, 1280, 0),
+                                       (77 * 4, 1280, 768, 256), (20000, 512, 512, 256)])
+def test_linear_2cta(M, N, K, bn):
+    x = _rand(1, 1, M, K, seed=31)
+    w = _rand(N, K, scale=K ** -0.5, seed=32)
+    bias = _rand(N, seed=33).float()
+    out = run_conv(x, w, 0, bias=bias, bn=bn, ver=2)
+    ref = ref_conv(x, w, 0, bias=bias)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= _tol(ref), (err, _tol(ref))
+
+
+@pytest.mark.parametrize("B,H,W,Cc,N,conv", [(2, 16, 16, 64, 128, 1), (4, 64, 64, 320, 320, 1), (2, 8, 8, 320, 320, 1),
+                                              (3, 4, 4, 128, 256, 1), (2, 32, 32, 192, 160, 1), (1, 24, 24, 64, 128, 1),
+                                              (2, 16, 16, 64, 128, 2), (2, 64, 64, 320, 320, 2), (2, 8, 8, 64, 128, 3),
+                                              (1, 32, 32, 128, 128, 3)])
+def test_conv_2cta(B, H, W, Cc, N, conv):
+    x = _rand(B, H, W, Cc, seed=34)
+    w = _rand(N, Cc, 3, 3, scale=(9 * Cc) ** -0.5, seed=35)
+    bias = _rand(N, seed=36).float()
+    rowvec = _rand(B, N, seed=37).float() if conv == 1 else None
+    resid = None
+    out = run_conv(x, w, conv, bias=bias, rowvec=rowvec, ver=2)
+    ref = ref_conv(x, w, conv, bias=bias, rowvec=rowvec)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= _tol(ref), (err, _tol(ref))
+
+
+def test_conv_residual_2cta_many_tiles():
+    """more tiles than clusters: exercises the persistent loop, TMEM double buffering and barrier phase wrap."""
+    x = _rand(8, 64, 64, 128, seed=38)
+    w = _rand(256, 128, 3, 3, scale=(9 * 128) ** -0.5, seed=39)
+    resid = _rand(8, 64, 64, 256, seed=40)
+    bias = _rand(256, seed=41).float()
+    out = run_conv(x, w, 1, bias=bias, resid=resid, ver=2, bn=128)
+    ref = ref_conv(x, w, 1, bias=bias, resid=resid)
+    assert (out.float() - ref).abs().max().item() <= _tol(ref)
+
+
+def test_geglu_2cta():
+    M, K, Ch = 1024, 320, 1280
+    x = _rand(1, 1, M, K, seed=42)
+    w = _rand(2 * Ch, K, scale=K ** -0.5, seed=43)
+    bias = _rand(2 * Ch, seed=44).float()
+    blk = torch.arange(2 * Ch, device="cuda")
+    b64, within = blk // 64, blk % 64
+    src = torch.where(within < 32, b64 * 32 + within, Ch + b64 * 32 + within - 32)
+    out = run_conv(x, w, 0, bias=bias[src].contiguous(), mode=1, ver=2)
+    h = x.float().reshape(M, K) @ w.float().t() + bias
+    a, g = h.chunk(2, dim=-1)
+    ref = (a * Fn.gelu(g)).reshape(1, 1, M, Ch)
+    assert (out.float() - ref).abs().max().item() <= _tol(ref)

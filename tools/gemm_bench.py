@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stable_diffusion_videos_b200 import _native as n  # noqa: E402
 
 
-def bench(B, H, W, C, N, conv, iters=20, bn=0):
+def bench(B, H, W, C, N, conv, iters=20, bn=0, ver=0):
     x = torch.randn(B, H, W, C, device="cuda").half()
     k = 3 if conv else 1
     w = (torch.randn(N, C, k, k, device="cuda") * (C * k * k) ** -0.5).half()
@@ -21,7 +21,7 @@ def bench(B, H, W, C, N, conv, iters=20, bn=0):
     d.conv = 1 if conv else 0
     d.Wt = wp.data_ptr(); d.N = N
     d.out = out.data_ptr(); d.ldc = N
-    d.alpha = 1.0; d.bn = bn
+    d.alpha = 1.0; d.bn = bn; d.ver = ver
     for _ in range(3):
         n.gemm(d)
     torch.cuda.synchronize()
@@ -53,6 +53,7 @@ if __name__ == "__main__":
         ("vae conv3x3 512x512 128->128", F, 512, 512, 128, 128, 1),
     ]
     for name, B, H, W, C, N, conv in shapes:
-        for bn in ((0, 256) if N % 256 == 0 or N >= 512 else (0,)):
-            ms, tf = bench(B, H, W, C, N, conv, bn=bn)
-            print(f"{name:36s} B={B:3d} bn={bn or 'auto':>4} {ms*1e3:9.1f} us {tf:8.1f} TFLOP/s", flush=True)
+        for ver in (1, 2):
+            for bn in ((0, 256) if (N % 256 == 0 and ver == 2) else (0,)):
+                ms, tf = bench(B, H, W, C, N, conv, bn=bn, ver=ver)
+                print(f"{name:36s} B={B:3d} v{ver} bn={bn or 'auto':>4} {ms*1e3:9.1f} us {tf:8.1f} TFLOP/s", flush=True)
