@@ -32,15 +32,18 @@ struct alignas(64) AttnKParams {
   int64_t out_ld;
 };
 
-template <int DKA, int DVP, int BKV, int ST>
+// SB = number of S accumulator buffers: 2 (double-buffered, one CTA per SM) or 1 (TMEM 256 columns and <= 113 KB of
+// shared memory, so TWO CTAs share an SM: one CTA's softmax overlaps the other's MMAs and both keep the MUFU pipe fed)
+template <int DKA, int DVP, int BKV, int ST, int SB>
 struct AttnCfg {
   static constexpr int Q_BYTES = DKA * ATT_BQ * 128;
   static constexpr int K_STAGE = DKA * BKV * 128;
   static constexpr int V_STAGE = (BKV / 64) * DVP * 128;
   static constexpr int P_BYTES = (BKV / 64) * ATT_BQ * 128;
   static constexpr int SMEM = Q_BYTES + P_BYTES + ST * (K_STAGE + V_STAGE) + 1024 + 256;
-  static constexpr int TMEM_COLS = 512;
-  static constexpr int O_COL = 2 * BKV;
+  static constexpr int TMEM_COLS = SB == 1 ? 256 : 512;
+  static constexpr int O_COL = SB * BKV;
+  static_assert(SB * BKV + DVP <= TMEM_COLS, "TMEM budget");
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -49,9 +52,10 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-template <int DKA, int DVP, int BKV, int ST>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_constant__ AttnKParams p) {
-  using Cfg = AttnCfg<DKA, DVP, BKV, ST>;
+template <int DKA, int DVP, int BKV, int ST, int SB>
+__global__ void __launch_bounds__(ATT_THREADS, SB == 1 ? 2 : 1)
+    attn_fwd_kernel(const __grid_constant__ AttnKParams p) {
+  using Cfg = AttnCfg<DKA, DVP, BKV, ST, SB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;
@@ -127,21 +131,23 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
         mbar_wait(&kv_full[s], (j / ST) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(k_smem + s * Cfg::K_STAGE);
-        const uint32_t ts = tmem + (j & 1) * BKV;
+        const uint32_t ts = tmem + (j % SB) * BKV;
         for (int ks = 0; ks < p.dk_steps; ++ks) {
           const uint64_t da = make_desc_k_sw128(q_addr + (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32);
           const uint64_t db = make_desc_k_sw128(k_addr + (ks >> 2) * (BKV * 128) + (ks & 3) * 32);
           umma_f16_ss(ts, da, db, idesc_s, ks != 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[j & 1]);
+        umma_commit(&s_full[j % SB]);
       };
       mbar_wait(q_full, 0);
       tc_fence_after();
       issue_s(0);
-      if (ntiles > 1) issue_s(1);
+      if (SB == 2 && ntiles > 1) issue_s(1);
       for (int j = 0; j < ntiles; ++j) {
         mbar_wait(p_ready, j & 1);
         tc_fence_after();
+        // single S buffer: the softmax has consumed S_j (p_ready), so S_{j+1} goes first and overlaps PV_j
+        if (SB == 1 && j + 1 < ntiles) issue_s(j + 1);
         const int s = j % ST;
         const uint32_t v_addr = smem_u32(v_smem + s * Cfg::V_STAGE);
 #pragma unroll
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
         }
         umma_commit(pv_done);
         umma_commit(&kv_empty[s]);
-        if (j + 2 < ntiles) issue_s(j + 2);
+        if (SB == 2 && j + 2 < ntiles) issue_s(j + 2);
       }
     }
   } else {
@@ -167,9 +173,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_kernel(const __grid_c
     const int sw = r & 7;
 
     for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&s_full[j % SB], (j / SB) & 1);
       tc_fence_after();
-      const uint32_t t_s = tmem + lane_base + (j & 1) * BKV;
+      const uint32_t t_s = tmem + lane_base + (j % SB) * BKV;
       float v[BKV];
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c) {
@@ -284,22 +290,22 @@ struct AttnLaunchImpl {
   int variant;
 };
 
-template <int DKA, int DVP, int BKV, int ST>
+template <int DKA, int DVP, int BKV, int ST, int SB>
 static int attn_set_attr() {
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<DKA, DVP, BKV, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   AttnCfg<DKA, DVP, BKV, ST>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<DKA, DVP, BKV, ST, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   AttnCfg<DKA, DVP, BKV, ST, SB>::SMEM));
   return 0;
 }
 
 static bool g_attn_init = false;
 static int attn_init() {
   if (g_attn_init) return 0;
-  if (int e = attn_set_attr<1, 16, 128, 2>()) return e;
-  if (int e = attn_set_attr<1, 32, 128, 2>()) return e;
-  if (int e = attn_set_attr<1, 48, 128, 2>()) return e;
-  if (int e = attn_set_attr<1, 64, 128, 2>()) return e;
-  if (int e = attn_set_attr<2, 80, 128, 2>()) return e;
-  if (int e = attn_set_attr<3, 160, 64, 3>()) return e;
+  if (int e = attn_set_attr<1, 16, 128, 2, 1>()) return e;
+  if (int e = attn_set_attr<1, 32, 128, 2, 1>()) return e;
+  if (int e = attn_set_attr<1, 48, 128, 2, 1>()) return e;
+  if (int e = attn_set_attr<1, 64, 128, 2, 1>()) return e;
+  if (int e = attn_set_attr<2, 80, 128, 2, 2>()) return e;
+  if (int e = attn_set_attr<3, 160, 64, 3, 2>()) return e;
   g_attn_init = true;
   return 0;
 }
@@ -363,12 +369,12 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
   if (int e = attn_init()) return e;
   const AttnLaunchImpl* I = reinterpret_cast<const AttnLaunchImpl*>(L.storage);
   switch (I->variant) {
-    case 0: attn_fwd_kernel<1, 16, 128, 2><<<I->grid, ATT_THREADS, AttnCfg<1, 16, 128, 2>::SMEM, stream>>>(I->p); break;
-    case 1: attn_fwd_kernel<1, 32, 128, 2><<<I->grid, ATT_THREADS, AttnCfg<1, 32, 128, 2>::SMEM, stream>>>(I->p); break;
-    case 2: attn_fwd_kernel<1, 48, 128, 2><<<I->grid, ATT_THREADS, AttnCfg<1, 48, 128, 2>::SMEM, stream>>>(I->p); break;
-    case 3: attn_fwd_kernel<1, 64, 128, 2><<<I->grid, ATT_THREADS, AttnCfg<1, 64, 128, 2>::SMEM, stream>>>(I->p); break;
-    case 4: attn_fwd_kernel<2, 80, 128, 2><<<I->grid, ATT_THREADS, AttnCfg<2, 80, 128, 2>::SMEM, stream>>>(I->p); break;
-    case 5: attn_fwd_kernel<3, 160, 64, 3><<<I->grid, ATT_THREADS, AttnCfg<3, 160, 64, 3>::SMEM, stream>>>(I->p); break;
+    case 0: attn_fwd_kernel<1, 16, 128, 2, 1><<<I->grid, ATT_THREADS, AttnCfg<1, 16, 128, 2, 1>::SMEM, stream>>>(I->p); break;
+    case 1: attn_fwd_kernel<1, 32, 128, 2, 1><<<I->grid, ATT_THREADS, AttnCfg<1, 32, 128, 2, 1>::SMEM, stream>>>(I->p); break;
+    case 2: attn_fwd_kernel<1, 48, 128, 2, 1><<<I->grid, ATT_THREADS, AttnCfg<1, 48, 128, 2, 1>::SMEM, stream>>>(I->p); break;
+    case 3: attn_fwd_kernel<1, 64, 128, 2, 1><<<I->grid, ATT_THREADS, AttnCfg<1, 64, 128, 2, 1>::SMEM, stream>>>(I->p); break;
+    case 4: attn_fwd_kernel<2, 80, 128, 2, 2><<<I->grid, ATT_THREADS, AttnCfg<2, 80, 128, 2, 2>::SMEM, stream>>>(I->p); break;
+    case 5: attn_fwd_kernel<3, 160, 64, 3, 2><<<I->grid, ATT_THREADS, AttnCfg<3, 160, 64, 3, 2>::SMEM, stream>>>(I->p); break;
     default: set_error("bad attention variant"); return 1;
   }
   SDW_CUDA_OK(cudaGetLastError());

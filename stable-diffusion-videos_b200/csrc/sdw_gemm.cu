@@ -304,16 +304,18 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
   // BLOCK_N choice
   int bn = d.bn;
   if (bn == 0 && ver == 2) {
-    // largest of {256, 160, 128} wasting < 10 % of the padded N (GEGLU needs 64-column pairs)
+    // persistent grid of 74 CTA pairs: pick the BLOCK_N in {256, 160, 128} minimising waves x tile time, where the
+    // tile time scales with BLOCK_N and smaller tiles pay more operand bytes per FLOP (GEGLU needs 64-column pairs)
     const int cand[3] = {256, 160, 128};
+    const int mp = (m_tiles + 1) / 2;
     int best = 128;
     double best_cost = 1e30;
     for (int c : cand) {
       if (d.mode == GEMM_GEGLU && c % 64 != 0) continue;
-      const int tiles = (d.N + c - 1) / c;
-      const double waste = static_cast<double>(tiles) * c / d.N;
-      const double eff = c == 256 ? 1.0 : (c == 160 ? 1.12 : 1.2);  // smaller tiles pay more L2 bytes per FLOP
-      const double cost = waste * eff;
+      const int tiles = mp * ((d.N + c - 1) / c);
+      const int waves = (tiles + 73) / 74;
+      const double eff = c == 256 ? 1.0 : (c == 160 ? 1.12 : 1.2);
+      const double cost = static_cast<double>(waves) * c * eff;
       if (cost < best_cost) {
         best_cost = cost;
         best = c;

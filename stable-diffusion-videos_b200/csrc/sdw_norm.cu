@@ -129,10 +129,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
   const int64_t items = (p1 - p0) * vecs;
   const __half* xb = x + static_cast<int64_t>(b) * P * ldx;
   __half* yb = y + static_cast<int64_t>(b) * P * ldy;
-  for (int64_t it = threadIdx.x; it < items; it += blockDim.x) {
-    const int v = static_cast<int>(it % vecs);
-    const int64_t p = p0 + it / vecs;
-    const uint4 u = *reinterpret_cast<const uint4*>(xb + p * ldx + v * 8);
+  auto apply8 = [&](const uint4& u, int v, int64_t p) {
     const __half2* h = reinterpret_cast<const __half2*>(&u);
     float o[8];
 #pragma unroll
@@ -141,11 +138,16 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
       o[2 * j] = f.x;
       o[2 * j + 1] = f.y;
     }
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = v * 8 + j;
-      const int g = c / cg;
-      float t = (o[j] - s_mean[g]) * s_rstd[g] * __ldg(&gamma[c]) + __ldg(&beta[c]);
+      const int g = (v * 8 + j) / cg;
+      float t = (o[j] - s_mean[g]) * s_rstd[g] * gg[j] + bb[j];
       if (silu) t = silu_f(t);
       o[j] = t;
     }
@@ -155,6 +157,27 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
     w.z = pack_h2(o[4], o[5]);
     w.w = pack_h2(o[6], o[7]);
     *reinterpret_cast<uint4*>(yb + p * ldy + v * 8) = w;
+  };
+  // 4 independent 16-byte loads in flight per thread
+  int64_t it = threadIdx.x;
+  for (; it + 3 * blockDim.x < items; it += 4 * blockDim.x) {
+    uint4 u[4];
+    int vv[4];
+    int64_t pp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t i2 = it + k * blockDim.x;
+      vv[k] = static_cast<int>(i2 % vecs);
+      pp[k] = p0 + i2 / vecs;
+      u[k] = *reinterpret_cast<const uint4*>(xb + pp[k] * ldx + vv[k] * 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) apply8(u[k], vv[k], pp[k]);
+  }
+  for (; it < items; it += blockDim.x) {
+    const int v = static_cast<int>(it % vecs);
+    const int64_t p = p0 + it / vecs;
+    apply8(*reinterpret_cast<const uint4*>(xb + p * ldx + v * 8), v, p);
   }
 }
 
