@@ -112,7 +112,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--frames-per-call", type=int, default=int(os.environ.get("SDW_BENCH_F", "4")))
+    ap.add_argument("--frames-per-call", type=int, default=int(os.environ.get("SDW_BENCH_F", "16")))
     ap.add_argument("--inference-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
