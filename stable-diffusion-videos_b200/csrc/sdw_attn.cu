@@ -52,6 +52,20 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// 2^t for t <= 0 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax, max rel. error 7.5e-5 — below the fp16
+// rounding of P): the MUFU pipe (16 ex2/clk/SM) is the attention bottleneck at head dim 40, so every 4th score is
+// exponentiated here instead (the split FlashAttention-4 uses).
+__device__ __forceinline__ float ex2_poly(float t) {
+  t = fmaxf(t, -126.f);
+  const float xr = __fadd_rd(t, 12582912.f);  // 1.5 * 2^23: the low mantissa bits now hold floor(t)
+  const float f = t - (xr - 12582912.f);       // fractional part in [0, 1)
+  float q = fmaf(f, 0.0780244991f, 0.2260671854f);
+  q = fmaf(q, f, 0.6958335042f);
+  q = fmaf(q, f, 0.9999251962f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(xr) << 23));
+}
+static constexpr int ATT_POLY_EVERY = 4;
+
 template <int DKA, int DVP, int BKV, int ST, int SB>
 __global__ void __launch_bounds__(ATT_THREADS, SB == 1 ? 2 : 1)
     attn_fwd_kernel(const __grid_constant__ AttnKParams p) {
@@ -200,7 +214,8 @@ __global__ void __launch_bounds__(ATT_THREADS, SB == 1 ? 2 : 1)
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < BKV; ++i) {
-        v[i] = ex2f(fmaf(v[i], sl2, -mb));
+        const float t = fmaf(v[i], sl2, -mb);
+        v[i] = (i % ATT_POLY_EVERY == ATT_POLY_EVERY - 1) ? ex2_poly(t) : ex2f(t);
         sum += v[i];
       }
       l_run = fmaf(l_run, alpha, sum);

@@ -11,7 +11,7 @@
 //                         signalled on the LEADER's full barrier (cta_group::2 TMA, mapa'd barrier address).
 //   warp 1 (leader)     : MMA issuer, 4 x UMMA(M=256, N=BN, K=16) per K block; tcgen05.commit multicast frees the
 //                         smem stage in both CTAs / publishes the accumulator to both epilogues.
-//   warps 2-5 (both)    : epilogue on the CTA's own 128 rows (sdw_gemm_epi.cuh), then a remote arrive on the
+//   warps 2-9 (both)    : epilogue on the CTA's own 128 rows, two warps per TMEM lane quarter (sdw_gemm_epi.cuh), then a remote arrive on the
 //                         leader's tmem_empty barrier.
 #include "sdw_gemm_epi.cuh"
 #include "sdw_internal.h"
@@ -19,7 +19,7 @@
 
 namespace sdw {
 
-static constexpr int G2_THREADS = 192;
+static constexpr int G2_THREADS = 320;  // producer, MMA, 8 epilogue warps (two per TMEM lane quarter)
 static constexpr int G2_A_STAGE = 128 * 64 * 2;
 
 template <int BN>
@@ -63,7 +63,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 8);  // 4 epilogue warps x 2 CTAs
+      mbar_init(&tmem_empty[a], 16);  // 8 epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -149,7 +149,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
       int x0, y0, b0, n0;
       tile_coords(t, x0, y0, b0, n0);
       const int a = it & 1;
-      gemm_epilogue<BN>(p, tmem_base + a * BN, warp, lane, x0, y0, b0, n0, &tmem_full[a], (it >> 1) & 1);
+      // the two warps of a lane quarter interleave 32-column chunks: twice the loads / stores in flight
+      gemm_epilogue<BN>(p, tmem_base + a * BN, warp, lane, x0, y0, b0, n0, &tmem_full[a], (it >> 1) & 1,
+                        (warp - 2) >> 2, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[a]), 0));

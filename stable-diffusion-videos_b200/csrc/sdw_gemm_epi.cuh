@@ -73,55 +73,76 @@ __device__ __forceinline__ void epi_vt_chunk(const GemmKParams& p, const uint32_
   }
 }
 
+// The residual tile is fetched one chunk AHEAD (16 registers) so its L2/DRAM latency overlaps the previous chunk's
+// TMEM load, math and stores; bias / time-embedding rows are L1-resident across the tiles of a persistent CTA.
+template <int FLAGS>
+__device__ __forceinline__ void epi_res_load(uint4 (&rs)[4], int n, int nvalid, bool row_ok, const __half* res_row) {
+  if (FLAGS & 4) {
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8)
+      if (j8 * 8 < nvalid && row_ok) rs[j8] = *reinterpret_cast<const uint4*>(res_row + n + j8 * 8);
+  }
+}
+
 template <int BN, int FLAGS>
 __device__ __forceinline__ void epi_fast(const GemmKParams& p, uint32_t taddr, int n0, bool row_ok, int64_t pix_in,
-                                         __half* out_row, const __half* res_row, const float* rowvec) {
+                                         __half* out_row, const __half* res_row, const float* rowvec, int chunk0,
+                                         int chunk_step) {
   const int nmax = min(BN, p.N - n0);  // valid columns of this tile (multiple of 8)
+  const bool vt_mode = p.mode == GEMM_QKV_VT;
+  uint4 rs_cur[4], rs_nxt[4];
+  int c = chunk0;
+  if (c * 32 < nmax) epi_res_load<FLAGS>(rs_cur, n0 + c * 32, nmax - c * 32, row_ok, res_row);
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    if (c * 32 >= nmax) break;
+  for (; c * 32 < nmax; c += chunk_step) {
     uint32_t v[32];
     tmem_ld_32x32(taddr + c * 32, v);
+    const int cn = c + chunk_step;
+    if (cn * 32 < nmax) epi_res_load<FLAGS>(rs_nxt, n0 + cn * 32, nmax - cn * 32, row_ok, res_row);
     tmem_ld_wait();
-    if (!row_ok) continue;
     const int n = n0 + c * 32;
-    if (p.mode == GEMM_QKV_VT && n >= p.vt_col0) {
-      epi_vt_chunk(p, v, n, pix_in);
-      continue;
-    }
+    if (row_ok) {
+      if (vt_mode && n >= p.vt_col0) {
+        epi_vt_chunk(p, v, n, pix_in);
+      } else {
 #pragma unroll
-    for (int j8 = 0; j8 < 4; ++j8) {
-      if (c * 32 + j8 * 8 < nmax) {
-        const int nn = n + j8 * 8;
-        float o[8];
+        for (int j8 = 0; j8 < 4; ++j8) {
+          if (c * 32 + j8 * 8 < nmax) {
+            const int nn = n + j8 * 8;
+            float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          o[j] = __uint_as_float(v[j8 * 8 + j]);
-          if (FLAGS & 16) o[j] *= p.alpha;
-        }
-        if (FLAGS & 1) add8(o, p.bias + nn);
-        if (FLAGS & 2) add8(o, rowvec + nn);
-        if (FLAGS & 8) {
+            for (int j = 0; j < 8; ++j) {
+              o[j] = __uint_as_float(v[j8 * 8 + j]);
+              if (FLAGS & 16) o[j] *= p.alpha;
+            }
+            if (FLAGS & 1) add8(o, p.bias + nn);
+            if (FLAGS & 2) add8(o, rowvec + nn);
+            if (FLAGS & 8) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = silu_f(o[j]);
-        }
-        if (FLAGS & 4) {
-          const uint4 u = *reinterpret_cast<const uint4*>(res_row + nn);
-          const __half2* h = reinterpret_cast<const __half2*>(&u);
+              for (int j = 0; j < 8; ++j) o[j] = silu_f(o[j]);
+            }
+            if (FLAGS & 4) {
+              const __half2* h = reinterpret_cast<const __half2*>(&rs_cur[j8]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(h[j]);
-            o[2 * j] += f.x;
-            o[2 * j + 1] += f.y;
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h[j]);
+                o[2 * j] += f.x;
+                o[2 * j + 1] += f.y;
+              }
+            }
+            uint4 w;
+            w.x = pack_h2(o[0], o[1]);
+            w.y = pack_h2(o[2], o[3]);
+            w.z = pack_h2(o[4], o[5]);
+            w.w = pack_h2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(out_row + nn) = w;
           }
         }
-        uint4 w;
-        w.x = pack_h2(o[0], o[1]);
-        w.y = pack_h2(o[2], o[3]);
-        w.z = pack_h2(o[4], o[5]);
-        w.w = pack_h2(o[6], o[7]);
-        *reinterpret_cast<uint4*>(out_row + nn) = w;
       }
+    }
+    if (FLAGS & 4) {
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) rs_cur[j8] = rs_nxt[j8];
     }
   }
 }
@@ -129,9 +150,9 @@ __device__ __forceinline__ void epi_fast(const GemmKParams& p, uint32_t taddr, i
 // GEGLU: packed columns [32 value | 32 gate] pairs -> 32 outputs a * gelu(g)
 template <int BN>
 __device__ __forceinline__ void epi_geglu(const GemmKParams& p, uint32_t taddr, int n0, bool row_ok, __half* out_row,
-                                          bool vec_out) {
+                                          bool vec_out, int chunk0, int chunk_step) {
 #pragma unroll 1
-  for (int c = 0; c < BN / 64; ++c) {
+  for (int c = chunk0; c < BN / 64; c += chunk_step) {
     const int n = n0 + c * 64;
     if (n >= p.N) break;
     uint32_t va[32], vg[32];
@@ -163,7 +184,8 @@ __device__ __forceinline__ void epi_geglu(const GemmKParams& p, uint32_t taddr, 
 // warp = absolute warp index of an epilogue warp (its TMEM lane quarter is warp & 3); tmem_acc = accumulator base.
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, uint32_t tmem_acc, int warp, int lane, int x0,
-                                              int y0, int b0, int n0, uint64_t* tmem_full_bar, uint32_t full_parity = 0) {
+                                              int y0, int b0, int n0, uint64_t* tmem_full_bar, uint32_t full_parity = 0,
+                                              int chunk0 = 0, int chunk_step = 1) {
   const int quarter = warp & 3;  // TMEM lane quarter this warp may read
   const int r = quarter * 32 + lane;
   const int lx = r % p.bw;
@@ -187,7 +209,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, uint32_t tme
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
 
   if (p.mode == GEMM_GEGLU) {
-    epi_geglu<BN>(p, taddr, n0, row_ok, out_row, vec_out);
+    epi_geglu<BN>(p, taddr, n0, row_ok, out_row, vec_out, chunk0, chunk_step);
     return;
   }
   const bool fast = vec_out && (!p.resid || vec_res) && ((p.N & 7) == 0) &&
@@ -197,17 +219,17 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, uint32_t tme
     const int flags = (p.bias ? 1 : 0) | (p.rowvec ? 2 : 0) | (p.resid ? 4 : 0) | (p.act == 1 ? 8 : 0) |
                       (p.alpha != 1.f ? 16 : 0);
     switch (flags) {
-      case 0: epi_fast<BN, 0>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec); return;
-      case 1: epi_fast<BN, 1>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec); return;
-      case 3: epi_fast<BN, 3>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec); return;
-      case 5: epi_fast<BN, 5>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec); return;
-      case 16: epi_fast<BN, 16>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec); return;
+      case 0: epi_fast<BN, 0>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step); return;
+      case 1: epi_fast<BN, 1>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step); return;
+      case 3: epi_fast<BN, 3>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step); return;
+      case 5: epi_fast<BN, 5>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step); return;
+      case 16: epi_fast<BN, 16>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step); return;
       default: break;
     }
   }
   // ---- generic path (unaligned views, odd N, rarely used flag combinations) --------------------
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = chunk0; c < BN / 32; c += chunk_step) {
     const int n = n0 + c * 32;
     if (n >= p.N) break;
     uint32_t v[32];

@@ -144,12 +144,17 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
     const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    int g = (v * 8) / cg;          // one division per 8 channels; the group index then advances incrementally
+    int rem = v * 8 - g * cg;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (v * 8 + j) / cg;
       float t = (o[j] - s_mean[g]) * s_rstd[g] * gg[j] + bb[j];
-      if (silu) t = silu_f(t);
+      if (silu) t = __fdividef(t, 1.f + __expf(-t));
       o[j] = t;
+      if (++rem == cg) {
+        rem = 0;
+        ++g;
+      }
     }
     uint4 w;
     w.x = pack_h2(o[0], o[1]);
@@ -221,64 +226,79 @@ int groupnorm(const __half* x, int64_t ldx, int B, int64_t P, int C, int G, cons
 // =============================================================================================
 // LayerNorm over the channel dim: one warp per token row, fp32 two-pass in registers.
 // =============================================================================================
-template <int MAXV>  // 16-byte vectors per lane
+template <int MAXV, int R>  // 16-byte vectors per lane per row, rows per warp (independent loads in flight)
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int64_t ldx, int64_t rows,
                                                         int C, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
                                                         __half* __restrict__ y, int64_t ldy) {
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
   const int lane = threadIdx.x & 31;
   const int vecs = C / 8;
-  float v[MAXV][8];
-  float sum = 0.f;
+  uint4 u[R][MAXV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < vecs) {
-      const uint4 u = *reinterpret_cast<const uint4*>(x + row * ldx + vi * 8);
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
+  for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h[j]);
-        v[i][2 * j] = f.x;
-        v[i][2 * j + 1] = f.y;
-        sum += f.x + f.y;
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < vecs && row0 + r < rows) u[r][i] = *reinterpret_cast<const uint4*>(x + (row0 + r) * ldx + vi * 8);
+    }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int64_t row = row0 + r;
+    if (row >= rows) break;  // warp-uniform
+    float v[MAXV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < vecs) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u[r][i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          v[i][2 * j] = f.x;
+          v[i][2 * j + 1] = f.y;
+          sum += f.x + f.y;
+        }
       }
     }
-  }
-  sum = warp_sum(sum);
-  const float mean = sum / C;
-  float sq = 0.f;
+    sum = warp_sum(sum);
+    const float mean = sum / C;
+    float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < vecs) {
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < vecs) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[i][j] - mean;
-        sq = fmaf(d, d, sq);
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          sq = fmaf(d, d, sq);
+        }
       }
     }
-  }
-  sq = warp_sum(sq);
-  const float rstd = rsqrtf(sq / C + eps);
+    sq = warp_sum(sq);
+    const float rstd = rsqrtf(sq / C + eps);
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < vecs) {
-      float o[8];
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < vecs) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8) + 1);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = vi * 8 + j;
-        o[j] = (v[i][j] - mean) * rstd * __ldg(&gamma[c]) + __ldg(&beta[c]);
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
+        uint4 w;
+        w.x = pack_h2(o[0], o[1]);
+        w.y = pack_h2(o[2], o[3]);
+        w.z = pack_h2(o[4], o[5]);
+        w.w = pack_h2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(y + row * ldy + vi * 8) = w;
       }
-      uint4 w;
-      w.x = pack_h2(o[0], o[1]);
-      w.y = pack_h2(o[2], o[3]);
-      w.z = pack_h2(o[4], o[5]);
-      w.w = pack_h2(o[6], o[7]);
-      *reinterpret_cast<uint4*>(y + row * ldy + vi * 8) = w;
     }
   }
 }
@@ -286,14 +306,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
 int layernorm(const __half* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
               __half* y, int64_t ldy, cudaStream_t stream) {
   SDW_REQUIRE(C % 8 == 0 && C <= 8 * 32 * 8, "LayerNorm: C % 8 == 0 and C <= 2048");
-  const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
   const int vecs = C / 8;
-  if (vecs <= 64)
-    layernorm_kernel<2><<<blocks, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, y, ldy);
-  else if (vecs <= 160)
-    layernorm_kernel<5><<<blocks, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, y, ldy);
-  else
-    layernorm_kernel<8><<<blocks, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, y, ldy);
+  if (vecs <= 64) {
+    const unsigned blocks = static_cast<unsigned>((rows + 31) / 32);
+    layernorm_kernel<2, 4><<<blocks, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, y, ldy);
+  } else if (vecs <= 160) {
+    const unsigned blocks = static_cast<unsigned>((rows + 15) / 16);
+    layernorm_kernel<5, 2><<<blocks, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, y, ldy);
+  } else {
+    const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+    layernorm_kernel<8, 1><<<blocks, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, y, ldy);
+  }
   SDW_CUDA_OK(cudaGetLastError());
   return 0;
 }
