@@ -11,7 +11,7 @@
 //                         signalled on the LEADER's full barrier (cta_group::2 TMA, mapa'd barrier address).
 //   warp 1 (leader)     : MMA issuer, 4 x UMMA(M=256, N=BN, K=16) per K block; tcgen05.commit multicast frees the
 //                         smem stage in both CTAs / publishes the accumulator to both epilogues.
-//   warps 2-9 (both)    : epilogue on the CTA's own 128 rows, two warps per TMEM lane quarter (sdw_gemm_epi.cuh), then a remote arrive on the
+//   warps 4-11 (both)   : epilogue on the CTA's own 128 rows, two warps per TMEM lane quarter (sdw_gemm_epi.cuh), then a remote arrive on the
 //                         leader's tmem_empty barrier.
 #include "sdw_gemm_epi.cuh"
 #include "sdw_internal.h"
@@ -19,7 +19,7 @@
 
 namespace sdw {
 
-static constexpr int G2_THREADS = 320;  // producer, MMA, 8 epilogue warps (two per TMEM lane quarter)
+static constexpr int G2_THREADS = 384;  // warpgroup 0: producer, MMA (+2 idle warps); warpgroups 1-2: 8 epilogue warps
 static constexpr int G2_A_STAGE = 128 * 64 * 2;
 
 template <int BN>
@@ -28,7 +28,8 @@ struct Gemm2Cfg {
   static constexpr int B_STAGE = BH * 128;
   static constexpr int STAGES = BN == 256 ? 6 : (BN == 160 ? 7 : 8);
   static constexpr int TMEM_COLS = BN <= 128 ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * (G2_A_STAGE + B_STAGE) + 1024 + 256;
+  static constexpr int EPI_STAGE = 8 * 2048;  // 2 KB store-coalescing buffer per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * (G2_A_STAGE + B_STAGE) + EPI_STAGE + 1024 + 256;
 };
 
 template <int BN>
@@ -40,7 +41,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * G2_A_STAGE;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * Cfg::B_STAGE);
+  uint8_t* epi_stage = smem_b + STAGES * Cfg::B_STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + Cfg::EPI_STAGE);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]  (leader's copy is the one in use)
@@ -75,7 +77,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-
   auto tile_coords = [&](int t, int& x0, int& y0, int& b0, int& n0) {
     const int m_pair = t % p.m_pairs;
     const int n_tile = t / p.m_pairs;
@@ -142,7 +143,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
         umma_commit_2cta(&tmem_full[a], 0b11);
       }
     }
-  } else {
+  } else if (warp >= 4) {
     // =========================== epilogue (both CTAs, own 128 rows) ==================
     int it = 0;
     for (int t = cluster_id; t < total_tiles; t += nclusters, ++it) {
@@ -151,7 +152,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
       const int a = it & 1;
       // the two warps of a lane quarter interleave 32-column chunks: twice the loads / stores in flight
       gemm_epilogue<BN>(p, tmem_base + a * BN, warp, lane, x0, y0, b0, n0, &tmem_full[a], (it >> 1) & 1,
-                        (warp - 2) >> 2, 2);
+                        (warp - 4) >> 2, 2, epi_stage + (warp - 4) * 2048);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[a]), 0));

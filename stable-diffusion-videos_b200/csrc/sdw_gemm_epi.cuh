@@ -73,6 +73,31 @@ __device__ __forceinline__ void epi_vt_chunk(const GemmKParams& p, const uint32_
   }
 }
 
+// Coalescing stage: the row-owner layout (thread = output row) would store 16 B per lane into 32 different cache lines
+// per instruction.  Instead each warp bounces a 32-row x 64-byte chunk through 2 KB of shared memory (XOR-swizzled,
+// conflict-free both ways) and writes it back with 4 lanes per row: 8 full 64-byte row segments per store instruction.
+//   w[j8]      : this lane's row, 8 fp16 columns each (j8 < npieces valid)
+//   row_off    : element offset of this lane's output row, or -1 if the row is out of range
+__device__ __forceinline__ void staged_store32(uint8_t* stage, int lane, const uint4 (&w)[4], int npieces,
+                                               int64_t row_off, __half* out, int col) {
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j8 = 0; j8 < 4; ++j8)
+    if (j8 < npieces && row_off >= 0) *reinterpret_cast<uint4*>(stage + lane * 64 + ((j8 ^ sw) << 4)) = w[j8];
+  __syncwarp();
+  const int piece = lane & 3;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2);
+    const int64_t off = __shfl_sync(0xffffffffu, row_off, row);
+    if (off >= 0 && piece < npieces) {
+      const uint4 u = *reinterpret_cast<const uint4*>(stage + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
+      *reinterpret_cast<uint4*>(out + off + col + piece * 8) = u;
+    }
+  }
+  __syncwarp();
+}
+
 // The residual tile is fetched one chunk AHEAD (16 registers) so its L2/DRAM latency overlaps the previous chunk's
 // TMEM load, math and stores; bias / time-embedding rows are L1-resident across the tiles of a persistent CTA.
 template <int FLAGS>
@@ -87,9 +112,10 @@ __device__ __forceinline__ void epi_res_load(uint4 (&rs)[4], int n, int nvalid, 
 template <int BN, int FLAGS>
 __device__ __forceinline__ void epi_fast(const GemmKParams& p, uint32_t taddr, int n0, bool row_ok, int64_t pix_in,
                                          __half* out_row, const __half* res_row, const float* rowvec, int chunk0,
-                                         int chunk_step) {
+                                         int chunk_step, uint8_t* stage, int lane, int64_t out_off) {
   const int nmax = min(BN, p.N - n0);  // valid columns of this tile (multiple of 8)
   const bool vt_mode = p.mode == GEMM_QKV_VT;
+  const int64_t row_off = row_ok ? out_off : -1;
   uint4 rs_cur[4], rs_nxt[4];
   int c = chunk0;
   if (c * 32 < nmax) epi_res_load<FLAGS>(rs_cur, n0 + c * 32, nmax - c * 32, row_ok, res_row);
@@ -101,27 +127,29 @@ __device__ __forceinline__ void epi_fast(const GemmKParams& p, uint32_t taddr, i
     if (cn * 32 < nmax) epi_res_load<FLAGS>(rs_nxt, n0 + cn * 32, nmax - cn * 32, row_ok, res_row);
     tmem_ld_wait();
     const int n = n0 + c * 32;
-    if (row_ok) {
-      if (vt_mode && n >= p.vt_col0) {
-        epi_vt_chunk(p, v, n, pix_in);
-      } else {
+    if (vt_mode && n >= p.vt_col0) {
+      if (row_ok) epi_vt_chunk(p, v, n, pix_in);
+    } else {
+      uint4 w[4];
+      const int npieces = min(4, (nmax - c * 32) >> 3);
 #pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          if (c * 32 + j8 * 8 < nmax) {
-            const int nn = n + j8 * 8;
-            float o[8];
+      for (int j8 = 0; j8 < 4; ++j8) {
+        if (j8 < npieces) {
+          const int nn = n + j8 * 8;
+          float o[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              o[j] = __uint_as_float(v[j8 * 8 + j]);
-              if (FLAGS & 16) o[j] *= p.alpha;
-            }
-            if (FLAGS & 1) add8(o, p.bias + nn);
-            if (FLAGS & 2) add8(o, rowvec + nn);
-            if (FLAGS & 8) {
+          for (int j = 0; j < 8; ++j) {
+            o[j] = __uint_as_float(v[j8 * 8 + j]);
+            if (FLAGS & 16) o[j] *= p.alpha;
+          }
+          if (FLAGS & 1) add8(o, p.bias + nn);
+          if (FLAGS & 2) add8(o, rowvec + nn);
+          if (FLAGS & 8) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = silu_f(o[j]);
-            }
-            if (FLAGS & 4) {
+            for (int j = 0; j < 8; ++j) o[j] = silu_f(o[j]);
+          }
+          if (FLAGS & 4) {
+            if (row_ok) {
               const __half2* h = reinterpret_cast<const __half2*>(&rs_cur[j8]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -130,14 +158,19 @@ __device__ __forceinline__ void epi_fast(const GemmKParams& p, uint32_t taddr, i
                 o[2 * j + 1] += f.y;
               }
             }
-            uint4 w;
-            w.x = pack_h2(o[0], o[1]);
-            w.y = pack_h2(o[2], o[3]);
-            w.z = pack_h2(o[4], o[5]);
-            w.w = pack_h2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(out_row + nn) = w;
           }
+          w[j8].x = pack_h2(o[0], o[1]);
+          w[j8].y = pack_h2(o[2], o[3]);
+          w[j8].z = pack_h2(o[4], o[5]);
+          w[j8].w = pack_h2(o[6], o[7]);
         }
+      }
+      if (stage) {
+        staged_store32(stage, lane, w, npieces, row_off, p.out, n);
+      } else if (row_ok) {
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8)
+          if (j8 < npieces) *reinterpret_cast<uint4*>(out_row + n + j8 * 8) = w[j8];
       }
     }
     if (FLAGS & 4) {
@@ -150,33 +183,55 @@ __device__ __forceinline__ void epi_fast(const GemmKParams& p, uint32_t taddr, i
 // GEGLU: packed columns [32 value | 32 gate] pairs -> 32 outputs a * gelu(g)
 template <int BN>
 __device__ __forceinline__ void epi_geglu(const GemmKParams& p, uint32_t taddr, int n0, bool row_ok, __half* out_row,
-                                          bool vec_out, int chunk0, int chunk_step) {
+                                          bool vec_out, int chunk0, int chunk_step, uint8_t* stage, int lane,
+                                          int64_t out_off) {
+  const int64_t row_off = row_ok ? out_off : -1;
 #pragma unroll 1
   for (int c = chunk0; c < BN / 64; c += chunk_step) {
     const int n = n0 + c * 64;
     if (n >= p.N) break;
-    uint32_t va[32], vg[32];
-    tmem_ld_32x32(taddr + c * 64, va);
-    tmem_ld_32x32(taddr + c * 64 + 32, vg);
-    tmem_ld_wait();
-    if (!row_ok) continue;
-    __half* dst = out_row + n / 2;
+    uint4 w[4];
 #pragma unroll
-    for (int j8 = 0; j8 < 4; ++j8) {
-      float a[8], g[8];
+    for (int half = 0; half < 2; ++half) {  // 16 + 16 columns at a time keeps the live register set small
+      uint32_t va[16], vg[16];
+      tmem_ld_32x16(taddr + c * 64 + half * 16, va);
+      tmem_ld_32x16(taddr + c * 64 + 32 + half * 16, vg);
+      tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a[j] = __uint_as_float(va[j8 * 8 + j]) * p.alpha;
-        g[j] = __uint_as_float(vg[j8 * 8 + j]) * p.alpha;
+      for (int q = 0; q < 2; ++q) {
+        const int j8 = half * 2 + q;
+        float a[8], g[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a[j] = __uint_as_float(va[q * 8 + j]) * p.alpha;
+          g[j] = __uint_as_float(vg[q * 8 + j]) * p.alpha;
+        }
+        if (p.bias) {
+          add8(a, p.bias + n + j8 * 8);
+          add8(g, p.bias + n + 32 + j8 * 8);
+        }
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = a[j] * gelu_fast_f(g[j]);
+        w[j8].x = pack_h2(o[0], o[1]);
+        w[j8].y = pack_h2(o[2], o[3]);
+        w[j8].z = pack_h2(o[4], o[5]);
+        w[j8].w = pack_h2(o[6], o[7]);
       }
-      if (p.bias) {
-        add8(a, p.bias + n + j8 * 8);
-        add8(g, p.bias + n + 32 + j8 * 8);
-      }
-      float o[8];
+    }
+    if (stage && vec_out) {
+      staged_store32(stage, lane, w, 4, row_off, p.out, n / 2);
+    } else if (row_ok) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = a[j] * gelu_erf_f(g[j]);
-      store8(dst + j8 * 8, o, vec_out, 8);
+      for (int j8 = 0; j8 < 4; ++j8) {
+        if (vec_out) {
+          *reinterpret_cast<uint4*>(out_row + n / 2 + j8 * 8) = w[j8];
+        } else {
+          const __half* h = reinterpret_cast<const __half*>(&w[j8]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) out_row[n / 2 + j8 * 8 + j] = h[j];
+        }
+      }
     }
   }
 }
@@ -185,7 +240,7 @@ __device__ __forceinline__ void epi_geglu(const GemmKParams& p, uint32_t taddr, 
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, uint32_t tmem_acc, int warp, int lane, int x0,
                                               int y0, int b0, int n0, uint64_t* tmem_full_bar, uint32_t full_parity = 0,
-                                              int chunk0 = 0, int chunk_step = 1) {
+                                              int chunk0 = 0, int chunk_step = 1, uint8_t* stage = nullptr) {
   const int quarter = warp & 3;  // TMEM lane quarter this warp may read
   const int r = quarter * 32 + lane;
   const int lx = r % p.bw;
@@ -209,7 +264,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, uint32_t tme
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
 
   if (p.mode == GEMM_GEGLU) {
-    epi_geglu<BN>(p, taddr, n0, row_ok, out_row, vec_out, chunk0, chunk_step);
+    epi_geglu<BN>(p, taddr, n0, row_ok, out_row, vec_out, chunk0, chunk_step, stage, lane, out_off);
     return;
   }
   const bool fast = vec_out && (!p.resid || vec_res) && ((p.N & 7) == 0) &&
@@ -219,11 +274,11 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, uint32_t tme
     const int flags = (p.bias ? 1 : 0) | (p.rowvec ? 2 : 0) | (p.resid ? 4 : 0) | (p.act == 1 ? 8 : 0) |
                       (p.alpha != 1.f ? 16 : 0);
     switch (flags) {
-      case 0: epi_fast<BN, 0>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step); return;
-      case 1: epi_fast<BN, 1>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step); return;
-      case 3: epi_fast<BN, 3>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step); return;
-      case 5: epi_fast<BN, 5>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step); return;
-      case 16: epi_fast<BN, 16>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step); return;
+      case 0: epi_fast<BN, 0>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off); return;
+      case 1: epi_fast<BN, 1>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off); return;
+      case 3: epi_fast<BN, 3>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off); return;
+      case 5: epi_fast<BN, 5>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off); return;
+      case 16: epi_fast<BN, 16>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off); return;
       default: break;
     }
   }
