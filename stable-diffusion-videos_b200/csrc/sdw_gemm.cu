@@ -336,6 +336,12 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
   if (d.mode == GEMM_QKV_VT) SDW_REQUIRE(d.vt && d.vt_col0 % 32 == 0 && d.vt_d > 0, "bad V^T split");
   L->bn = bn;
   L->grid = dim3(m_tiles, (d.N + bn - 1) / bn, 1);
+  {
+    // store staging pays off when the epilogue, not the mainloop, bounds the tile (short K, wide N)
+    static const int stage_env = [] { const char* e = std::getenv("SDW_STAGE"); return e ? std::atoi(e) : -1; }();
+    const int kblocks = p.ntaps * kchunks;
+    p.stage_stores = stage_env >= 0 ? stage_env : (kblocks <= 10 && d.N >= 640 ? 1 : 0);
+  }
   if (ver == 2) {
     p.m_pairs = (m_tiles + 1) / 2;
     p.n_tiles = (d.N + bn - 1) / bn;

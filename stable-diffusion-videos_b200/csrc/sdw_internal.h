@@ -54,6 +54,7 @@ struct alignas(64) GemmKParams {
   int tiles_w, tiles_h;     // tiles per (w,h); tiles along b = gridDim.x / (tiles_w*tiles_h)
   int N;                    // GEMM N (packed columns)
   int b_batched;            // 1: weight map coords (.., y0, b0) = lattice (h, b) (batched matmul)
+  int stage_stores;         // 1: bounce output chunks through shared memory for coalesced stores (wide-N GEMMs)
   int m_pairs, n_tiles;     // 2-CTA persistent kernel: tile grid (pairs of 128-row M tiles x BN-wide N tiles)
   // epilogue
   const float* bias;        // [N] or null

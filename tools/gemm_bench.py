@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stable_diffusion_videos_b200 import _native as n  # noqa: E402
 
 
-def bench(B, H, W, C, N, conv, iters=20, bn=0, ver=0):
+def bench(B, H, W, C, N, conv, iters=20, bn=0, ver=0, epi=False):
     x = torch.randn(B, H, W, C, device="cuda").half()
     k = 3 if conv else 1
     w = (torch.randn(N, C, k, k, device="cuda") * (C * k * k) ** -0.5).half()
@@ -22,6 +22,10 @@ def bench(B, H, W, C, N, conv, iters=20, bn=0, ver=0):
     d.Wt = wp.data_ptr(); d.N = N
     d.out = out.data_ptr(); d.ldc = N
     d.alpha = 1.0; d.bn = bn; d.ver = ver
+    if epi:  # bias + residual epilogue, as the ResBlock conv2 / attention out-projections run
+        bias = torch.randn(N, device="cuda")
+        resid = torch.randn(B, H, W, N, device="cuda").half()
+        d.bias = bias.data_ptr(); d.resid = resid.data_ptr(); d.ldr = N
     for _ in range(3):
         n.gemm(d)
     torch.cuda.synchronize()
@@ -53,7 +57,9 @@ if __name__ == "__main__":
         ("vae conv3x3 512x512 128->128", F, 512, 512, 128, 128, 1),
     ]
     for name, B, H, W, C, N, conv in shapes:
-        for ver in (1, 2):
+        for ver in ((1, 2) if os.environ.get('BOTH') else (2,)):
             for bn in ((0, 256) if (N % 256 == 0 and ver == 2) else (0,)):
-                ms, tf = bench(B, H, W, C, N, conv, bn=bn, ver=ver)
-                print(f"{name:36s} B={B:3d} v{ver} bn={bn or 'auto':>4} {ms*1e3:9.1f} us {tf:8.1f} TFLOP/s", flush=True)
+                for epi in (False, True):
+                    ms, tf = bench(B, H, W, C, N, conv, bn=bn, ver=ver, epi=epi)
+                    print(f"{name:36s} B={B:3d} v{ver} bn={bn or 'auto':>4} epi={'bias+res' if epi else 'none':8s} "
+                          f"{ms*1e3:9.1f} us {tf:8.1f} TFLOP/s", flush=True)
