@@ -22,6 +22,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, from profiles/r01_ncu_gemm_conv_*.csv (batch 16)
+DOMINANT_KERNEL_DRAM_BYTES = 49.5e6
 FLOP_PER_FRAME = {"sd14": 2 * 51 * 0.8033e12 + 2.5145e12}  # SURVEY.md §8d algorithmic FLOPs (84.45 T)
 UNET_FLOP_B1 = 0.8033e12
 VAE_FLOP = 2.5145e12
@@ -79,8 +81,9 @@ def cpu_reference_leg(steps, warmup, threads=None):
     from oracle.unet import UNet2DConditionModel, UNetConfig
     from oracle.vae import AutoencoderKLDecoder, VAEConfig
 
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
+    if threads:
+        torch.set_num_threads(threads)
+    threads = torch.get_num_threads()  # torch's default: one thread per physical core of the box
     torch.manual_seed(0)
     unet = UNet2DConditionModel(UNetConfig.sd14()).eval()
     vae = AutoencoderKLDecoder(VAEConfig()).eval()
@@ -90,7 +93,7 @@ def cpu_reference_leg(steps, warmup, threads=None):
     with torch.no_grad():
         # bounded sample: a batch-2 fp32 UNet forward costs ~1 min on a shared host, so at most 1 warm-up + 2 timed
         steps = max(1, min(steps, 2))
-        for _ in range(min(1, warmup)):
+        for _ in range(min(1, warmup) if steps > 1 else 0):
             unet(x, torch.tensor(981), ctx)
         t0 = time.perf_counter()
         for _ in range(steps):
@@ -240,9 +243,48 @@ def main():
     h2d = F * (4 * h * w + 77 * 768) * 2
     d2h = F * 512 * 512 * 3
 
+    # ---- roofline of the dominant kernel, measured live: the 64x64-level ResBlock conv3x3 (320 -> 320, bias + residual)
+    #      through the tcgen05 implicit-GEMM kernel at this run's UNet batch (2F), CUDA events on the launch stream
+    kern = None
+    if rank == 0:
+        import ctypes as C
+
+        Bn = 2 * F
+        xk = torch.randn(Bn, 64, 64, 320, device=dev).half()
+        wk = _native.pack_weight((torch.randn(320, 320, 3, 3, device=dev) * (2880 ** -0.5)).half())
+        bk = torch.randn(320, device=dev)
+        rk = torch.randn(Bn, 64, 64, 320, device=dev).half()
+        ok = torch.empty(Bn, 64, 64, 320, device=dev, dtype=torch.float16)
+        d = _native.GemmDesc()
+        d.A = xk.data_ptr(); d.C, d.W, d.H, d.B = 320, 64, 64, Bn
+        d.sW, d.sH, d.sB = 320, 64 * 320, 64 * 64 * 320
+        d.conv = 1; d.Wt = wk.data_ptr(); d.N = 320
+        d.bias = bk.data_ptr(); d.resid = rk.data_ptr(); d.ldr = 320
+        d.out = ok.data_ptr(); d.ldc = 320; d.alpha = 1.0
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+        for _ in range(3):
+            _native.gemm(d)
+        torch.cuda.synchronize()
+        tot = 0.0
+        reps = 10
+        for _ in range(reps):
+            flush.zero_()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            _native.gemm(d)
+            k1.record()
+            torch.cuda.synchronize()
+            tot += k0.elapsed_time(k1)
+        kern = {"name": "gemm2_tc_kernel<160> conv3x3 64x64 320->320 bias+residual", "batch": Bn,
+                "flop_per_launch": 2.0 * Bn * 64 * 64 * 320 * 2880, "us_per_launch": tot / reps * 1e3}
+        del xk, wk, rk, ok, flush
+
     if rank != 0:
         return
     peak_tf, peak_gbs, peak_src = _peaks()
+    burst_tf = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1736.7) \
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
+    k_ach = kern["flop_per_launch"] / (kern["us_per_launch"] * 1e-6) / 1e12
     achieved_tf = value * FLOP_PER_FRAME["sd14"] / 1e12 / world
     pro, per_step, vae_l = eng.launches()
     launches_per_call = pro + 1 + n_unet_calls * (per_step + 1) + vae_l
@@ -253,9 +295,14 @@ def main():
         "config": {"workload": workload, "frames_per_step": F, "unet_calls_per_frame": n_unet_calls,
                    "unet_batch": 2 * F, "parallelism": f"frame-dp{world}", "cuda_graph": not a.no_graph,
                    "l2": "working set per step (1.8 GB weights + activations) exceeds the 126 MB L2"},
-        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf, "traffic": None,
-                     "note": f"whole sampler: frames x 84.45 TFLOP / time / gpus, vs {peak_src} sustained bf16/fp16 peak"},
+        "roofline": {"bound": "tensor", "achieved": k_ach, "peak": burst_tf, "unit": "TFLOP/s",
+                     "frac": k_ach / burst_tf, "traffic": DOMINANT_KERNEL_DRAM_BYTES,
+                     "kernel": kern["name"], "kernel_batch": kern["batch"], "us_per_launch": kern["us_per_launch"],
+                     "note": f"dominant kernel timed alone (L2 flushed between launches) vs {peak_src} burst fp16/bf16 "
+                             "peak; traffic = dram read+write bytes per launch from the committed ncu --set full "
+                             "capture (profiles/), at that capture's batch",
+                     "whole_sampler": {"achieved": achieved_tf, "peak": peak_tf, "frac": achieved_tf / peak_tf,
+                                       "note": "frames x 84.45 TFLOP / time / gpus vs sustained peak"}},
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches_per_call * K,
         "clocks": clk,

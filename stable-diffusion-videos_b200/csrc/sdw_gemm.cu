@@ -341,6 +341,9 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
     static const int stage_env = [] { const char* e = std::getenv("SDW_STAGE"); return e ? std::atoi(e) : -1; }();
     const int kblocks = p.ntaps * kchunks;
     p.stage_stores = stage_env >= 0 ? stage_env : (kblocks <= 10 && d.N >= 640 ? 1 : 0);
+    // the coalescing stage keeps 32-bit row offsets
+    const int64_t max_off = static_cast<int64_t>(d.B) * OH * OW * std::max<int64_t>(d.ldc, d.ldr ? d.ldr : d.ldc);
+    SDW_REQUIRE(max_off < (int64_t(1) << 31) || ver == 1, "output too large for the 2-CTA epilogue (>= 2^31 elements)");
   }
   if (ver == 2) {
     p.m_pairs = (m_tiles + 1) / 2;

@@ -152,7 +152,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
       const int a = it & 1;
       // the two warps of a lane quarter interleave 32-column chunks: twice the loads / stores in flight
       gemm_epilogue<BN>(p, tmem_base + a * BN, warp, lane, x0, y0, b0, n0, &tmem_full[a], (it >> 1) & 1,
-                        (warp - 4) >> 2, 2, p.stage_stores ? epi_stage + (warp - 4) * 2048 : nullptr);
+                        (warp - 4) >> 2, 2, epi_stage + (warp - 4) * 2048);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[a]), 0));

@@ -73,33 +73,66 @@ __device__ __forceinline__ void epi_vt_chunk(const GemmKParams& p, const uint32_
   }
 }
 
-// Coalescing stage: the row-owner layout (thread = output row) would store 16 B per lane into 32 different cache lines
-// per instruction.  Instead each warp bounces a 32-row x 64-byte chunk through 2 KB of shared memory (XOR-swizzled,
-// conflict-free both ways) and writes it back with 4 lanes per row: 8 full 64-byte row segments per store instruction.
-//   w[j8]      : this lane's row, 8 fp16 columns each (j8 < npieces valid)
-//   row_off    : element offset of this lane's output row, or -1 if the row is out of range
+// Coalescing stage: the row-owner layout (thread = output row) would move 16 B per lane to / from 32 different cache
+// lines per instruction.  Instead each warp bounces a 32-row x 64-byte chunk through 2 KB of shared memory
+// (XOR-swizzled, conflict-free both ways) and talks to global memory with 4 lanes per row: 8 full 64-byte row
+// segments per instruction.  "Coalesced layout": lane l, slot it <-> (row = it*8 + l/4, 16-byte piece = l%4).
+struct EpiRows {
+  int32_t out[4];  // element offsets of rows it*8 + lane/4 in the output (or -1); the planner guarantees < 2^31
+  int32_t res[4];  // ... in the residual (or -1)
+};
+__device__ __forceinline__ void epi_rows_init(EpiRows& R, int lane, int64_t out_off, int64_t res_off) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2);
+    R.out[it] = __shfl_sync(0xffffffffu, static_cast<int32_t>(out_off), row);
+    R.res[it] = __shfl_sync(0xffffffffu, static_cast<int32_t>(res_off), row);
+  }
+}
+// w[j8]: this lane's row, 8 fp16 columns each (j8 < npieces valid) -> coalesced global stores
 __device__ __forceinline__ void staged_store32(uint8_t* stage, int lane, const uint4 (&w)[4], int npieces,
-                                               int64_t row_off, __half* out, int col) {
+                                               bool row_ok, const EpiRows& R, __half* out, int col) {
   const int sw = (lane >> 1) & 3;
 #pragma unroll
   for (int j8 = 0; j8 < 4; ++j8)
-    if (j8 < npieces && row_off >= 0) *reinterpret_cast<uint4*>(stage + lane * 64 + ((j8 ^ sw) << 4)) = w[j8];
+    if (j8 < npieces && row_ok) *reinterpret_cast<uint4*>(stage + lane * 64 + ((j8 ^ sw) << 4)) = w[j8];
   __syncwarp();
   const int piece = lane & 3;
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int row = it * 8 + (lane >> 2);
-    const int64_t off = __shfl_sync(0xffffffffu, row_off, row);
-    if (off >= 0 && piece < npieces) {
+    if (R.out[it] >= 0 && piece < npieces) {
       const uint4 u = *reinterpret_cast<const uint4*>(stage + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
-      *reinterpret_cast<uint4*>(out + off + col + piece * 8) = u;
+      *reinterpret_cast<uint4*>(out + R.out[it] + col + piece * 8) = u;
     }
   }
   __syncwarp();
 }
+// residual chunk, coalesced layout: issue the global loads (registers), later transpose through the stage
+__device__ __forceinline__ void res_issue32(uint4 (&g)[4], int lane, int npieces, const EpiRows& R,
+                                            const __half* resid, int col) {
+  const int piece = lane & 3;
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+    if (R.res[it] >= 0 && piece < npieces) g[it] = *reinterpret_cast<const uint4*>(resid + R.res[it] + col + piece * 8);
+}
+__device__ __forceinline__ void res_transpose32(uint8_t* stage, int lane, const uint4 (&g)[4], uint4 (&rs)[4],
+                                                int npieces) {
+  const int piece = lane & 3;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2);
+    if (piece < npieces) *reinterpret_cast<uint4*>(stage + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4)) = g[it];
+  }
+  __syncwarp();
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j8 = 0; j8 < 4; ++j8)
+    if (j8 < npieces) rs[j8] = *reinterpret_cast<const uint4*>(stage + lane * 64 + ((j8 ^ sw) << 4));
+  __syncwarp();
+}
 
-// The residual tile is fetched one chunk AHEAD (16 registers) so its L2/DRAM latency overlaps the previous chunk's
-// TMEM load, math and stores; bias / time-embedding rows are L1-resident across the tiles of a persistent CTA.
+// direct (row-owner) residual load, used when no stage buffer exists (1-CTA kernel)
 template <int FLAGS>
 __device__ __forceinline__ void epi_res_load(uint4 (&rs)[4], int n, int nvalid, bool row_ok, const __half* res_row) {
   if (FLAGS & 4) {
@@ -112,45 +145,70 @@ __device__ __forceinline__ void epi_res_load(uint4 (&rs)[4], int n, int nvalid, 
 template <int BN, int FLAGS>
 __device__ __forceinline__ void epi_fast(const GemmKParams& p, uint32_t taddr, int n0, bool row_ok, int64_t pix_in,
                                          __half* out_row, const __half* res_row, const float* rowvec, int chunk0,
-                                         int chunk_step, uint8_t* stage, int lane, int64_t out_off) {
+                                         int chunk_step, uint8_t* stage, int lane, int64_t out_off, int64_t res_off) {
   const int nmax = min(BN, p.N - n0);  // valid columns of this tile (multiple of 8)
   const bool vt_mode = p.mode == GEMM_QKV_VT;
-  const int64_t row_off = row_ok ? out_off : -1;
-  uint4 rs_cur[4], rs_nxt[4];
+  EpiRows R;
+  if (stage) epi_rows_init(R, lane, row_ok ? out_off : -1, (row_ok && (FLAGS & 4)) ? res_off : -1);
+  const bool stage_st = stage && p.stage_stores;
+  uint4 g[4];  // residual of the NEXT chunk in flight: coalesced layout (staged path) or row-owner layout (direct)
   int c = chunk0;
-  if (c * 32 < nmax) epi_res_load<FLAGS>(rs_cur, n0 + c * 32, nmax - c * 32, row_ok, res_row);
+  if ((FLAGS & 4) && c * 32 < nmax) {
+    if (stage) res_issue32(g, lane, min(4, (nmax - c * 32) >> 3), R, p.resid, n0 + c * 32);
+    else epi_res_load<FLAGS>(g, n0 + c * 32, nmax - c * 32, row_ok, res_row);
+  }
 #pragma unroll 1
   for (; c * 32 < nmax; c += chunk_step) {
-    uint32_t v[32];
-    tmem_ld_32x32(taddr + c * 32, v);
-    const int cn = c + chunk_step;
-    if (cn * 32 < nmax) epi_res_load<FLAGS>(rs_nxt, n0 + cn * 32, nmax - cn * 32, row_ok, res_row);
-    tmem_ld_wait();
     const int n = n0 + c * 32;
-    if (vt_mode && n >= p.vt_col0) {
+    const int npieces = min(4, (nmax - c * 32) >> 3);
+    const bool vt_chunk = vt_mode && n >= p.vt_col0;
+    uint4 rs[4];
+    if ((FLAGS & 4) && !vt_chunk) {
+      if (stage) {
+        res_transpose32(stage, lane, g, rs, npieces);
+      } else {
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) rs[j8] = g[j8];
+      }
+    }
+    if (vt_chunk) {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      tmem_ld_wait();
       if (row_ok) epi_vt_chunk(p, v, n, pix_in);
     } else {
       uint4 w[4];
-      const int npieces = min(4, (nmax - c * 32) >> 3);
 #pragma unroll
-      for (int j8 = 0; j8 < 4; ++j8) {
-        if (j8 < npieces) {
-          const int nn = n + j8 * 8;
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            o[j] = __uint_as_float(v[j8 * 8 + j]);
-            if (FLAGS & 16) o[j] *= p.alpha;
+      for (int half = 0; half < 2; ++half) {  // 16 accumulator columns at a time: small live register set
+        uint32_t v[16];
+        tmem_ld_32x16(taddr + c * 32 + half * 16, v);
+        if (half == 0) {
+          // the next chunk's residual does not depend on the accumulator: issue it before the TMEM wait
+          const int cn = c + chunk_step;
+          if ((FLAGS & 4) && cn * 32 < nmax) {
+            if (stage) res_issue32(g, lane, min(4, (nmax - cn * 32) >> 3), R, p.resid, n0 + cn * 32);
+            else epi_res_load<FLAGS>(g, n0 + cn * 32, nmax - cn * 32, row_ok, res_row);
           }
-          if (FLAGS & 1) add8(o, p.bias + nn);
-          if (FLAGS & 2) add8(o, rowvec + nn);
-          if (FLAGS & 8) {
+        }
+        tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = silu_f(o[j]);
-          }
-          if (FLAGS & 4) {
-            if (row_ok) {
-              const __half2* h = reinterpret_cast<const __half2*>(&rs_cur[j8]);
+        for (int q = 0; q < 2; ++q) {
+          const int j8 = half * 2 + q;
+          if (j8 < npieces) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              o[j] = __uint_as_float(v[q * 8 + j]);
+              if (FLAGS & 16) o[j] *= p.alpha;
+            }
+            if (FLAGS & 1) add8(o, p.bias + n + j8 * 8);
+            if (FLAGS & 2) add8(o, rowvec + n + j8 * 8);
+            if (FLAGS & 8) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = silu_f(o[j]);
+            }
+            if (FLAGS & 4) {
+              const __half2* h = reinterpret_cast<const __half2*>(&rs[j8]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 f = __half22float2(h[j]);
@@ -158,24 +216,20 @@ __device__ __forceinline__ void epi_fast(const GemmKParams& p, uint32_t taddr, i
                 o[2 * j + 1] += f.y;
               }
             }
+            w[j8].x = pack_h2(o[0], o[1]);
+            w[j8].y = pack_h2(o[2], o[3]);
+            w[j8].z = pack_h2(o[4], o[5]);
+            w[j8].w = pack_h2(o[6], o[7]);
           }
-          w[j8].x = pack_h2(o[0], o[1]);
-          w[j8].y = pack_h2(o[2], o[3]);
-          w[j8].z = pack_h2(o[4], o[5]);
-          w[j8].w = pack_h2(o[6], o[7]);
         }
       }
-      if (stage) {
-        staged_store32(stage, lane, w, npieces, row_off, p.out, n);
+      if (stage_st) {
+        staged_store32(stage, lane, w, npieces, row_ok, R, p.out, n);
       } else if (row_ok) {
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8)
           if (j8 < npieces) *reinterpret_cast<uint4*>(out_row + n + j8 * 8) = w[j8];
       }
-    }
-    if (FLAGS & 4) {
-#pragma unroll
-      for (int j8 = 0; j8 < 4; ++j8) rs_cur[j8] = rs_nxt[j8];
     }
   }
 }
@@ -185,7 +239,9 @@ template <int BN>
 __device__ __forceinline__ void epi_geglu(const GemmKParams& p, uint32_t taddr, int n0, bool row_ok, __half* out_row,
                                           bool vec_out, int chunk0, int chunk_step, uint8_t* stage, int lane,
                                           int64_t out_off) {
-  const int64_t row_off = row_ok ? out_off : -1;
+  EpiRows R;
+  const bool stage_st = stage && p.stage_stores && vec_out;
+  if (stage_st) epi_rows_init(R, lane, row_ok ? out_off : -1, -1);
 #pragma unroll 1
   for (int c = chunk0; c < BN / 64; c += chunk_step) {
     const int n = n0 + c * 64;
@@ -219,8 +275,8 @@ __device__ __forceinline__ void epi_geglu(const GemmKParams& p, uint32_t taddr, 
         w[j8].w = pack_h2(o[6], o[7]);
       }
     }
-    if (stage && vec_out) {
-      staged_store32(stage, lane, w, 4, row_off, p.out, n / 2);
+    if (stage_st) {
+      staged_store32(stage, lane, w, 4, row_ok, R, p.out, n / 2);
     } else if (row_ok) {
 #pragma unroll
       for (int j8 = 0; j8 < 4; ++j8) {
@@ -274,11 +330,11 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, uint32_t tme
     const int flags = (p.bias ? 1 : 0) | (p.rowvec ? 2 : 0) | (p.resid ? 4 : 0) | (p.act == 1 ? 8 : 0) |
                       (p.alpha != 1.f ? 16 : 0);
     switch (flags) {
-      case 0: epi_fast<BN, 0>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off); return;
-      case 1: epi_fast<BN, 1>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off); return;
-      case 3: epi_fast<BN, 3>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off); return;
-      case 5: epi_fast<BN, 5>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off); return;
-      case 16: epi_fast<BN, 16>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off); return;
+      case 0: epi_fast<BN, 0>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, res_off); return;
+      case 1: epi_fast<BN, 1>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, res_off); return;
+      case 3: epi_fast<BN, 3>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, res_off); return;
+      case 5: epi_fast<BN, 5>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, res_off); return;
+      case 16: epi_fast<BN, 16>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, res_off); return;
       default: break;
     }
   }
