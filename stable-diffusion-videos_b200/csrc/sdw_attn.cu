@@ -190,34 +190,37 @@ __global__ void __launch_bounds__(ATT_THREADS, SB == 1 ? 2 : 1)
       mbar_wait(&s_full[j % SB], (j / SB) & 1);
       tc_fence_after();
       const uint32_t t_s = tmem + lane_base + (j % SB) * BKV;
+      // all TMEM loads of the tile are issued back to back, one wait
+      uint32_t vu[BKV / 32][32];
+#pragma unroll
+      for (int c = 0; c < BKV / 32; ++c) tmem_ld_32x32(t_s + c * 32, vu[c]);
+      tmem_ld_wait();
       float v[BKV];
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t tmp[32];
-        tmem_ld_32x32(t_s + c * 32, tmp);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[c * 32 + i] = __uint_as_float(tmp[i]);
-      }
+      for (int i = 0; i < BKV; ++i) v[i] = __uint_as_float(vu[i / 32][i % 32]);
       const int kv0 = j * BKV;
       if (kv0 + BKV > p.Nk) {
 #pragma unroll
         for (int i = 0; i < BKV; ++i)
           if (kv0 + i >= p.Nk) v[i] = -INFINITY;
       }
-      float m_t = v[0];
+      // row max / row sum with 4 independent accumulators: a single 128-long dependent chain would cost
+      // 128 x (4-cycle ALU latency) per reduction with only two softmax warps per scheduler to hide it
+      float mx[4] = {v[0], v[1], v[2], v[3]};
 #pragma unroll
-      for (int i = 1; i < BKV; ++i) m_t = fmaxf(m_t, v[i]);
+      for (int i = 4; i < BKV; ++i) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
+      const float m_t = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       const float m_new = fmaxf(m_run, m_t);
       const float alpha = ex2f((m_run - m_new) * sl2);
       const float mb = m_new * sl2;
-      float sum = 0.f;
+      float sm[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < BKV; ++i) {
         const float t = fmaf(v[i], sl2, -mb);
         v[i] = (i % ATT_POLY_EVERY == ATT_POLY_EVERY - 1) ? ex2_poly(t) : ex2f(t);
-        sum += v[i];
+        sm[i & 3] += v[i];
       }
+      const float sum = (sm[0] + sm[1]) + (sm[2] + sm[3]);
       l_run = fmaf(l_run, alpha, sum);
       m_run = m_new;
       if (j > 0) {

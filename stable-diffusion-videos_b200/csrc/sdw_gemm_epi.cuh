@@ -108,30 +108,6 @@ __device__ __forceinline__ void staged_store32(uint8_t* stage, int lane, const u
   }
   __syncwarp();
 }
-// residual chunk, coalesced layout: issue the global loads (registers), later transpose through the stage
-__device__ __forceinline__ void res_issue32(uint4 (&g)[4], int lane, int npieces, const EpiRows& R,
-                                            const __half* resid, int col) {
-  const int piece = lane & 3;
-#pragma unroll
-  for (int it = 0; it < 4; ++it)
-    if (R.res[it] >= 0 && piece < npieces) g[it] = *reinterpret_cast<const uint4*>(resid + R.res[it] + col + piece * 8);
-}
-__device__ __forceinline__ void res_transpose32(uint8_t* stage, int lane, const uint4 (&g)[4], uint4 (&rs)[4],
-                                                int npieces) {
-  const int piece = lane & 3;
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int row = it * 8 + (lane >> 2);
-    if (piece < npieces) *reinterpret_cast<uint4*>(stage + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4)) = g[it];
-  }
-  __syncwarp();
-  const int sw = (lane >> 1) & 3;
-#pragma unroll
-  for (int j8 = 0; j8 < 4; ++j8)
-    if (j8 < npieces) rs[j8] = *reinterpret_cast<const uint4*>(stage + lane * 64 + ((j8 ^ sw) << 4));
-  __syncwarp();
-}
-
 // direct (row-owner) residual load, used when no stage buffer exists (1-CTA kernel)
 template <int FLAGS>
 __device__ __forceinline__ void epi_res_load(uint4 (&rs)[4], int n, int nvalid, bool row_ok, const __half* res_row) {
@@ -145,18 +121,15 @@ __device__ __forceinline__ void epi_res_load(uint4 (&rs)[4], int n, int nvalid, 
 template <int BN, int FLAGS>
 __device__ __forceinline__ void epi_fast(const GemmKParams& p, uint32_t taddr, int n0, bool row_ok, int64_t pix_in,
                                          __half* out_row, const __half* res_row, const float* rowvec, int chunk0,
-                                         int chunk_step, uint8_t* stage, int lane, int64_t out_off, int64_t res_off) {
+                                         int chunk_step, uint8_t* stage, int lane, int64_t out_off, uint4 (&g)[4]) {
   const int nmax = min(BN, p.N - n0);  // valid columns of this tile (multiple of 8)
   const bool vt_mode = p.mode == GEMM_QKV_VT;
   EpiRows R;
-  if (stage) epi_rows_init(R, lane, row_ok ? out_off : -1, (row_ok && (FLAGS & 4)) ? res_off : -1);
   const bool stage_st = stage && p.stage_stores;
-  uint4 g[4];  // residual of the NEXT chunk in flight: coalesced layout (staged path) or row-owner layout (direct)
+  if (stage_st) epi_rows_init(R, lane, row_ok ? out_off : -1, -1);
+  // residual of the NEXT chunk in flight (row-owner layout; its first chunk was issued before the TMEM-full wait and
+  // the whole row segment was prefetched into L2 — see gemm_epilogue)
   int c = chunk0;
-  if ((FLAGS & 4) && c * 32 < nmax) {
-    if (stage) res_issue32(g, lane, min(4, (nmax - c * 32) >> 3), R, p.resid, n0 + c * 32);
-    else epi_res_load<FLAGS>(g, n0 + c * 32, nmax - c * 32, row_ok, res_row);
-  }
 #pragma unroll 1
   for (; c * 32 < nmax; c += chunk_step) {
     const int n = n0 + c * 32;
@@ -164,12 +137,8 @@ __device__ __forceinline__ void epi_fast(const GemmKParams& p, uint32_t taddr, i
     const bool vt_chunk = vt_mode && n >= p.vt_col0;
     uint4 rs[4];
     if ((FLAGS & 4) && !vt_chunk) {
-      if (stage) {
-        res_transpose32(stage, lane, g, rs, npieces);
-      } else {
 #pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) rs[j8] = g[j8];
-      }
+      for (int j8 = 0; j8 < 4; ++j8) rs[j8] = g[j8];
     }
     if (vt_chunk) {
       uint32_t v[32];
@@ -186,8 +155,7 @@ __device__ __forceinline__ void epi_fast(const GemmKParams& p, uint32_t taddr, i
           // the next chunk's residual does not depend on the accumulator: issue it before the TMEM wait
           const int cn = c + chunk_step;
           if ((FLAGS & 4) && cn * 32 < nmax) {
-            if (stage) res_issue32(g, lane, min(4, (nmax - cn * 32) >> 3), R, p.resid, n0 + cn * 32);
-            else epi_res_load<FLAGS>(g, n0 + cn * 32, nmax - cn * 32, row_ok, res_row);
+            epi_res_load<FLAGS>(g, n0 + cn * 32, nmax - cn * 32, row_ok, res_row);
           }
         }
         tmem_ld_wait();
@@ -315,6 +283,19 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, uint32_t tme
   __half* out_row = p.out + out_off;
   const __half* res_row = p.resid ? p.resid + res_off : nullptr;
 
+  const bool fast = vec_out && (!p.resid || vec_res) && ((p.N & 7) == 0) &&
+                    (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
+                    (!p.rowvec || ((reinterpret_cast<uintptr_t>(p.rowvec) & 15) == 0 && (p.rowvec_ld & 3) == 0));
+  // the residual does not depend on the accumulator: while the mainloop of this tile is still running, pull this
+  // row's residual segment into L2 and issue the first chunk's loads (their latency hides behind the TMEM-full wait)
+  uint4 g[4];
+  if (fast && p.resid && p.mode != GEMM_GEGLU && row_ok) {
+    const int nmax = min(BN, p.N - n0);
+    for (int cb = 0; cb < nmax * 2; cb += 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(res_row + n0) + cb));
+    if (chunk0 * 32 < nmax) epi_res_load<4>(g, n0 + chunk0 * 32, nmax - chunk0 * 32, true, res_row);
+  }
+
   mbar_wait(tmem_full_bar, full_parity);
   tc_fence_after();
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -323,18 +304,15 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, uint32_t tme
     epi_geglu<BN>(p, taddr, n0, row_ok, out_row, vec_out, chunk0, chunk_step, stage, lane, out_off);
     return;
   }
-  const bool fast = vec_out && (!p.resid || vec_res) && ((p.N & 7) == 0) &&
-                    (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
-                    (!p.rowvec || ((reinterpret_cast<uintptr_t>(p.rowvec) & 15) == 0 && (p.rowvec_ld & 3) == 0));
   if (fast) {
     const int flags = (p.bias ? 1 : 0) | (p.rowvec ? 2 : 0) | (p.resid ? 4 : 0) | (p.act == 1 ? 8 : 0) |
                       (p.alpha != 1.f ? 16 : 0);
     switch (flags) {
-      case 0: epi_fast<BN, 0>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, res_off); return;
-      case 1: epi_fast<BN, 1>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, res_off); return;
-      case 3: epi_fast<BN, 3>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, res_off); return;
-      case 5: epi_fast<BN, 5>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, res_off); return;
-      case 16: epi_fast<BN, 16>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, res_off); return;
+      case 0: epi_fast<BN, 0>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, g); return;
+      case 1: epi_fast<BN, 1>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, g); return;
+      case 3: epi_fast<BN, 3>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, g); return;
+      case 5: epi_fast<BN, 5>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, g); return;
+      case 16: epi_fast<BN, 16>(p, taddr, n0, row_ok, pix_in, out_row, res_row, rowvec, chunk0, chunk_step, stage, lane, out_off, g); return;
       default: break;
     }
   }
