@@ -16,6 +16,7 @@
 #include "sdw_ptx.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace sdw {
@@ -41,7 +42,9 @@ struct AttnCfg {
   static constexpr int V_STAGE = (BKV / 64) * DVP * 128;
   static constexpr int P_BYTES = (BKV / 64) * ATT_BQ * 128;
   static constexpr int SMEM = Q_BYTES + P_BYTES + ST * (K_STAGE + V_STAGE) + 1024 + 256;
-  static constexpr int TMEM_COLS = SB == 1 ? 256 : 512;
+  static constexpr int NEED = SB * BKV + DVP;
+  static constexpr int TMEM_COLS = NEED <= 128 ? 128 : (NEED <= 256 ? 256 : 512);
+  static constexpr int NCTA = SMEM <= 64 * 1024 && TMEM_COLS <= 128 ? 3 : (SMEM <= 114 * 1024 && TMEM_COLS <= 256 ? 2 : 1);  // CTAs per SM
   static constexpr int O_COL = SB * BKV;
   static_assert(SB * BKV + DVP <= TMEM_COLS, "TMEM budget");
 };
@@ -67,7 +70,7 @@ __device__ __forceinline__ float ex2_poly(float t) {
 static constexpr int ATT_POLY_EVERY = 4;
 
 template <int DKA, int DVP, int BKV, int ST, int SB>
-__global__ void __launch_bounds__(ATT_THREADS, SB == 1 ? 2 : 1)
+__global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::NCTA)
     attn_fwd_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = AttnCfg<DKA, DVP, BKV, ST, SB>;
   extern __shared__ uint8_t smem_raw[];
@@ -324,6 +327,7 @@ static int attn_init() {
   if (int e = attn_set_attr<1, 64, 128, 2, 1>()) return e;
   if (int e = attn_set_attr<2, 80, 128, 2, 2>()) return e;
   if (int e = attn_set_attr<3, 160, 64, 3, 2>()) return e;
+  if (int e = attn_set_attr<1, 48, 64, 2, 1>()) return e;
   g_attn_init = true;
   return 0;
 }
@@ -333,7 +337,8 @@ bool attn_supported(int d) { return d % 8 == 0 && d >= 8 && d <= 160; }
 static int variant_for(int d) {
   if (d <= 16) return 0;
   if (d <= 32) return 1;
-  if (d <= 48) return 2;
+  static const bool bkv64 = [] { const char* e = std::getenv("SDW_ATTN_BKV64"); return e && e[0] == '1'; }();
+  if (d <= 48) return bkv64 && d > 32 ? 6 : 2;
   if (d <= 64) return 3;
   if (d <= 80) return 4;
   return 5;
@@ -347,8 +352,8 @@ int plan_attention(const AttnDesc& a, AttnLaunch* L) {
   AttnLaunchImpl* I = reinterpret_cast<AttnLaunchImpl*>(L->storage);
   std::memset(I, 0, sizeof(*I));
   I->variant = variant_for(a.d);
-  const int bkv = I->variant == 5 ? 64 : 128;
-  const int dvp_tab[6] = {16, 32, 48, 64, 80, 160};
+  const int bkv = (I->variant == 5 || I->variant == 6) ? 64 : 128;
+  const int dvp_tab[7] = {16, 32, 48, 64, 80, 160, 48};
   const int dvp = dvp_tab[I->variant];
   AttnKParams& p = I->p;
   p.Nq = a.Nq; p.Nk = a.Nk; p.d = a.d; p.heads = a.heads;
@@ -393,6 +398,7 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     case 3: attn_fwd_kernel<1, 64, 128, 2, 1><<<I->grid, ATT_THREADS, AttnCfg<1, 64, 128, 2, 1>::SMEM, stream>>>(I->p); break;
     case 4: attn_fwd_kernel<2, 80, 128, 2, 2><<<I->grid, ATT_THREADS, AttnCfg<2, 80, 128, 2, 2>::SMEM, stream>>>(I->p); break;
     case 5: attn_fwd_kernel<3, 160, 64, 3, 2><<<I->grid, ATT_THREADS, AttnCfg<3, 160, 64, 3, 2>::SMEM, stream>>>(I->p); break;
+    case 6: attn_fwd_kernel<1, 48, 64, 2, 1><<<I->grid, ATT_THREADS, AttnCfg<1, 48, 64, 2, 1>::SMEM, stream>>>(I->p); break;
     default: set_error("bad attention variant"); return 1;
   }
   SDW_CUDA_OK(cudaGetLastError());

@@ -5,7 +5,7 @@
 // tensor 34 %).  A CTA pair computes a 256 x BN tile with ONE tcgen05.mma.cta_group::2 (M = 256): each CTA stages its
 // own 128 activation rows and only HALF of the weight tile, so operand bytes per FLOP drop by ~1.6-2x, and the
 // accumulators of two consecutive tiles double-buffer in TMEM so the epilogue of tile i overlaps the mainloop of
-// tile i+1 (persistent grid: one cluster per SM pair, static round-robin over tiles, M fastest for weight reuse in L2).
+// tile i+1 (persistent grid: one cluster per SM pair, static round-robin over tiles, N fastest so an activation tile leaves DRAM once).
 //
 //   warp 0 (both CTAs)  : TMA producer — own A tile [128 x 64] + own half of B [BN/2 x 64]; completion bytes are
 //                         signalled on the LEADER's full barrier (cta_group::2 TMA, mapa'd barrier address).
@@ -78,8 +78,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   auto tile_coords = [&](int t, int& x0, int& y0, int& b0, int& n0) {
-    const int m_pair = t % p.m_pairs;
-    const int n_tile = t / p.m_pairs;
+    // N fastest: the n_tiles column tiles of one M pair run on neighbouring clusters at the same time, so the
+    // activation tile is fetched from DRAM once and re-read from L2 (the whole weight matrix is L2-resident anyway)
+    const int m_pair = t / p.n_tiles;
+    const int n_tile = t - m_pair * p.n_tiles;
     const int m_tile = m_pair * 2 + static_cast<int>(rank);
     const int tw = m_tile % p.tiles_w;
     const int th = (m_tile / p.tiles_w) % p.tiles_h;

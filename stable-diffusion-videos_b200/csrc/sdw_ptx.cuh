@@ -183,8 +183,11 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// remote arrive (default .release.cta semantics, as CUTLASS' ClusterBarrier::arrive): a cluster-scope release would
+// compile to MEMBAR.ALL.GPU and stall the epilogue warp until all its global stores have drained
+// (profiles/r01_ncu_gemm2_conv.md) — only the TMEM reads, already waited on, need to be ordered before it
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d_2sm(const void* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
                                                 int c2, int c3) {
