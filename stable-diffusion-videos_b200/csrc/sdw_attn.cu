@@ -55,6 +55,26 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// packed fp32x2 math (sm_100a FFMA2 / FADD2): one issue slot for two lanes of the softmax arithmetic
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // 2^t for t <= 0 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax, max rel. error 7.5e-5 — below the fp16
 // rounding of P): the MUFU pipe (16 ex2/clk/SM) is the attention bottleneck at head dim 40, so every 4th score is
 // exponentiated here instead (the split FlashAttention-4 uses).
@@ -67,9 +87,8 @@ __device__ __forceinline__ float ex2_poly(float t) {
   q = fmaf(q, f, 0.9999251962f);
   return __int_as_float(__float_as_int(q) + (__float_as_int(xr) << 23));
 }
-static constexpr int ATT_POLY_EVERY = 4;
 
-template <int DKA, int DVP, int BKV, int ST, int SB>
+template <int DKA, int DVP, int BKV, int ST, int SB, int POLY = 4>  // POLY: every POLY-th exp on the FMA pipe (0 = none)
 __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::NCTA)
     attn_fwd_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = AttnCfg<DKA, DVP, BKV, ST, SB>;
@@ -216,14 +235,22 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::N
       const float m_new = fmaxf(m_run, m_t);
       const float alpha = ex2f((m_run - m_new) * sl2);
       const float mb = m_new * sl2;
-      float sm[4] = {0.f, 0.f, 0.f, 0.f};
+      // (s - m) * scale*log2e as FFMA2, exp2 per lane (MUFU, every POLY-th on the FMA pipe), sums as FADD2 pairs
+      const uint64_t sl2_2 = pk2(sl2, sl2), nmb_2 = pk2(-mb, -mb);
+      uint64_t sm2[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
 #pragma unroll
-      for (int i = 0; i < BKV; ++i) {
-        const float t = fmaf(v[i], sl2, -mb);
-        v[i] = (i % ATT_POLY_EVERY == ATT_POLY_EVERY - 1) ? ex2_poly(t) : ex2f(t);
-        sm[i & 3] += v[i];
+      for (int i = 0; i < BKV; i += 2) {
+        float t0, t1;
+        upk2(fma2(pk2(v[i], v[i + 1]), sl2_2, nmb_2), t0, t1);
+        v[i] = ex2f(t0);
+        v[i + 1] = (POLY > 0 && (i / 2) % (POLY > 1 ? POLY / 2 : 1) == (POLY > 1 ? POLY / 2 : 1) - 1) ? ex2_poly(t1)
+                                                                                                      : ex2f(t1);
+        sm2[(i >> 1) & 1] = add2(sm2[(i >> 1) & 1], pk2(v[i], v[i + 1]));
       }
-      const float sum = (sm[0] + sm[1]) + (sm[2] + sm[3]);
+      float s0, s1, s2, s3;
+      upk2(sm2[0], s0, s1);
+      upk2(sm2[1], s2, s3);
+      const float sum = (s0 + s1) + (s2 + s3);
       l_run = fmaf(l_run, alpha, sum);
       m_run = m_new;
       if (j > 0) {
@@ -311,10 +338,10 @@ struct AttnLaunchImpl {
   int variant;
 };
 
-template <int DKA, int DVP, int BKV, int ST, int SB>
+template <int DKA, int DVP, int BKV, int ST, int SB, int POLY = 4>
 static int attn_set_attr() {
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<DKA, DVP, BKV, ST, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   AttnCfg<DKA, DVP, BKV, ST, SB>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<DKA, DVP, BKV, ST, SB, POLY>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<DKA, DVP, BKV, ST, SB>::SMEM));
   return 0;
 }
 
@@ -328,6 +355,8 @@ static int attn_init() {
   if (int e = attn_set_attr<2, 80, 128, 2, 2>()) return e;
   if (int e = attn_set_attr<3, 160, 64, 3, 2>()) return e;
   if (int e = attn_set_attr<1, 48, 64, 2, 1>()) return e;
+  if (int e = attn_set_attr<1, 48, 128, 2, 1, 0>()) return e;
+  if (int e = attn_set_attr<1, 48, 128, 2, 1, 8>()) return e;
   g_attn_init = true;
   return 0;
 }
@@ -338,6 +367,9 @@ static int variant_for(int d) {
   if (d <= 16) return 0;
   if (d <= 32) return 1;
   static const bool bkv64 = [] { const char* e = std::getenv("SDW_ATTN_BKV64"); return e && e[0] == '1'; }();
+  static const int poly = [] { const char* e = std::getenv("SDW_ATTN_POLY"); return e ? std::atoi(e) : 4; }();
+  if (d <= 48 && d > 32 && !bkv64 && poly == 0) return 7;
+  if (d <= 48 && d > 32 && !bkv64 && poly == 8) return 8;
   if (d <= 48) return bkv64 && d > 32 ? 6 : 2;
   if (d <= 64) return 3;
   if (d <= 80) return 4;
@@ -353,7 +385,7 @@ int plan_attention(const AttnDesc& a, AttnLaunch* L) {
   std::memset(I, 0, sizeof(*I));
   I->variant = variant_for(a.d);
   const int bkv = (I->variant == 5 || I->variant == 6) ? 64 : 128;
-  const int dvp_tab[7] = {16, 32, 48, 64, 80, 160, 48};
+  const int dvp_tab[9] = {16, 32, 48, 64, 80, 160, 48, 48, 48};
   const int dvp = dvp_tab[I->variant];
   AttnKParams& p = I->p;
   p.Nq = a.Nq; p.Nk = a.Nk; p.d = a.d; p.heads = a.heads;
@@ -399,6 +431,8 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     case 4: attn_fwd_kernel<2, 80, 128, 2, 2><<<I->grid, ATT_THREADS, AttnCfg<2, 80, 128, 2, 2>::SMEM, stream>>>(I->p); break;
     case 5: attn_fwd_kernel<3, 160, 64, 3, 2><<<I->grid, ATT_THREADS, AttnCfg<3, 160, 64, 3, 2>::SMEM, stream>>>(I->p); break;
     case 6: attn_fwd_kernel<1, 48, 64, 2, 1><<<I->grid, ATT_THREADS, AttnCfg<1, 48, 64, 2, 1>::SMEM, stream>>>(I->p); break;
+    case 7: attn_fwd_kernel<1, 48, 128, 2, 1, 0><<<I->grid, ATT_THREADS, AttnCfg<1, 48, 128, 2, 1>::SMEM, stream>>>(I->p); break;
+    case 8: attn_fwd_kernel<1, 48, 128, 2, 1, 8><<<I->grid, ATT_THREADS, AttnCfg<1, 48, 128, 2, 1>::SMEM, stream>>>(I->p); break;
     default: set_error("bad attention variant"); return 1;
   }
   SDW_CUDA_OK(cudaGetLastError());
