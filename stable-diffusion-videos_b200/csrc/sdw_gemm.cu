@@ -329,7 +329,7 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
     else if (d.N <= 64) bn = 64;
     else bn = 128;
   }
-  SDW_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "unsupported BLOCK_N");
+  SDW_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256 || (bn == 192 && ver == 2), "unsupported BLOCK_N");
   if (ver == 2) SDW_REQUIRE(bn != 64, "the 2-CTA kernel needs BLOCK_N >= 128");
   L->ver = ver;
   if (d.mode == GEMM_GEGLU) SDW_REQUIRE(bn % 64 == 0 && d.N % 64 == 0, "GEGLU needs 64-column pairs");

@@ -26,7 +26,7 @@ template <int BN>
 struct Gemm2Cfg {
   static constexpr int BH = BN / 2;
   static constexpr int B_STAGE = BH * 128;
-  static constexpr int STAGES = BN == 256 ? 6 : (BN == 160 ? 7 : 8);
+  static constexpr int STAGES = BN == 256 ? 6 : (BN >= 160 ? 7 : 8);
   static constexpr int TMEM_COLS = BN <= 128 ? 256 : 512;
   static constexpr int EPI_STAGE = 8 * 2048;  // 2 KB store-coalescing buffer per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * (G2_A_STAGE + B_STAGE) + EPI_STAGE + 1024 + 256;
@@ -181,6 +181,7 @@ int gemm2_init() {
   if (g_init2) return 0;
   if (int e = set_attr2<128>()) return e;
   if (int e = set_attr2<160>()) return e;
+  if (int e = set_attr2<192>()) return e;
   if (int e = set_attr2<256>()) return e;
   g_init2 = true;
   return 0;
@@ -194,6 +195,9 @@ int launch_gemm2(const GemmLaunch& l, cudaStream_t stream) {
       break;
     case 160:
       gemm2_tc_kernel<160><<<l.grid, G2_THREADS, Gemm2Cfg<160>::SMEM_BYTES, stream>>>(l.p);
+      break;
+    case 192:
+      gemm2_tc_kernel<192><<<l.grid, G2_THREADS, Gemm2Cfg<192>::SMEM_BYTES, stream>>>(l.p);
       break;
     case 256:
       gemm2_tc_kernel<256><<<l.grid, G2_THREADS, Gemm2Cfg<256>::SMEM_BYTES, stream>>>(l.p);
