@@ -57,6 +57,7 @@ int sdw_gemm(const sdw_gemm_desc* c, void* stream) {
   d.vt = static_cast<__half*>(c->vt); d.vt_ld = c->vt_ld;
   d.bn = c->bn;
   d.ver = c->ver;
+  d.nsub = c->nsub;
   GemmLaunch L;
   if (int e = plan_gemm(d, &L)) return e;
   return launch_gemm(L, static_cast<cudaStream_t>(stream));

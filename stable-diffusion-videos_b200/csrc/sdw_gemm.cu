@@ -303,25 +303,34 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
   if (ver == 2) SDW_REQUIRE(!d.b_batched || p.tiles_w % 2 == 0, "2-CTA batched matmul needs an even tile count per row");
   // BLOCK_N choice
   int bn = d.bn;
-  if (bn == 0 && ver == 2) {
-    // persistent grid of 74 CTA pairs: pick the BLOCK_N in {256, 160, 128} minimising waves x tile time, where the
-    // tile time scales with BLOCK_N and smaller tiles pay more operand bytes per FLOP (GEGLU needs 64-column pairs)
-    const int cand[3] = {256, 160, 128};
+  int nsub = 1;
+  if (ver == 2 && (bn == 0 || d.nsub == 2)) {
+    // The 2-CTA kernel is L2->SM bandwidth bound (profiles/r01_mma_eff_vs_blockN.txt): a tile costs about
+    // (16 KB of A + 64 B x columns of W) per K block, so the choice minimises waves x bytes over
+    // BLOCK_N in {256, 192, 160, 128} and, for long-K problems, the two-accumulator 2 x 160 tile (single-buffered TMEM).
+    struct Cand { int bn, nsub; };
+    const Cand cand[5] = {{160, 2}, {256, 1}, {192, 1}, {160, 1}, {128, 1}};
     const int mp = (m_tiles + 1) / 2;
-    int best = 128;
+    const int kblocks = p.ntaps * kchunks;
     double best_cost = 1e30;
-    for (int c : cand) {
-      if (d.mode == GEMM_GEGLU && c % 64 != 0) continue;
-      const int tiles = mp * ((d.N + c - 1) / c);
+    int best_bn = 128;
+    for (const Cand& c : cand) {
+      if (d.bn && d.bn != c.bn) continue;
+      if (d.nsub && d.nsub != c.nsub) continue;
+      if (d.mode == GEMM_GEGLU && c.bn % 64 != 0) continue;
+      if (c.nsub == 2 && (kblocks < 18 || d.mode != GEMM_PLAIN) && d.nsub != 2) continue;
+      const int width = c.bn * c.nsub;
+      const int tiles = mp * ((d.N + width - 1) / width);
       const int waves = (tiles + 73) / 74;
-      const double eff = c == 256 ? 1.0 : (c == 160 ? 1.12 : 1.2);
-      const double cost = static_cast<double>(waves) * c * eff;
+      double cost = static_cast<double>(waves) * (16384.0 + 64.0 * width);
+      if (c.nsub == 2) cost *= 1.0 + 6.0 / kblocks;  // un-overlapped epilogue
       if (cost < best_cost) {
         best_cost = cost;
-        best = c;
+        best_bn = c.bn;
+        nsub = c.nsub;
       }
     }
-    bn = best;
+    bn = best_bn;
   }
   if (bn == 0) {
     if (d.mode == GEMM_GEGLU) bn = 128;
@@ -332,6 +341,7 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
   SDW_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256 || (bn == 192 && ver == 2), "unsupported BLOCK_N");
   if (ver == 2) SDW_REQUIRE(bn != 64, "the 2-CTA kernel needs BLOCK_N >= 128");
   L->ver = ver;
+  L->nsub = nsub;
   if (d.mode == GEMM_GEGLU) SDW_REQUIRE(bn % 64 == 0 && d.N % 64 == 0, "GEGLU needs 64-column pairs");
   if (d.mode == GEMM_QKV_VT) SDW_REQUIRE(d.vt && d.vt_col0 % 32 == 0 && d.vt_d > 0, "bad V^T split");
   L->bn = bn;
@@ -347,7 +357,7 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
   }
   if (ver == 2) {
     p.m_pairs = (m_tiles + 1) / 2;
-    p.n_tiles = (d.N + bn - 1) / bn;
+    p.n_tiles = (d.N + bn * nsub - 1) / (bn * nsub);
     const int clusters = std::min(p.m_pairs * p.n_tiles, 74);
     L->grid = dim3(2 * clusters, 1, 1);
   }

@@ -22,20 +22,29 @@ namespace sdw {
 static constexpr int G2_THREADS = 384;  // warpgroup 0: producer, MMA (+2 idle warps); warpgroups 1-2: 8 epilogue warps
 static constexpr int G2_A_STAGE = 128 * 64 * 2;
 
-template <int BN>
+// NSUB = accumulators per activation tile: NSUB = 2 computes a 256 x (2*BN) tile per CTA pair — the A tile is pulled
+// from L2 once for twice the columns (the kernel is L2->SM bandwidth bound: profiles/r01_mma_eff_vs_blockN.txt) at the
+// price of single-buffered TMEM (2 * 2 * 160 > 512 columns), so it is used for long-K problems (3x3 convs) only.
+template <int BN, int NSUB>
 struct Gemm2Cfg {
   static constexpr int BH = BN / 2;
-  static constexpr int B_STAGE = BH * 128;
-  static constexpr int STAGES = BN == 256 ? 6 : (BN >= 160 ? 7 : 8);
-  static constexpr int TMEM_COLS = BN <= 128 ? 256 : 512;
+  static constexpr int B_SUB = BH * 128;           // one CTA's half of one BN-wide weight tile
+  static constexpr int B_STAGE = NSUB * B_SUB;
+  static constexpr int NBUF = (2 * NSUB * BN <= 512) ? 2 : 1;  // accumulator buffers in TMEM
+  static constexpr int ACC_COLS = NSUB * BN;
+  static constexpr int TMEM_COLS = NBUF * ACC_COLS <= 256 ? 256 : 512;
   static constexpr int EPI_STAGE = 8 * 2048;  // 2 KB store-coalescing buffer per epilogue warp
+  static constexpr int STAGES = (227 * 1024 - EPI_STAGE - 2048) / (G2_A_STAGE + B_STAGE) > 8
+                                    ? 8
+                                    : (227 * 1024 - EPI_STAGE - 2048) / (G2_A_STAGE + B_STAGE);
   static constexpr int SMEM_BYTES = STAGES * (G2_A_STAGE + B_STAGE) + EPI_STAGE + 1024 + 256;
 };
 
-template <int BN>
+template <int BN, int NSUB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
     gemm2_tc_kernel(const __grid_constant__ GemmKParams p) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, NSUB>;
+  constexpr int NBUF = Cfg::NBUF;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -89,7 +98,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
     x0 = tw * p.bw;
     y0 = th * p.bh;
     b0 = tb * p.bb;
-    n0 = n_tile * BN;
+    n0 = n_tile * (NSUB * BN);
   };
 
   if (warp == 0) {
@@ -108,8 +117,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
           const uint32_t bar = mapa_rank(smem_u32(&full_bar[stage]), 0);
           tma_load_4d_2sm(&p.mapA[p.tap_map[tap]], bar, smem_a + stage * G2_A_STAGE, kc * 64, x0 + p.tap_dx[tap],
                           y0 + p.tap_dy[tap], b0);
-          tma_load_4d_2sm(&p.mapB, bar, smem_b + stage * Cfg::B_STAGE, kb * 64, n0 + static_cast<int>(rank) * Cfg::BH,
-                          p.b_batched ? y0 : 0, p.b_batched ? b0 : 0);
+#pragma unroll
+          for (int sub = 0; sub < NSUB; ++sub)
+            tma_load_4d_2sm(&p.mapB, bar, smem_b + stage * Cfg::B_STAGE + sub * Cfg::B_SUB, kb * 64,
+                            n0 + sub * BN + static_cast<int>(rank) * Cfg::BH, p.b_batched ? y0 : 0,
+                            p.b_batched ? b0 : 0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -125,17 +137,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
       uint32_t phase = 0;
       int it = 0;
       for (int t = cluster_id; t < total_tiles; t += nclusters, ++it) {
-        const int a = it & 1;
-        mbar_wait(&tmem_empty[a], ((it >> 1) & 1) ^ 1);
+        const int a = it % NBUF;
+        mbar_wait(&tmem_empty[a], ((it / NBUF) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + a * BN;
+        const uint32_t tmem_acc = tmem_base + a * Cfg::ACC_COLS;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t da = make_desc_k_sw128(smem_u32(smem_a + stage * G2_A_STAGE));
           const uint64_t db = make_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss_2cta(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub)
+              umma_f16_ss_2cta(tmem_acc + sub * BN, da + 2 * k, db + sub * (Cfg::B_SUB >> 4) + 2 * k, idesc,
+                               (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit_2cta(&empty_bar[stage], 0b11);
           if (++stage == STAGES) {
             stage = 0;
@@ -151,10 +168,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
     for (int t = cluster_id; t < total_tiles; t += nclusters, ++it) {
       int x0, y0, b0, n0;
       tile_coords(t, x0, y0, b0, n0);
-      const int a = it & 1;
+      const int a = it % NBUF;
       // the two warps of a lane quarter interleave 32-column chunks: twice the loads / stores in flight
-      gemm_epilogue<BN>(p, tmem_base + a * BN, warp, lane, x0, y0, b0, n0, &tmem_full[a], (it >> 1) & 1,
-                        (warp - 4) >> 2, 2, epi_stage + (warp - 4) * 2048);
+#pragma unroll
+      for (int sub = 0; sub < NSUB; ++sub)
+        gemm_epilogue<BN>(p, tmem_base + a * Cfg::ACC_COLS + sub * BN, warp, lane, x0, y0, b0, n0 + sub * BN,
+                          &tmem_full[a], (it / NBUF) & 1, (warp - 4) >> 2, 2, epi_stage + (warp - 4) * 2048);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[a]), 0));
@@ -169,38 +188,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
   }
 }
 
-template <int BN>
+template <int BN, int NSUB>
 static int set_attr2() {
-  SDW_CUDA_OK(cudaFuncSetAttribute(gemm2_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Gemm2Cfg<BN>::SMEM_BYTES));
+  SDW_CUDA_OK(cudaFuncSetAttribute(gemm2_tc_kernel<BN, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Gemm2Cfg<BN, NSUB>::SMEM_BYTES));
   return 0;
 }
 
 static bool g_init2 = false;
 int gemm2_init() {
   if (g_init2) return 0;
-  if (int e = set_attr2<128>()) return e;
-  if (int e = set_attr2<160>()) return e;
-  if (int e = set_attr2<192>()) return e;
-  if (int e = set_attr2<256>()) return e;
+  if (int e = set_attr2<128, 1>()) return e;
+  if (int e = set_attr2<160, 1>()) return e;
+  if (int e = set_attr2<192, 1>()) return e;
+  if (int e = set_attr2<256, 1>()) return e;
+  if (int e = set_attr2<160, 2>()) return e;
   g_init2 = true;
   return 0;
 }
 
 int launch_gemm2(const GemmLaunch& l, cudaStream_t stream) {
   if (int e = gemm2_init()) return e;
+  if (l.nsub == 2) {
+    if (l.bn != 160) {
+      set_error("the two-accumulator variant exists for BLOCK_N = 160 only");
+      return 1;
+    }
+    gemm2_tc_kernel<160, 2><<<l.grid, G2_THREADS, Gemm2Cfg<160, 2>::SMEM_BYTES, stream>>>(l.p);
+    SDW_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   switch (l.bn) {
     case 128:
-      gemm2_tc_kernel<128><<<l.grid, G2_THREADS, Gemm2Cfg<128>::SMEM_BYTES, stream>>>(l.p);
+      gemm2_tc_kernel<128, 1><<<l.grid, G2_THREADS, Gemm2Cfg<128, 1>::SMEM_BYTES, stream>>>(l.p);
       break;
     case 160:
-      gemm2_tc_kernel<160><<<l.grid, G2_THREADS, Gemm2Cfg<160>::SMEM_BYTES, stream>>>(l.p);
+      gemm2_tc_kernel<160, 1><<<l.grid, G2_THREADS, Gemm2Cfg<160, 1>::SMEM_BYTES, stream>>>(l.p);
       break;
     case 192:
-      gemm2_tc_kernel<192><<<l.grid, G2_THREADS, Gemm2Cfg<192>::SMEM_BYTES, stream>>>(l.p);
+      gemm2_tc_kernel<192, 1><<<l.grid, G2_THREADS, Gemm2Cfg<192, 1>::SMEM_BYTES, stream>>>(l.p);
       break;
     case 256:
-      gemm2_tc_kernel<256><<<l.grid, G2_THREADS, Gemm2Cfg<256>::SMEM_BYTES, stream>>>(l.p);
+      gemm2_tc_kernel<256, 1><<<l.grid, G2_THREADS, Gemm2Cfg<256, 1>::SMEM_BYTES, stream>>>(l.p);
       break;
     default:
       set_error("bad BLOCK_N for the 2-CTA kernel");

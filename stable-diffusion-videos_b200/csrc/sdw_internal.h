@@ -79,6 +79,7 @@ struct GemmLaunch {
   dim3 grid;
   int bn;   // BLOCK_N variant
   int ver;  // 1: one 128xBN tile per CTA (sdw_gemm.cu); 2: persistent CTA pairs, 256xBN tiles (sdw_gemm2.cu)
+  int nsub = 1;  // ver 2: accumulators per activation tile (2 -> 256 x 2*BN tiles, single-buffered TMEM)
 };
 
 // Describes one implicit GEMM in host terms; plan_gemm() turns it into a launch.
@@ -111,6 +112,7 @@ struct GemmDesc {
   int64_t vt_ld = 0;
   int bn = 0;   // 0 = auto
   int ver = 0;  // 0 = auto, 1 / 2 force a kernel version
+  int nsub = 0; // 0 = auto, 1 / 2: accumulators per activation tile in the 2-CTA kernel
 };
 
 int plan_gemm(const GemmDesc& d, GemmLaunch* out);

@@ -21,7 +21,7 @@ def _tol(ref):
     return float(ref.abs().max()) * 2.0 ** -9 + 1e-3
 
 
-def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None, ver=0):
+def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None, ver=0, nsub=0):
     """x: [B,H,W,C] fp16 cuda; returns NHWC fp16 output computed by the native kernel."""
     n = _native()
     B, H, W, Cc = x_nhwc.shape
@@ -59,6 +59,7 @@ def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn
         d.alpha = 1.0
         d.bn = bn
         d.ver = ver
+        d.nsub = nsub
         n.gemm(d)
     torch.cuda.synchronize()
     return out
@@ -284,3 +285,21 @@ def test_geglu_2cta():
     a, g = h.chunk(2, dim=-1)
     ref = (a * Fn.gelu(g)).reshape(1, 1, M, Ch)
     assert (out.float() - ref).abs().max().item() <= _tol(ref)
+
+
+# ---- two accumulators per activation tile (256 x 320 tiles, single-buffered TMEM) --------------------------------
+@pytest.mark.parametrize("B,H,W,Cc,N,conv", [(4, 64, 64, 320, 320, 1), (2, 32, 32, 640, 640, 1), (2, 16, 16, 128, 1280, 1),
+                                              (1, 8, 8, 64, 480, 1), (2, 64, 64, 64, 320, 2), (2, 16, 16, 64, 640, 3),
+                                              (1, 1, 5000, 1280, 960, 0)])
+def test_gemm_2cta_two_accumulators(B, H, W, Cc, N, conv):
+    x = _rand(B, H, W, Cc, seed=51)
+    k = 3 if conv else 1
+    w = _rand(N, Cc, k, k, scale=(k * k * Cc) ** -0.5, seed=52)
+    bias = _rand(N, seed=53).float()
+    oh, ow = (H // 2, W // 2) if conv == 2 else ((2 * H, 2 * W) if conv == 3 else (H, W))
+    resid = _rand(B, oh, ow, N, seed=54)
+    out = run_conv(x, w, conv, bias=bias, resid=resid, ver=2, bn=160, nsub=2)
+    ref = ref_conv(x, w if conv else w.reshape(N, Cc), conv, bias=bias, resid=resid)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= _tol(ref), (err, _tol(ref))
