@@ -367,9 +367,12 @@ static int variant_for(int d) {
   if (d <= 16) return 0;
   if (d <= 32) return 1;
   static const bool bkv64 = [] { const char* e = std::getenv("SDW_ATTN_BKV64"); return e && e[0] == '1'; }();
-  static const int poly = [] { const char* e = std::getenv("SDW_ATTN_POLY"); return e ? std::atoi(e) : 4; }();
+  static const int poly = [] { const char* e = std::getenv("SDW_ATTN_POLY"); return e ? std::atoi(e) : 0; }();
+  // measured equal within noise (profiles/r01_attn_bench_packed_poly.txt): the softmax warps are latency-, not
+  // MUFU-bound, so the default is the exact MUFU path (POLY = 0); SDW_ATTN_POLY=4|8 selects the offload variants
   if (d <= 48 && d > 32 && !bkv64 && poly == 0) return 7;
   if (d <= 48 && d > 32 && !bkv64 && poly == 8) return 8;
+  if (d <= 48 && d > 32 && poly != 4 && !bkv64) return 7;
   if (d <= 48) return bkv64 && d > 32 ? 6 : 2;
   if (d <= 64) return 3;
   if (d <= 80) return 4;

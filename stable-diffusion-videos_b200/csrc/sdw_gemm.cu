@@ -323,7 +323,7 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
       const int tiles = mp * ((d.N + width - 1) / width);
       const int waves = (tiles + 73) / 74;
       double cost = static_cast<double>(waves) * (16384.0 + 64.0 * width);
-      if (c.nsub == 2) cost *= 1.0 + 6.0 / kblocks;  // un-overlapped epilogue
+      if (c.nsub == 2) cost *= 1.0 + 24.0 / kblocks;  // un-overlapped epilogue ~ 24 K-block times (fit: profiles/r01_gemm_shapes_nsub2.txt)
       if (cost < best_cost) {
         best_cost = cost;
         best_bn = c.bn;
