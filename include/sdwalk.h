@@ -145,7 +145,8 @@ typedef struct sdw_gemm_desc {
   const void* A;             /* fp16 NHWC lattice base */
   int32_t C, W, H, B;
   int64_t sW, sH, sB;        /* element strides */
-  int32_t conv;              /* 0: 1x1; 1: 3x3 s1 p1; 2: 3x3 s2 p1; 3: nearest-up2 + 3x3 (one output parity) */
+  int32_t conv;              /* 0: 1x1; 1: 3x3 s1 p1; 2: 3x3 s2 p1; 3: nearest-up2 + 3x3 for one output parity,
+                                folded to a 2x2 conv (Wt = the parity's sdw_pack_weight_up4 block) */
   int32_t up_px, up_py;
   const void* Wt;            /* fp16 [N][taps*Cp] K-major, Cp = ceil64(C) */
   int32_t N;
@@ -181,6 +182,9 @@ int sdw_attention(const void* q, int64_t q_ld, const void* k, int64_t k_ld, cons
 
 /* pack an OIHW fp16 conv / [N][K] linear weight into the kernel's K-major [N][taps][Cp] layout */
 int sdw_pack_weight(const void* w_oihw, int N, int C, int kh, int kw, int geglu_interleave, void* out, void* stream);
+/* upsampler (nearest x2 + 3x3) weights folded to four 2x2 parity convs: out = 4 blocks of [N][4][ceil64(C)];
+ * block (py*2+px) is the weight operand of a conv = 3 GEMM with up_py/up_px = (py, px) */
+int sdw_pack_weight_up4(const void* w_oihw, int N, int C, void* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -106,5 +106,16 @@ def pack_weight(w, geglu=False):
     return out
 
 
+def pack_weight_up4(w):
+    """[N, C, 3, 3] upsampler weight -> [4 parities][N][4 taps][ceil64(C)] (taps pre-summed in fp32)."""
+    require_cuda(w)
+    w = w.to(torch.float16).contiguous()
+    N, Cc = w.shape[0], w.shape[1]
+    cp = (Cc + 63) // 64 * 64
+    out = torch.empty((4, N, 4 * cp), dtype=torch.float16, device=w.device)
+    check(lib().sdw_pack_weight_up4(ptr(w), N, Cc, ptr(out), stream_ptr()))
+    return out
+
+
 def gemm(desc):
     check(lib().sdw_gemm(C.byref(desc), stream_ptr()))

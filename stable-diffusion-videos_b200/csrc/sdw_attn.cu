@@ -208,56 +208,109 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::N
     uint8_t* p_row = p_smem + r * 128;
     const int sw = r & 7;
 
+    // Two softmax paths per KV tile (the FlashAttention-4 "lazy rescale" idea):
+    //  fast : exponentials are taken against the row's REFERENCE max m_run (the true running max as of the last slow
+    //         tile) instead of this tile's max, so nothing depends on a whole-row reduction: 32-column TMEM loads are
+    //         software-pipelined against the MUFU / FMA work of the previous chunk, and O is never rescaled.  P values
+    //         may exceed 1, by at most 2^LAZY_LOG2 — harmless in fp16 P / fp32 sums since every term shares m_run.
+    //  slow : the exact online-softmax update (true max, O rescale in TMEM).  Taken for tile 0, for ragged tiles, and
+    //         — warp-uniformly — whenever any row's tile max exceeds its reference by more than 2^LAZY_LOG2
+    //         (S_j is still intact in TMEM, so the tile is simply re-read).
+    constexpr float LAZY_LOG2 = 8.f;
+    uint32_t pk[BKV / 2];  // P_j of this row, packed fp16 pairs
+
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(&s_full[j % SB], (j / SB) & 1);
       tc_fence_after();
       const uint32_t t_s = tmem + lane_base + (j % SB) * BKV;
-      // all TMEM loads of the tile are issued back to back, one wait
-      uint32_t vu[BKV / 32][32];
-#pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) tmem_ld_32x32(t_s + c * 32, vu[c]);
-      tmem_ld_wait();
-      float v[BKV];
-#pragma unroll
-      for (int i = 0; i < BKV; ++i) v[i] = __uint_as_float(vu[i / 32][i % 32]);
       const int kv0 = j * BKV;
-      if (kv0 + BKV > p.Nk) {
+      const bool ragged = kv0 + BKV > p.Nk;
+      bool need_slow = (j == 0) || ragged;
+      float alpha = 1.f;
+
+      if (!need_slow) {
+        // ---------------- fast path: chunk-pipelined, reference max ----------------
+        const float mb = m_run * sl2;
+        const uint64_t sl2_2 = pk2(sl2, sl2), nmb_2 = pk2(-mb, -mb);
+        uint64_t sm2[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
+        float mx[2] = {-INFINITY, -INFINITY};
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(t_s, va);
+        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < BKV; ++i)
-          if (kv0 + i >= p.Nk) v[i] = -INFINITY;
+        for (int c = 0; c < BKV / 32; ++c) {
+          uint32_t(&cur)[32] = (c & 1) ? vb : va;
+          uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+          if (c + 1 < BKV / 32) tmem_ld_32x32(t_s + (c + 1) * 32, nxt);  // in flight while this chunk is exponentiated
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float x0 = __uint_as_float(cur[i]), x1 = __uint_as_float(cur[i + 1]);
+            mx[0] = fmaxf(mx[0], x0);
+            mx[1] = fmaxf(mx[1], x1);
+            float t0, t1;
+            upk2(fma2(pk2(x0, x1), sl2_2, nmb_2), t0, t1);
+            const float e0 = ex2f(t0), e1 = ex2f(t1);
+            sm2[(i >> 1) & 1] = add2(sm2[(i >> 1) & 1], pk2(e0, e1));
+            pk[c * 16 + (i >> 1)] = pack_h2(e0, e1);
+          }
+          if (c + 1 < BKV / 32) tmem_ld_wait();
+        }
+        const float m_t = fmaxf(mx[0], mx[1]);
+        need_slow = __any_sync(0xffffffffu, (m_t - m_run) * sl2 > LAZY_LOG2);
+        if (!need_slow) {
+          float s0, s1, s2, s3;
+          upk2(sm2[0], s0, s1);
+          upk2(sm2[1], s2, s3);
+          l_run += (s0 + s1) + (s2 + s3);
+        }
       }
-      // row max / row sum with 4 independent accumulators: a single 128-long dependent chain would cost
-      // 128 x (4-cycle ALU latency) per reduction with only two softmax warps per scheduler to hide it
-      float mx[4] = {v[0], v[1], v[2], v[3]};
+      if (need_slow) {
+        // ---------------- slow path: exact online softmax ----------------
+        float v[BKV];
+        {
+          uint32_t vu[BKV / 32][32];
 #pragma unroll
-      for (int i = 4; i < BKV; ++i) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
-      const float m_t = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      const float m_new = fmaxf(m_run, m_t);
-      const float alpha = ex2f((m_run - m_new) * sl2);
-      const float mb = m_new * sl2;
-      // (s - m) * scale*log2e as FFMA2, exp2 per lane (MUFU, every POLY-th on the FMA pipe), sums as FADD2 pairs
-      const uint64_t sl2_2 = pk2(sl2, sl2), nmb_2 = pk2(-mb, -mb);
-      uint64_t sm2[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
+          for (int c = 0; c < BKV / 32; ++c) tmem_ld_32x32(t_s + c * 32, vu[c]);
+          tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < BKV; i += 2) {
-        float t0, t1;
-        upk2(fma2(pk2(v[i], v[i + 1]), sl2_2, nmb_2), t0, t1);
-        v[i] = ex2f(t0);
-        v[i + 1] = (POLY > 0 && (i / 2) % (POLY > 1 ? POLY / 2 : 1) == (POLY > 1 ? POLY / 2 : 1) - 1) ? ex2_poly(t1)
-                                                                                                      : ex2f(t1);
-        sm2[(i >> 1) & 1] = add2(sm2[(i >> 1) & 1], pk2(v[i], v[i + 1]));
+          for (int i = 0; i < BKV; ++i) v[i] = __uint_as_float(vu[i / 32][i % 32]);
+        }
+        if (ragged) {
+#pragma unroll
+          for (int i = 0; i < BKV; ++i)
+            if (kv0 + i >= p.Nk) v[i] = -INFINITY;
+        }
+        float mx[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+        for (int i = 4; i < BKV; ++i) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
+        const float m_t = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        const float m_new = fmaxf(m_run, m_t);
+        alpha = ex2f((m_run - m_new) * sl2);
+        const float mb = m_new * sl2;
+        const uint64_t sl2_2 = pk2(sl2, sl2), nmb_2 = pk2(-mb, -mb);
+        uint64_t sm2[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
+#pragma unroll
+        for (int i = 0; i < BKV; i += 2) {
+          float t0, t1;
+          upk2(fma2(pk2(v[i], v[i + 1]), sl2_2, nmb_2), t0, t1);
+          const float e0 = ex2f(t0);
+          const float e1 = (POLY > 0 && (i / 2) % (POLY > 1 ? POLY / 2 : 1) == (POLY > 1 ? POLY / 2 : 1) - 1)
+                               ? ex2_poly(t1)
+                               : ex2f(t1);
+          sm2[(i >> 1) & 1] = add2(sm2[(i >> 1) & 1], pk2(e0, e1));
+          pk[i >> 1] = pack_h2(e0, e1);
+        }
+        float s0, s1, s2, s3;
+        upk2(sm2[0], s0, s1);
+        upk2(sm2[1], s2, s3);
+        l_run = fmaf(l_run, alpha, (s0 + s1) + (s2 + s3));
+        m_run = m_new;
       }
-      float s0, s1, s2, s3;
-      upk2(sm2[0], s0, s1);
-      upk2(sm2[1], s2, s3);
-      const float sum = (s0 + s1) + (s2 + s3);
-      l_run = fmaf(l_run, alpha, sum);
-      m_run = m_new;
       if (j > 0) {
         // P smem and the O accumulator are free once PV_{j-1} has completed
         mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {
+        if (need_slow && __any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll
           for (int c = 0; c < DVP / 16; ++c) {
             uint32_t o[16];
@@ -274,10 +327,10 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::N
 #pragma unroll
       for (int c8 = 0; c8 < BKV / 8; ++c8) {
         uint4 u;
-        u.x = pack_h2(v[c8 * 8 + 0], v[c8 * 8 + 1]);
-        u.y = pack_h2(v[c8 * 8 + 2], v[c8 * 8 + 3]);
-        u.z = pack_h2(v[c8 * 8 + 4], v[c8 * 8 + 5]);
-        u.w = pack_h2(v[c8 * 8 + 6], v[c8 * 8 + 7]);
+        u.x = pk[c8 * 4 + 0];
+        u.y = pk[c8 * 4 + 1];
+        u.z = pk[c8 * 4 + 2];
+        u.w = pk[c8 * 4 + 3];
         *reinterpret_cast<uint4*>(p_row + (c8 >> 3) * (ATT_BQ * 128) + (((c8 & 7) ^ sw) << 4)) = u;
       }
       fence_proxy_async_smem();

@@ -76,6 +76,10 @@ int sdw_attention(const void* q, int64_t q_ld, const void* k, int64_t k_ld, cons
   return launch_attention(L, static_cast<cudaStream_t>(stream));
 }
 
+int sdw_pack_weight_up4(const void* w_oihw, int N, int C, void* out, void* stream) {
+  return pack_weight_up4(w_oihw, N, C, out, static_cast<cudaStream_t>(stream));
+}
+
 int sdw_pack_weight(const void* w_oihw, int N, int C, int kh, int kw, int geglu_interleave, void* out, void* stream) {
   return pack_weight(w_oihw, N, C, kh, kw, geglu_interleave, out, static_cast<cudaStream_t>(stream));
 }

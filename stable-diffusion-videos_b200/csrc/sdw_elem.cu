@@ -236,6 +236,44 @@ __global__ void pack_weight_kernel(const __half* __restrict__ w, int N, int C, i
   }
 }
 
+// nearest-neighbour x2 upsampling followed by a 3x3 conv == four 2x2 convs on the LOW-res grid, one per output
+// parity (py, px): the taps that read the same low-res pixel are pre-summed (fp32, rounded once to fp16), which cuts
+// the upsampler FLOPs by 9/4.  Layout per parity: [N][4 taps (a*2+b)][Cp]; row group a / column group b:
+//   parity 0: group 0 = {k=0} (shift -1), group 1 = {k=1,2} (shift 0);  parity 1: group 0 = {k=0,1} (0), group 1 = {k=2} (+1)
+__global__ void pack_weight_up4_kernel(const __half* __restrict__ w, int N, int C, int Cp, __half* __restrict__ out) {
+  const int64_t per = static_cast<int64_t>(N) * 4 * Cp;
+  const int64_t total = per * 4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int par = static_cast<int>(i / per);
+    const int64_t r = i - par * per;
+    const int c = static_cast<int>(r % Cp);
+    const int tap = static_cast<int>((r / Cp) % 4);
+    const int n = static_cast<int>(r / (static_cast<int64_t>(Cp) * 4));
+    const int py = par >> 1, px = par & 1, a = tap >> 1, b = tap & 1;
+    float acc = 0.f;
+    if (c < C) {
+      const int ky0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2);
+      const int ky1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+      const int kx0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2);
+      const int kx1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+      for (int ky = ky0; ky <= ky1; ++ky)
+        for (int kx = kx0; kx <= kx1; ++kx) acc += __half2float(w[((static_cast<int64_t>(n) * C + c) * 3 + ky) * 3 + kx]);
+    }
+    out[i] = __float2half_rn(acc);
+  }
+}
+
+int pack_weight_up4(const void* w, int N, int C, void* out, cudaStream_t stream) {
+  SDW_REQUIRE(w && out && N > 0 && C > 0, "bad weight");
+  const int Cp = (C + 63) / 64 * 64;
+  const int64_t total = static_cast<int64_t>(N) * 16 * Cp;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 16));
+  pack_weight_up4_kernel<<<blocks, 256, 0, stream>>>(static_cast<const __half*>(w), N, C, Cp, static_cast<__half*>(out));
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int pack_weight(const void* w, int N, int C, int kh, int kw, int geglu, void* out, cudaStream_t stream) {
   SDW_REQUIRE(w && out && N > 0 && C > 0 && kh > 0 && kw > 0, "bad weight");
   if (geglu) SDW_REQUIRE(N % 64 == 0, "GEGLU interleave needs N % 64 == 0");

@@ -36,7 +36,7 @@ struct T {  // NHWC fp16 view
   int64_t pixels() const { return static_cast<int64_t>(B) * H * W; }
 };
 
-enum ParamKind { P_PACKED, P_RAW, P_VEC };
+enum ParamKind { P_PACKED, P_RAW, P_VEC, P_PACKED_UP4 };
 struct ParamSlot {
   ParamKind kind;
   void* dst;
@@ -122,6 +122,13 @@ struct Engine {
     params[name] = s;
     return dst;
   }
+  // upsampler conv: four parity blocks of pre-summed 2x2 taps (pack_weight_up4)
+  const __half* w_packed_up4(const std::string& name, int N, int C) {
+    const int cp = (C + 63) / 64 * 64;
+    __half* dst = static_cast<__half*>(alloc(static_cast<size_t>(N) * 16 * cp * 2));
+    params[name] = ParamSlot{P_PACKED_UP4, dst, N, C, 3, 3, 0, static_cast<int64_t>(N) * C * 9};
+    return dst;
+  }
   const __half* w_raw(const std::string& name, int64_t numel) {
     __half* dst = static_cast<__half*>(alloc(static_cast<size_t>(numel) * 2));
     params[name] = ParamSlot{P_RAW, dst, 0, 0, 0, 0, 0, numel};
@@ -169,6 +176,7 @@ struct Engine {
       d.sW = x.ld; d.sH = static_cast<int64_t>(x.W) * x.ld; d.sB = static_cast<int64_t>(x.H) * x.W * x.ld;
       d.conv = kind; d.up_py = par / 2; d.up_px = par % 2;
       d.Wt = w; d.N = N; d.bias = bias;
+      if (kind == 3 && w) d.Wt = w + static_cast<size_t>(par) * N * 4 * ((x.C + 63) / 64 * 64);
       d.out = out.p; d.ldc = out.ld;
       if (resid) { d.resid = resid->p; d.ldr = resid->ld; }
       d.mode = mode;
@@ -472,7 +480,7 @@ struct Engine {
       }
       if (!last) {
         T dest = slice(cat[i + 1][0].buf, 0, cat[i + 1][0].rin);
-        if (int e = conv(up_in, w_packed(bp + ".upsamplers.0.conv.weight", cout, cout, 3),
+        if (int e = conv(up_in, w_packed_up4(bp + ".upsamplers.0.conv.weight", cout, cout),
                          vec(bp + ".upsamplers.0.conv.bias", cout), cout, 3, dest))
           return e;
       } else {
@@ -567,7 +575,7 @@ struct Engine {
       }
       if (i < nlev - 1) {
         T o = act(h.B, h.H * 2, h.W * 2, cout);
-        if (int e = conv(h, w_packed(bp + ".upsamplers.0.conv.weight", cout, cout, 3),
+        if (int e = conv(h, w_packed_up4(bp + ".upsamplers.0.conv.weight", cout, cout),
                          vec(bp + ".upsamplers.0.conv.bias", cout), cout, 3, o))
           return e;
         h = o;
@@ -753,6 +761,7 @@ int sdw_engine_load_param(sdw_engine* e, const char* name, const void* src_f16, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = 0;
   if (s.kind == P_PACKED) rc = pack_weight(src_f16, s.N, s.C, s.kh, s.kw, s.geglu, s.dst, st);
+  else if (s.kind == P_PACKED_UP4) rc = pack_weight_up4(src_f16, s.N, s.C, s.dst, st);
   else if (s.kind == P_RAW) {
     SDW_CUDA_OK(cudaMemcpyAsync(s.dst, src_f16, static_cast<size_t>(numel) * 2, cudaMemcpyDeviceToDevice, st));
   } else rc = half_to_float(static_cast<const __half*>(src_f16), static_cast<float*>(s.dst), numel, s.N, st);

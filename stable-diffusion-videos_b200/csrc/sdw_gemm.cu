@@ -225,7 +225,7 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
   const int kchunks = (d.C + BK - 1) / BK;
   const int Cp = kchunks * BK;
   p.kchunks = kchunks;
-  p.ntaps = d.conv == 0 ? 1 : 9;
+  p.ntaps = d.conv == 0 ? 1 : (d.conv == 3 ? 4 : 9);
   // domain (lattice the M tiles walk over) and the tap table
   int Wd = d.W, Hd = d.H;
   int nmaps = 1;
@@ -255,14 +255,13 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
       p.tap_dx[t] = static_cast<int8_t>(sh[kx]);
     }
   } else if (d.conv == 3) {
-    // nearest-up x2 then 3x3: output parity (py,px) reads low-res rows yo + floor((py+ky-1)/2)
-    const int sh0[3] = {-1, 0, 0};
-    const int sh1[3] = {0, 0, 1};
-    for (int t = 0; t < 9; ++t) {
-      const int ky = t / 3, kx = t % 3;
+    // nearest-up x2 then 3x3, folded into a 2x2 conv per output parity (weights from pack_weight_up4):
+    // parity 0 reads low-res rows {yo-1, yo}, parity 1 reads {yo, yo+1}; same for columns
+    for (int t = 0; t < 4; ++t) {
+      const int a = t >> 1, b = t & 1;
       p.tap_map[t] = 0;
-      p.tap_dy[t] = static_cast<int8_t>(d.up_py ? sh1[ky] : sh0[ky]);
-      p.tap_dx[t] = static_cast<int8_t>(d.up_px ? sh1[kx] : sh0[kx]);
+      p.tap_dy[t] = static_cast<int8_t>(d.up_py ? a : a - 1);
+      p.tap_dx[t] = static_cast<int8_t>(d.up_px ? b : b - 1);
     }
     p.os = 2;
     p.ox = d.up_px;

@@ -87,7 +87,8 @@ struct GemmDesc {
   const __half* A = nullptr;       // lattice base
   int C = 0, W = 0, H = 1, B = 1;  // input lattice extents (elements)
   int64_t sW = 0, sH = 0, sB = 0;  // element strides of the input lattice (channel stride is 1)
-  int conv = 0;                    // 0: 1x1 / linear; 1: 3x3 stride 1 pad 1; 2: 3x3 stride 2 pad 1; 3: nearest-up2 + 3x3 (parity in up_px/up_py)
+  int conv = 0;                    // 0: 1x1 / linear; 1: 3x3 stride 1 pad 1; 2: 3x3 stride 2 pad 1; 3: nearest-up2 + 3x3 as a
+                                   //    2x2 conv per output parity (up_px/up_py) on pack_weight_up4 weights
   int up_px = 0, up_py = 0;
   const __half* Wt = nullptr;      // [N][ntaps*Cp] (Cp = C rounded up to 64) K-major
   int N = 0;
@@ -155,6 +156,8 @@ int cfg_sched_step(const float* eps, int has_uncond, float* x, float* x_base, fl
 int latents_init(const void* latents, int is_f16, float sigma, float in_scale, float* x, void* model_in, int cpad,
                  int dup, int F, int C, int H, int W, cudaStream_t stream);
 int pack_weight(const void* w, int N, int C, int kh, int kw, int geglu, void* out, cudaStream_t stream);
+// upsampler weights: 4 parity blocks of [N][4][Cp] (taps pre-summed); block p = py*2+px at out + p*N*4*Cp
+int pack_weight_up4(const void* w, int N, int C, void* out, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------
 // norm / softmax / small-channel layers (sdw_norm.cu)

@@ -26,7 +26,7 @@ def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn
     n = _native()
     B, H, W, Cc = x_nhwc.shape
     N = w_oihw.shape[0]
-    wp = n.pack_weight(w_oihw, geglu=(mode == 1))
+    wp = n.pack_weight_up4(w_oihw) if conv == 3 else n.pack_weight(w_oihw, geglu=(mode == 1))
     if conv == 2:
         OH, OW = H // 2, W // 2
     elif conv == 3:
@@ -43,7 +43,7 @@ def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn
         d.sW, d.sH, d.sB = x_nhwc.stride(2), x_nhwc.stride(1), x_nhwc.stride(0)
         d.conv = conv
         d.up_px, d.up_py = px, py
-        d.Wt = wp.data_ptr()
+        d.Wt = wp[py * 2 + px].data_ptr() if conv == 3 else wp.data_ptr()
         d.N = N
         d.bias = bias.data_ptr() if bias is not None else None
         if rowvec is not None:
