@@ -410,6 +410,7 @@ static int attn_init() {
   if (int e = attn_set_attr<1, 48, 64, 2, 1>()) return e;
   if (int e = attn_set_attr<1, 48, 128, 2, 1, 0>()) return e;
   if (int e = attn_set_attr<1, 48, 128, 2, 1, 8>()) return e;
+  if (int e = attn_set_attr<2, 80, 64, 2, 1, 0>()) return e;
   g_attn_init = true;
   return 0;
 }
@@ -428,7 +429,8 @@ static int variant_for(int d) {
   if (d <= 48 && d > 32 && poly != 4 && !bkv64) return 7;
   if (d <= 48) return bkv64 && d > 32 ? 6 : 2;
   if (d <= 64) return 3;
-  if (d <= 80) return 4;
+  static const bool d80_bkv64 = [] { const char* e = std::getenv("SDW_ATTN_D80_BKV64"); return e && e[0] == '1'; }();
+  if (d <= 80) return d80_bkv64 ? 9 : 4;
   return 5;
 }
 
@@ -440,8 +442,8 @@ int plan_attention(const AttnDesc& a, AttnLaunch* L) {
   AttnLaunchImpl* I = reinterpret_cast<AttnLaunchImpl*>(L->storage);
   std::memset(I, 0, sizeof(*I));
   I->variant = variant_for(a.d);
-  const int bkv = (I->variant == 5 || I->variant == 6) ? 64 : 128;
-  const int dvp_tab[9] = {16, 32, 48, 64, 80, 160, 48, 48, 48};
+  const int bkv = (I->variant == 5 || I->variant == 6 || I->variant == 9) ? 64 : 128;
+  const int dvp_tab[10] = {16, 32, 48, 64, 80, 160, 48, 48, 48, 80};
   const int dvp = dvp_tab[I->variant];
   AttnKParams& p = I->p;
   p.Nq = a.Nq; p.Nk = a.Nk; p.d = a.d; p.heads = a.heads;
@@ -489,6 +491,7 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     case 6: attn_fwd_kernel<1, 48, 64, 2, 1><<<I->grid, ATT_THREADS, AttnCfg<1, 48, 64, 2, 1>::SMEM, stream>>>(I->p); break;
     case 7: attn_fwd_kernel<1, 48, 128, 2, 1, 0><<<I->grid, ATT_THREADS, AttnCfg<1, 48, 128, 2, 1>::SMEM, stream>>>(I->p); break;
     case 8: attn_fwd_kernel<1, 48, 128, 2, 1, 8><<<I->grid, ATT_THREADS, AttnCfg<1, 48, 128, 2, 1>::SMEM, stream>>>(I->p); break;
+    case 9: attn_fwd_kernel<2, 80, 64, 2, 1, 0><<<I->grid, ATT_THREADS, AttnCfg<2, 80, 64, 2, 1>::SMEM, stream>>>(I->p); break;
     default: set_error("bad attention variant"); return 1;
   }
   SDW_CUDA_OK(cudaGetLastError());
