@@ -429,8 +429,10 @@ static int variant_for(int d) {
   if (d <= 48 && d > 32 && poly != 4 && !bkv64) return 7;
   if (d <= 48) return bkv64 && d > 32 ? 6 : 2;
   if (d <= 64) return 3;
-  static const bool d80_bkv64 = [] { const char* e = std::getenv("SDW_ATTN_D80_BKV64"); return e && e[0] == '1'; }();
-  if (d <= 80) return d80_bkv64 ? 9 : 4;
+  // 64 < d <= 80: the BKV = 64 tile (2 CTAs per SM) beats the double-buffered BKV = 128 one (1 CTA per SM):
+  // 109 vs 129 us self, 28 vs 44 us cross at batch 16 (profiles/r01_attn_bench_lazy.txt); SDW_ATTN_D80_BKV64=0 reverts
+  static const bool d80_bkv128 = [] { const char* e = std::getenv("SDW_ATTN_D80_BKV64"); return e && e[0] == '0'; }();
+  if (d <= 80) return d80_bkv128 ? 4 : 9;
   return 5;
 }
 
