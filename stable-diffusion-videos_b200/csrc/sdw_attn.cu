@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::N
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ============================ TMA producer ============================================
@@ -484,16 +486,16 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
   if (int e = attn_init()) return e;
   const AttnLaunchImpl* I = reinterpret_cast<const AttnLaunchImpl*>(L.storage);
   switch (I->variant) {
-    case 0: attn_fwd_kernel<1, 16, 128, 2, 1><<<I->grid, ATT_THREADS, AttnCfg<1, 16, 128, 2, 1>::SMEM, stream>>>(I->p); break;
-    case 1: attn_fwd_kernel<1, 32, 128, 2, 1><<<I->grid, ATT_THREADS, AttnCfg<1, 32, 128, 2, 1>::SMEM, stream>>>(I->p); break;
-    case 2: attn_fwd_kernel<1, 48, 128, 2, 1><<<I->grid, ATT_THREADS, AttnCfg<1, 48, 128, 2, 1>::SMEM, stream>>>(I->p); break;
-    case 3: attn_fwd_kernel<1, 64, 128, 2, 1><<<I->grid, ATT_THREADS, AttnCfg<1, 64, 128, 2, 1>::SMEM, stream>>>(I->p); break;
-    case 4: attn_fwd_kernel<2, 80, 128, 2, 2><<<I->grid, ATT_THREADS, AttnCfg<2, 80, 128, 2, 2>::SMEM, stream>>>(I->p); break;
-    case 5: attn_fwd_kernel<3, 160, 64, 3, 2><<<I->grid, ATT_THREADS, AttnCfg<3, 160, 64, 3, 2>::SMEM, stream>>>(I->p); break;
-    case 6: attn_fwd_kernel<1, 48, 64, 2, 1><<<I->grid, ATT_THREADS, AttnCfg<1, 48, 64, 2, 1>::SMEM, stream>>>(I->p); break;
-    case 7: attn_fwd_kernel<1, 48, 128, 2, 1, 0><<<I->grid, ATT_THREADS, AttnCfg<1, 48, 128, 2, 1>::SMEM, stream>>>(I->p); break;
-    case 8: attn_fwd_kernel<1, 48, 128, 2, 1, 8><<<I->grid, ATT_THREADS, AttnCfg<1, 48, 128, 2, 1>::SMEM, stream>>>(I->p); break;
-    case 9: attn_fwd_kernel<2, 80, 64, 2, 1, 0><<<I->grid, ATT_THREADS, AttnCfg<2, 80, 64, 2, 1>::SMEM, stream>>>(I->p); break;
+    case 0: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 16, 128, 2, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 16, 128, 2, 1>::SMEM, stream, I->p)); break;
+    case 1: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 32, 128, 2, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 32, 128, 2, 1>::SMEM, stream, I->p)); break;
+    case 2: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 2, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 2, 1>::SMEM, stream, I->p)); break;
+    case 3: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 64, 128, 2, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 64, 128, 2, 1>::SMEM, stream, I->p)); break;
+    case 4: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<2, 80, 128, 2, 2>, I->grid, dim3(ATT_THREADS), AttnCfg<2, 80, 128, 2, 2>::SMEM, stream, I->p)); break;
+    case 5: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<3, 160, 64, 3, 2>, I->grid, dim3(ATT_THREADS), AttnCfg<3, 160, 64, 3, 2>::SMEM, stream, I->p)); break;
+    case 6: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 64, 2, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 64, 2, 1>::SMEM, stream, I->p)); break;
+    case 7: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 2, 1, 0>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 2, 1>::SMEM, stream, I->p)); break;
+    case 8: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 2, 1, 8>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 2, 1>::SMEM, stream, I->p)); break;
+    case 9: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<2, 80, 64, 2, 1, 0>, I->grid, dim3(ATT_THREADS), AttnCfg<2, 80, 64, 2, 1>::SMEM, stream, I->p)); break;
     default: set_error("bad attention variant"); return 1;
   }
   SDW_CUDA_OK(cudaGetLastError());

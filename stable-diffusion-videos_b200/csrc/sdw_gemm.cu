@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // =========================== TMA producer ===============================
@@ -424,16 +426,16 @@ int launch_gemm(const GemmLaunch& l, cudaStream_t stream) {
   if (l.ver == 2) return launch_gemm2(l, stream);
   switch (l.bn) {
     case 64:
-      gemm_tc_kernel<64><<<l.grid, GEMM_THREADS, GemmCfg<64>::SMEM_BYTES, stream>>>(l.p);
+      SDW_CUDA_OK(launch_pdl(gemm_tc_kernel<64>, l.grid, dim3(GEMM_THREADS), GemmCfg<64>::SMEM_BYTES, stream, l.p));
       break;
     case 128:
-      gemm_tc_kernel<128><<<l.grid, GEMM_THREADS, GemmCfg<128>::SMEM_BYTES, stream>>>(l.p);
+      SDW_CUDA_OK(launch_pdl(gemm_tc_kernel<128>, l.grid, dim3(GEMM_THREADS), GemmCfg<128>::SMEM_BYTES, stream, l.p));
       break;
     case 160:
-      gemm_tc_kernel<160><<<l.grid, GEMM_THREADS, GemmCfg<160>::SMEM_BYTES, stream>>>(l.p);
+      SDW_CUDA_OK(launch_pdl(gemm_tc_kernel<160>, l.grid, dim3(GEMM_THREADS), GemmCfg<160>::SMEM_BYTES, stream, l.p));
       break;
     case 256:
-      gemm_tc_kernel<256><<<l.grid, GEMM_THREADS, GemmCfg<256>::SMEM_BYTES, stream>>>(l.p);
+      SDW_CUDA_OK(launch_pdl(gemm_tc_kernel<256>, l.grid, dim3(GEMM_THREADS), GemmCfg<256>::SMEM_BYTES, stream, l.p));
       break;
     default:
       set_error("bad BLOCK_N");

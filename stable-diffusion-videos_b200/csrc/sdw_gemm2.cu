@@ -86,6 +86,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();               // the set-up above overlapped the previous kernel's tail; its outputs are visible from here
+  pdl_launch_dependents();  // let the next kernel's CTAs start their own set-up as soon as SMs free up
   auto tile_coords = [&](int t, int& x0, int& y0, int& b0, int& n0) {
     // N fastest: the n_tiles column tiles of one M pair run on neighbouring clusters at the same time, so the
     // activation tile is fetched from DRAM once and re-read from L2 (the whole weight matrix is L2-resident anyway)
@@ -214,22 +216,22 @@ int launch_gemm2(const GemmLaunch& l, cudaStream_t stream) {
       set_error("the two-accumulator variant exists for BLOCK_N = 160 only");
       return 1;
     }
-    gemm2_tc_kernel<160, 2><<<l.grid, G2_THREADS, Gemm2Cfg<160, 2>::SMEM_BYTES, stream>>>(l.p);
+    SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<160, 2>, l.grid, dim3(G2_THREADS), Gemm2Cfg<160, 2>::SMEM_BYTES, stream, l.p));
     SDW_CUDA_OK(cudaGetLastError());
     return 0;
   }
   switch (l.bn) {
     case 128:
-      gemm2_tc_kernel<128, 1><<<l.grid, G2_THREADS, Gemm2Cfg<128, 1>::SMEM_BYTES, stream>>>(l.p);
+      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<128, 1>, l.grid, dim3(G2_THREADS), Gemm2Cfg<128, 1>::SMEM_BYTES, stream, l.p));
       break;
     case 160:
-      gemm2_tc_kernel<160, 1><<<l.grid, G2_THREADS, Gemm2Cfg<160, 1>::SMEM_BYTES, stream>>>(l.p);
+      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<160, 1>, l.grid, dim3(G2_THREADS), Gemm2Cfg<160, 1>::SMEM_BYTES, stream, l.p));
       break;
     case 192:
-      gemm2_tc_kernel<192, 1><<<l.grid, G2_THREADS, Gemm2Cfg<192, 1>::SMEM_BYTES, stream>>>(l.p);
+      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<192, 1>, l.grid, dim3(G2_THREADS), Gemm2Cfg<192, 1>::SMEM_BYTES, stream, l.p));
       break;
     case 256:
-      gemm2_tc_kernel<256, 1><<<l.grid, G2_THREADS, Gemm2Cfg<256, 1>::SMEM_BYTES, stream>>>(l.p);
+      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<256, 1>, l.grid, dim3(G2_THREADS), Gemm2Cfg<256, 1>::SMEM_BYTES, stream, l.p));
       break;
     default:
       set_error("bad BLOCK_N for the 2-CTA kernel");

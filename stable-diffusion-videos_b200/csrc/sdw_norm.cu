@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(256) gn_partial_det_kernel(const __half* __res
                                                              int64_t P, int pix_per_chunk,
                                                              float2* __restrict__ part) {
   extern __shared__ float sm[];  // [rows][C] sums then [rows][C] squares
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int cg = C / G;
   const int vecs = C / 8;
@@ -90,6 +92,8 @@ __global__ void __launch_bounds__(256) gn_partial_det_kernel(const __half* __res
 // one warp per (b, g): fixed-order reduction of the chunk partials -> (mean, rstd)
 __global__ void __launch_bounds__(256) gn_finalize_kernel(const float2* __restrict__ part, int nchunks, int G, int BG,
                                                           float count, float eps, float2* __restrict__ stats) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (idx >= BG) return;
   const int lane = threadIdx.x & 31;
@@ -115,6 +119,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
                                                        const float* __restrict__ beta, int silu,
                                                        __half* __restrict__ y, int64_t ldy, int pix_per_block) {
   __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.y;
   const int cg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
@@ -209,17 +215,15 @@ int groupnorm(const __half* x, int64_t ldx, int B, int64_t P, int C, int G, cons
   const size_t smem = static_cast<size_t>(2) * rows * C * sizeof(float);
   SDW_REQUIRE(smem <= 48 * 1024, "GroupNorm: channel count too large for the stats kernel");
   float2* stats = partial_ws + static_cast<size_t>(B) * nchunks * G;
-  gn_partial_det_kernel<<<dim3(nchunks, B), 256, smem, stream>>>(x, ldx, C, G, P, ppc, partial_ws);
-  SDW_CUDA_OK(cudaGetLastError());
+  SDW_CUDA_OK(launch_pdl(gn_partial_det_kernel, dim3(nchunks, B), dim3(256), smem, stream, x, ldx, C, G, P, ppc, partial_ws));
   const int BG = B * G;
-  gn_finalize_kernel<<<(BG + 7) / 8, 256, 0, stream>>>(partial_ws, nchunks, G, BG, static_cast<float>(P) * (C / G), eps,
-                                                       stats);
-  SDW_CUDA_OK(cudaGetLastError());
+  SDW_CUDA_OK(launch_pdl(gn_finalize_kernel, dim3((BG + 7) / 8), dim3(256), 0, stream, partial_ws, nchunks, G, BG,
+                         static_cast<float>(P) * (C / G), eps, stats));
   int ppb = static_cast<int>(std::max<int64_t>(1, 4096 / C));  // ~4K elements per block pass
   ppb *= 8;
   const unsigned tiles = static_cast<unsigned>((P + ppb - 1) / ppb);
-  gn_apply_kernel<<<dim3(tiles, B), 256, 0, stream>>>(x, ldx, C, G, P, stats, gamma, beta, silu, y, ldy, ppb);
-  SDW_CUDA_OK(cudaGetLastError());
+  SDW_CUDA_OK(launch_pdl(gn_apply_kernel, dim3(tiles, B), dim3(256), 0, stream, x, ldx, C, G, P, stats, gamma, beta, silu,
+                         y, ldy, ppb));
   return 0;
 }
 
@@ -231,6 +235,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
                                                         int C, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
                                                         __half* __restrict__ y, int64_t ldy) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
   if (row0 >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -309,13 +315,13 @@ int layernorm(const __half* x, int64_t ldx, int64_t rows, int C, const float* ga
   const int vecs = C / 8;
   if (vecs <= 64) {
     const unsigned blocks = static_cast<unsigned>((rows + 31) / 32);
-    layernorm_kernel<2, 4><<<blocks, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, y, ldy);
+    SDW_CUDA_OK(launch_pdl(layernorm_kernel<2, 4>, dim3(blocks), dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, y, ldy));
   } else if (vecs <= 160) {
     const unsigned blocks = static_cast<unsigned>((rows + 15) / 16);
-    layernorm_kernel<5, 2><<<blocks, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, y, ldy);
+    SDW_CUDA_OK(launch_pdl(layernorm_kernel<5, 2>, dim3(blocks), dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, y, ldy));
   } else {
     const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
-    layernorm_kernel<8, 1><<<blocks, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, y, ldy);
+    SDW_CUDA_OK(launch_pdl(layernorm_kernel<8, 1>, dim3(blocks), dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, y, ldy));
   }
   SDW_CUDA_OK(cudaGetLastError());
   return 0;
