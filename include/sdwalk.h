@@ -170,6 +170,7 @@ typedef struct sdw_gemm_desc {
   int32_t bn;                /* BLOCK_N: 0 auto, 64/128/160/256 */
   int32_t ver;               /* 0 auto, 1: one CTA per 128xBN tile, 2: persistent CTA pairs (256xBN) */
   int32_t nsub;              /* 0 auto, 1 / 2: accumulators per activation tile in the CTA-pair kernel */
+  int32_t cl;                /* 0 auto, 2 / 4: cluster size (4: activation tile multicast to two CTA pairs) */
 } sdw_gemm_desc;
 
 int sdw_gemm(const sdw_gemm_desc* desc, void* stream);

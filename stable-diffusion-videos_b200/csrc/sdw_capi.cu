@@ -9,7 +9,7 @@ namespace sdw {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 bool pdl_enabled() {
-  static const bool on = [] { const char* e = std::getenv("SDW_PDL"); return !(e && e[0] == '0'); }();
+  static const bool on = [] { const char* e = std::getenv("SDW_PDL"); return e && e[0] == '1'; }();  // measured no gain: opt-in
   return on;
 }
 const char* last_error() { return g_err.c_str(); }
@@ -63,6 +63,7 @@ int sdw_gemm(const sdw_gemm_desc* c, void* stream) {
   d.bn = c->bn;
   d.ver = c->ver;
   d.nsub = c->nsub;
+  d.cl = c->cl;
   GemmLaunch L;
   if (int e = plan_gemm(d, &L)) return e;
   return launch_gemm(L, static_cast<cudaStream_t>(stream));

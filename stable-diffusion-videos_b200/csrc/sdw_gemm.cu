@@ -356,11 +356,23 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
     const int64_t max_off = static_cast<int64_t>(d.B) * OH * OW * std::max<int64_t>(d.ldc, d.ldr ? d.ldr : d.ldc);
     SDW_REQUIRE(max_off < (int64_t(1) << 31) || ver == 1, "output too large for the 2-CTA epilogue (>= 2^31 elements)");
   }
+  L->cl = 2;
   if (ver == 2) {
     p.m_pairs = (m_tiles + 1) / 2;
     p.n_tiles = (d.N + bn * nsub - 1) / (bn * nsub);
-    const int clusters = std::min(p.m_pairs * p.n_tiles, 74);
-    L->grid = dim3(2 * clusters, 1, 1);
+    // 4-CTA clusters (activation-tile multicast across two N tiles) when there are >= 2 N tiles of a supported width
+    static const int cl_env = [] { const char* e = std::getenv("SDW_GEMM_CL"); return e ? std::atoi(e) : 0; }();
+    int cl = d.cl ? d.cl : (cl_env ? cl_env : 2);
+    if (cl == 4 && !(nsub == 1 && (bn == 160 || bn == 256) && p.n_tiles >= 2 && !d.b_batched)) cl = 2;
+    L->cl = cl;
+    if (cl == 4) {
+      int maxc = g_plan_only ? 32 : (gemm2_init() == 0 ? gemm2_max_clusters4() : 32);
+      const int groups = p.m_pairs * ((p.n_tiles + 1) / 2);
+      L->grid = dim3(4 * std::min(groups, maxc), 1, 1);
+    } else {
+      const int clusters = std::min(p.m_pairs * p.n_tiles, 74);
+      L->grid = dim3(2 * clusters, 1, 1);
+    }
   }
   // tensor maps: A
   for (int m = 0; m < nmaps; ++m) {

@@ -40,8 +40,11 @@ struct Gemm2Cfg {
   static constexpr int SMEM_BYTES = STAGES * (G2_A_STAGE + B_STAGE) + EPI_STAGE + 1024 + 256;
 };
 
-template <int BN, int NSUB>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+// CL = cluster size.  CL = 4: two CTA pairs of one cluster compute the two neighbouring N tiles of the same M pair; the
+// activation tile is loaded ONCE per cluster (TMA multicast from pair 0 into both pairs' shared memory), which removes
+// a third of the L2->SM operand traffic that bounds this kernel (profiles/r01_mma_eff_vs_blockN.txt).
+template <int BN, int NSUB, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
     gemm2_tc_kernel(const __grid_constant__ GemmKParams p) {
   using Cfg = Gemm2Cfg<BN, NSUB>;
   constexpr int NBUF = Cfg::NBUF;
@@ -58,11 +61,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();  // rank in the cluster
+  const uint32_t rank = crank & 1;           // rank in the CTA pair
+  const uint32_t pair_id = crank >> 1;       // 0 for CL = 2
+  const uint32_t lead_rank = crank & ~1u;    // cluster rank of this pair's leader
   const bool leader = rank == 0;
-  const int cluster_id = blockIdx.x >> 1;
-  const int nclusters = gridDim.x >> 1;
-  const int total_tiles = p.m_pairs * p.n_tiles;
+  const int cluster_id = blockIdx.x / CL;
+  const int nclusters = gridDim.x / CL;
+  constexpr int NPAIR = CL / 2;
+  const int n_groups = (p.n_tiles + NPAIR - 1) / NPAIR;  // N tiles are handed out NPAIR at a time
+  const int total_tiles = p.m_pairs * n_groups;
   const int num_kb = p.ntaps * p.kchunks;
 
   if (warp == 0 && lane == 0) {
@@ -70,7 +78,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
     tma_prefetch_desc(&p.mapB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      // pair 0 also fills pair 1's activation stage, so its slot is free only when BOTH pairs' MMAs have drained it
+      mbar_init(&empty_bar[s], (CL == 4 && pair_id == 0) ? 2 : 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -91,8 +100,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
   auto tile_coords = [&](int t, int& x0, int& y0, int& b0, int& n0) {
     // N fastest: the n_tiles column tiles of one M pair run on neighbouring clusters at the same time, so the
     // activation tile is fetched from DRAM once and re-read from L2 (the whole weight matrix is L2-resident anyway)
-    const int m_pair = t / p.n_tiles;
-    const int n_tile = t - m_pair * p.n_tiles;
+    const int m_pair = t / n_groups;
+    const int n_tile = (t - m_pair * n_groups) * NPAIR + static_cast<int>(pair_id);
     const int m_tile = m_pair * 2 + static_cast<int>(rank);
     const int tw = m_tile % p.tiles_w;
     const int th = (m_tile / p.tiles_w) % p.tiles_h;
@@ -116,9 +125,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
           const int tap = kb / p.kchunks;
           const int kc = kb - tap * p.kchunks;
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * (G2_A_STAGE + Cfg::B_STAGE));
-          const uint32_t bar = mapa_rank(smem_u32(&full_bar[stage]), 0);
-          tma_load_4d_2sm(&p.mapA[p.tap_map[tap]], bar, smem_a + stage * G2_A_STAGE, kc * 64, x0 + p.tap_dx[tap],
-                          y0 + p.tap_dy[tap], b0);
+          const uint32_t bar = mapa_rank(smem_u32(&full_bar[stage]), lead_rank);
+          if (CL == 2) {
+            tma_load_4d_2sm(&p.mapA[p.tap_map[tap]], bar, smem_a + stage * G2_A_STAGE, kc * 64, x0 + p.tap_dx[tap],
+                            y0 + p.tap_dy[tap], b0);
+          } else if (pair_id == 0) {
+            // one L2 read feeds CTA `rank` of both pairs; each pair's leader barrier gets the bytes
+            tma_load_4d_2sm_mc(&p.mapA[p.tap_map[tap]], bar, smem_a + stage * G2_A_STAGE, kc * 64, x0 + p.tap_dx[tap],
+                               y0 + p.tap_dy[tap], b0, static_cast<uint16_t>(0x5u << rank));
+          }
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub)
             tma_load_4d_2sm(&p.mapB, bar, smem_b + stage * Cfg::B_STAGE + sub * Cfg::B_SUB, kb * 64,
@@ -155,13 +170,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
               umma_f16_ss_2cta(tmem_acc + sub * BN, da + 2 * k, db + sub * (Cfg::B_SUB >> 4) + 2 * k, idesc,
                                (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit_2cta(&empty_bar[stage], 0b11);
+          // frees this pair's stage; pair 1 additionally releases pair 0's (whose producer also fills pair 1's A)
+          umma_commit_2cta(&empty_bar[stage], CL == 2 ? 0b11 : (pair_id == 0 ? 0b0011 : 0b1111));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2cta(&tmem_full[a], 0b11);
+        umma_commit_2cta(&tmem_full[a], static_cast<uint16_t>(0b11u << (2 * pair_id)));
       }
     }
   } else if (warp >= 4) {
@@ -178,7 +194,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
                           &tmem_full[a], (it / NBUF) & 1, (warp - 4) >> 2, 2, epi_stage + (warp - 4) * 2048);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[a]), 0));
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[a]), lead_rank));
     }
   }
 
@@ -190,48 +206,84 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
   }
 }
 
-template <int BN, int NSUB>
+template <int BN, int NSUB, int CL>
 static int set_attr2() {
-  SDW_CUDA_OK(cudaFuncSetAttribute(gemm2_tc_kernel<BN, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SDW_CUDA_OK(cudaFuncSetAttribute(gemm2_tc_kernel<BN, NSUB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Gemm2Cfg<BN, NSUB>::SMEM_BYTES));
   return 0;
 }
 
+static int g_max_clusters4 = 0;
+int gemm2_max_clusters4() { return g_max_clusters4; }
+
 static bool g_init2 = false;
 int gemm2_init() {
   if (g_init2) return 0;
-  if (int e = set_attr2<128, 1>()) return e;
-  if (int e = set_attr2<160, 1>()) return e;
-  if (int e = set_attr2<192, 1>()) return e;
-  if (int e = set_attr2<256, 1>()) return e;
-  if (int e = set_attr2<160, 2>()) return e;
+  if (int e = set_attr2<128, 1, 2>()) return e;
+  if (int e = set_attr2<160, 1, 2>()) return e;
+  if (int e = set_attr2<192, 1, 2>()) return e;
+  if (int e = set_attr2<256, 1, 2>()) return e;
+  if (int e = set_attr2<160, 2, 2>()) return e;
+  if (int e = set_attr2<160, 1, 4>()) return e;
+  if (int e = set_attr2<256, 1, 4>()) return e;
+  {
+    // how many 4-CTA clusters of this kernel the device can hold at once (GPC boundaries strand some SMs)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(148);
+    cfg.blockDim = dim3(G2_THREADS);
+    cfg.dynamicSmemBytes = Gemm2Cfg<256, 1>::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm2_tc_kernel<256, 1, 4>, &cfg) != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      n = 32;
+    }
+    g_max_clusters4 = n;
+  }
   g_init2 = true;
   return 0;
 }
 
 int launch_gemm2(const GemmLaunch& l, cudaStream_t stream) {
   if (int e = gemm2_init()) return e;
+  if (l.cl == 4) {
+    if (l.nsub != 1 || (l.bn != 160 && l.bn != 256)) {
+      set_error("the 4-CTA cluster variant exists for BLOCK_N = 160 / 256, one accumulator");
+      return 1;
+    }
+    if (l.bn == 160)
+      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<160, 1, 4>, l.grid, dim3(G2_THREADS), Gemm2Cfg<160, 1>::SMEM_BYTES, stream, l.p));
+    else
+      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<256, 1, 4>, l.grid, dim3(G2_THREADS), Gemm2Cfg<256, 1>::SMEM_BYTES, stream, l.p));
+    return 0;
+  }
   if (l.nsub == 2) {
     if (l.bn != 160) {
       set_error("the two-accumulator variant exists for BLOCK_N = 160 only");
       return 1;
     }
-    SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<160, 2>, l.grid, dim3(G2_THREADS), Gemm2Cfg<160, 2>::SMEM_BYTES, stream, l.p));
+    SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<160, 2, 2>, l.grid, dim3(G2_THREADS), Gemm2Cfg<160, 2>::SMEM_BYTES, stream, l.p));
     SDW_CUDA_OK(cudaGetLastError());
     return 0;
   }
   switch (l.bn) {
     case 128:
-      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<128, 1>, l.grid, dim3(G2_THREADS), Gemm2Cfg<128, 1>::SMEM_BYTES, stream, l.p));
+      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<128, 1, 2>, l.grid, dim3(G2_THREADS), Gemm2Cfg<128, 1>::SMEM_BYTES, stream, l.p));
       break;
     case 160:
-      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<160, 1>, l.grid, dim3(G2_THREADS), Gemm2Cfg<160, 1>::SMEM_BYTES, stream, l.p));
+      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<160, 1, 2>, l.grid, dim3(G2_THREADS), Gemm2Cfg<160, 1>::SMEM_BYTES, stream, l.p));
       break;
     case 192:
-      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<192, 1>, l.grid, dim3(G2_THREADS), Gemm2Cfg<192, 1>::SMEM_BYTES, stream, l.p));
+      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<192, 1, 2>, l.grid, dim3(G2_THREADS), Gemm2Cfg<192, 1>::SMEM_BYTES, stream, l.p));
       break;
     case 256:
-      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<256, 1>, l.grid, dim3(G2_THREADS), Gemm2Cfg<256, 1>::SMEM_BYTES, stream, l.p));
+      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<256, 1, 2>, l.grid, dim3(G2_THREADS), Gemm2Cfg<256, 1>::SMEM_BYTES, stream, l.p));
       break;
     default:
       set_error("bad BLOCK_N for the 2-CTA kernel");

@@ -100,6 +100,7 @@ struct GemmLaunch {
   int bn;   // BLOCK_N variant
   int ver;  // 1: one 128xBN tile per CTA (sdw_gemm.cu); 2: persistent CTA pairs, 256xBN tiles (sdw_gemm2.cu)
   int nsub = 1;  // ver 2: accumulators per activation tile (2 -> 256 x 2*BN tiles, single-buffered TMEM)
+  int cl = 2;    // ver 2: cluster size (4 -> two CTA pairs share each activation tile via TMA multicast)
 };
 
 // Describes one implicit GEMM in host terms; plan_gemm() turns it into a launch.
@@ -134,11 +135,14 @@ struct GemmDesc {
   int bn = 0;   // 0 = auto
   int ver = 0;  // 0 = auto, 1 / 2 force a kernel version
   int nsub = 0; // 0 = auto, 1 / 2: accumulators per activation tile in the 2-CTA kernel
+  int cl = 0;   // 0 = auto, 2 / 4: cluster size of the 2-CTA kernel
 };
 
 int plan_gemm(const GemmDesc& d, GemmLaunch* out);
 int launch_gemm(const GemmLaunch& l, cudaStream_t stream);
 int launch_gemm2(const GemmLaunch& l, cudaStream_t stream);
+int gemm2_init();
+int gemm2_max_clusters4();
 void set_plan_only(bool on);
 int gemm_init();  // resolves the driver entry point, sets smem attributes
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,

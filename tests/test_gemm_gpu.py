@@ -21,7 +21,7 @@ def _tol(ref):
     return float(ref.abs().max()) * 2.0 ** -9 + 1e-3
 
 
-def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None, ver=0, nsub=0):
+def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None, ver=0, nsub=0, cl=0):
     """x: [B,H,W,C] fp16 cuda; returns NHWC fp16 output computed by the native kernel."""
     n = _native()
     B, H, W, Cc = x_nhwc.shape
@@ -60,6 +60,7 @@ def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn
         d.bn = bn
         d.ver = ver
         d.nsub = nsub
+        d.cl = cl
         n.gemm(d)
     torch.cuda.synchronize()
     return out
@@ -299,6 +300,26 @@ def test_gemm_2cta_two_accumulators(B, H, W, Cc, N, conv):
     oh, ow = (H // 2, W // 2) if conv == 2 else ((2 * H, 2 * W) if conv == 3 else (H, W))
     resid = _rand(B, oh, ow, N, seed=54)
     out = run_conv(x, w, conv, bias=bias, resid=resid, ver=2, bn=160, nsub=2)
+    ref = ref_conv(x, w if conv else w.reshape(N, Cc), conv, bias=bias, resid=resid)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= _tol(ref), (err, _tol(ref))
+
+
+# ---- 4-CTA clusters: the activation tile is TMA-multicast to two CTA pairs working on neighbouring N tiles -------------
+@pytest.mark.parametrize("B,H,W,Cc,N,conv,bn", [(4, 64, 64, 320, 320, 1, 160), (2, 32, 32, 640, 640, 1, 160),
+                                                 (2, 16, 16, 128, 1280, 1, 256), (1, 8, 8, 64, 480, 1, 160),
+                                                 (2, 64, 64, 64, 320, 2, 160), (2, 16, 16, 64, 640, 3, 160),
+                                                 (1, 1, 5000, 1280, 960, 0, 160), (8, 64, 64, 320, 2560, 0, 256),
+                                                 (1, 1, 300, 64, 768, 0, 256)])
+def test_gemm_4cta_cluster_multicast(B, H, W, Cc, N, conv, bn):
+    x = _rand(B, H, W, Cc, seed=61)
+    k = 3 if conv else 1
+    w = _rand(N, Cc, k, k, scale=(k * k * Cc) ** -0.5, seed=62)
+    bias = _rand(N, seed=63).float()
+    oh, ow = (H // 2, W // 2) if conv == 2 else ((2 * H, 2 * W) if conv == 3 else (H, W))
+    resid = _rand(B, oh, ow, N, seed=64)
+    out = run_conv(x, w, conv, bias=bias, resid=resid, ver=2, bn=bn, nsub=1, cl=4)
     ref = ref_conv(x, w if conv else w.reshape(N, Cc), conv, bias=bias, resid=resid)
     assert torch.isfinite(out.float()).all()
     err = (out.float() - ref).abs().max().item()
