@@ -368,6 +368,12 @@ class StableDiffusionWalkPipeline:
         if self._dist is not None:
             lo, hi = frame_block(Tk.shape[0], self._dist[1], self._dist[0])
         frame_index = skip + lo
+        # frame sink: PNG encoding runs on worker threads while the GPU renders the next batch
+        # (the reference saves serially, P:550-554); all writes are joined before the clip returns
+        from concurrent.futures import ThreadPoolExecutor
+
+        pending = []
+        pool = ThreadPoolExecutor(max_workers=8)
         gen = self.generate_inputs(prompt_a, prompt_b, seed_a, seed_b,
                                    (1, self.unet.in_channels, height // 8, width // 8), Tk[lo:hi], batch_size)
         for batch_idx, embeds_batch, noise_batch in gen:
@@ -380,8 +386,11 @@ class StableDiffusionWalkPipeline:
                            guidance_scale=guidance_scale, eta=eta, num_inference_steps=num_inference_steps,
                            output_type="pil", negative_prompt=negative_prompt)["images"][:nb]
             for image in outputs:
-                image.save(save_path / (f"frame%06d{image_file_ext}" % frame_index))
+                pending.append(pool.submit(image.save, save_path / (f"frame%06d{image_file_ext}" % frame_index)))
                 frame_index += 1
+        for fut in pending:
+            fut.result()  # re-raise any I/O error
+        pool.shutdown()
 
     # ------------------------------------------------------------------------------------------
     # walk (reference P:556-807)
