@@ -136,6 +136,8 @@ int sdw_engine_launches(const sdw_engine* e, int* prologue, int* unet_per_step, 
 int sdw_engine_debug_unet(sdw_engine* e, const float* x_nchw, int step, const void* ctx_f16, float* eps_nhwc_out,
                           void* stream);
 int sdw_engine_debug_vae(sdw_engine* e, const float* latents_nchw, uint8_t* out_u8, float* out_f32_nhwc, void* stream);
+/* tooling: CUDA-event time of every op of one UNet forward and of the VAE decode, written as TSV to `path` */
+int sdw_engine_debug_profile(sdw_engine* e, const char* path, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Low-level tensor-core op (tests / tooling): one implicit GEMM on the tcgen05 kernel.
@@ -171,6 +173,7 @@ typedef struct sdw_gemm_desc {
   int32_t ver;               /* 0 auto, 1: one CTA per 128xBN tile, 2: persistent CTA pairs (256xBN) */
   int32_t nsub;              /* 0 auto, 1 / 2: accumulators per activation tile in the CTA-pair kernel */
   int32_t cl;                /* 0 auto, 2 / 4: cluster size (4: activation tile multicast to two CTA pairs) */
+  int32_t tr;                /* 0 auto, 1 never, 2 require: 3x3 taps reuse one activation box in shared memory */
 } sdw_gemm_desc;
 
 int sdw_gemm(const sdw_gemm_desc* desc, void* stream);

@@ -143,8 +143,16 @@ struct Engine {
   // ---- op emission ---------------------------------------------------------
   std::vector<OpFn>* cur = nullptr;
   int* cur_count = nullptr;
+  // tags parallel to the op lists (tooling: sdw_engine_debug_profile); `tag_next` names the op about to be emitted
+  std::vector<std::string> prologue_tags, unet_tags, vae_tags;
+  std::string tag_next;
   void emit(OpFn f, int launches = 1) {
-    if (!dry) cur->push_back(std::move(f));
+    if (!dry) {
+      cur->push_back(std::move(f));
+      std::vector<std::string>& tags = cur == &prologue ? prologue_tags : (cur == &unet_ops ? unet_tags : vae_tags);
+      tags.push_back(tag_next.empty() ? std::string("op") : tag_next);
+    }
+    tag_next.clear();
     *cur_count += launches;
   }
   int emit_gemm(const GemmDesc& d, const float* rowvec_table = nullptr, int rowvec_stride = 0) {
@@ -154,6 +162,12 @@ struct Engine {
     }
     auto L = std::make_shared<GemmLaunch>();
     if (int e = plan_gemm(d, L.get())) return e;
+    {
+      char buf[160];
+      std::snprintf(buf, sizeof buf, "gemm conv%d C%d %dx%dx%d N%d mode%d bn%d nsub%d tr%d%s", d.conv, d.C, d.B, d.H, d.W, d.N,
+                    d.mode, L->bn, L->nsub, L->tr, d.b_batched ? " batched" : "");
+      tag_next = buf;
+    }
     emit([L, rowvec_table, rowvec_stride](cudaStream_t st, int step) {
       if (rowvec_table) {
         GemmLaunch l = *L;
@@ -201,6 +215,7 @@ struct Engine {
     const float* b = vec(name + ".bias", x.C);
     const int G = cfg_groups;
     float2* ws = gn_ws;
+    tag_next = "groupnorm C" + std::to_string(x.C) + " " + std::to_string(x.B) + "x" + std::to_string(x.H) + "x" + std::to_string(x.W);
     emit([=](cudaStream_t st, int) {
       return groupnorm(x.p, x.ld, x.B, static_cast<int64_t>(x.H) * x.W, x.C, G, g, b, eps, silu, out.p, out.ld, ws, st);
     }, 3);
@@ -208,6 +223,7 @@ struct Engine {
   void ln(const T& x, const std::string& name, const T& out) {
     const float* g = vec(name + ".weight", x.C);
     const float* b = vec(name + ".bias", x.C);
+    tag_next = "layernorm C" + std::to_string(x.C) + " rows" + std::to_string(x.pixels());
     emit([=](cudaStream_t st, int) { return layernorm(x.p, x.ld, x.pixels(), x.C, g, b, 1e-5f, out.p, out.ld, st); });
   }
   int cfg_groups = 32;
@@ -227,6 +243,8 @@ struct Engine {
       a.out = out.p; a.out_ld = out.ld;
       auto L = std::make_shared<AttnLaunch>();
       if (int e = plan_attention(a, L.get())) return e;
+      tag_next = "attention d" + std::to_string(d) + " B" + std::to_string(Bq) + " h" + std::to_string(heads) + " Nq" +
+                 std::to_string(Nq) + " Nk" + std::to_string(Nk);
       emit([L](cudaStream_t st, int) { return launch_attention(*L, st); });
       return 0;
     }
@@ -887,6 +905,42 @@ int sdw_engine_launches(const sdw_engine* e, int* prologue, int* unet, int* vae)
 }
 
 // ---- debug / parity entry points -------------------------------------------------------------------
+// tooling: time every op of one UNet forward (step 0) and of the VAE decode with CUDA events, after one untimed pass;
+// writes "section<TAB>index<TAB>microseconds<TAB>tag" lines.  The engine must be bound and have sampled once.
+int sdw_engine_debug_profile(sdw_engine* e, const char* path, void* stream) {
+  Engine* E = reinterpret_cast<Engine*>(e);
+  SDW_REQUIRE(E && path && !E->dry && E->n_steps > 0, "engine not bound / no schedule");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FILE* f = std::fopen(path, "w");
+  SDW_REQUIRE(f, "cannot open the profile file");
+  struct Sec { const char* name; std::vector<OpFn>* ops; std::vector<std::string>* tags; };
+  Sec secs[2] = {{"unet", &E->unet_ops, &E->unet_tags}, {"vae", &E->vae_ops, &E->vae_tags}};
+  int rc = 0;
+  for (const Sec& sc : secs) {
+    if ((rc = run_ops(*sc.ops, st, 0))) break;
+    const size_t n = sc.ops->size();
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& x : ev) cudaEventCreate(&x);
+    cudaEventRecord(ev[0], st);
+    for (size_t i = 0; i < n && !rc; ++i) {
+      rc = (*sc.ops)[i](st, 0);
+      cudaEventRecord(ev[i + 1], st);
+    }
+    cudaStreamSynchronize(st);
+    for (size_t i = 0; i < n && !rc; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      std::fprintf(f, "%s\t%zu\t%.2f\t%s\n", sc.name, i, ms * 1e3f, (*sc.tags)[i].c_str());
+    }
+    for (auto& x : ev) cudaEventDestroy(x);
+    if (rc) break;
+  }
+  std::fclose(f);
+  if (rc) return rc;
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int sdw_engine_debug_unet(sdw_engine* e, const float* x_nchw, int step, const void* ctx_f16, float* eps_nhwc_out,
                           void* stream) {
   Engine* E = reinterpret_cast<Engine*>(e);

@@ -302,6 +302,24 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
     ver = (!force_v1 && m_tiles >= 2 && d.N >= 128 && (!d.b_batched || p.tiles_w % 2 == 0)) ? 2 : 1;
   }
   if (ver == 2) SDW_REQUIRE(!d.b_batched || p.tiles_w % 2 == 0, "2-CTA batched matmul needs an even tile count per row");
+  // tap reuse (3x3 stride 1, CTA pairs): 16 x 8-pixel tiles, one 10-row activation box per (channel chunk, kx)
+  bool reuse = false;
+  {
+    static const int tr_env = [] { const char* e = std::getenv("SDW_GEMM_TR"); return e ? std::atoi(e) : -1; }();
+    const bool can = ver == 2 && d.conv == 1 && Wd % 16 == 0 && Hd % 8 == 0 && d.cl != 4;
+    if (d.tr == 2) SDW_REQUIRE(can, "tap reuse needs a 3x3 stride-1 conv on the CTA-pair kernel with W % 16 == 0, H % 8 == 0");
+    reuse = can && d.tr != 1 && (d.tr == 2 || tr_env != 0);
+    if (reuse) {
+      p.bw = bw = 16;
+      p.bh = bh = 8;
+      p.bb = bb = 1;
+      p.tiles_w = Wd / 16;
+      p.tiles_h = Hd / 8;
+    }
+  }
+  p.tap_reuse = reuse ? 1 : 0;
+  L->tr = p.tap_reuse;
+  const int m_tiles_f = p.tiles_w * p.tiles_h * ((d.B + bb - 1) / bb);
   // BLOCK_N choice
   int bn = d.bn;
   int nsub = 1;
@@ -311,19 +329,25 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
     // BLOCK_N in {256, 192, 160, 128} and, for long-K problems, the two-accumulator 2 x 160 tile (single-buffered TMEM).
     struct Cand { int bn, nsub; };
     const Cand cand[5] = {{160, 2}, {256, 1}, {192, 1}, {160, 1}, {128, 1}};
-    const int mp = (m_tiles + 1) / 2;
+    const int mp = (m_tiles_f + 1) / 2;
     const int kblocks = p.ntaps * kchunks;
+    // activation bytes per CTA per K block: a 128 x 64 tile, or a third of the 10-row box; the MMA floor is 2 clk per
+    // column at ~41 B/clk/SM of operand ingest -> 82 "bytes" per column
+    const double a_bytes = reuse ? 20480.0 / 3.0 : 16384.0;
     double best_cost = 1e30;
     int best_bn = 128;
     for (const Cand& c : cand) {
       if (d.bn && d.bn != c.bn) continue;
       if (d.nsub && d.nsub != c.nsub) continue;
       if (d.mode == GEMM_GEGLU && c.bn % 64 != 0) continue;
-      if (c.nsub == 2 && (kblocks < 18 || d.mode != GEMM_PLAIN) && d.nsub != 2) continue;
+      if (c.nsub == 2 && (kblocks < 18 || d.mode != GEMM_PLAIN || reuse) && d.nsub != 2) continue;  // reuse: only 2 stages fit
       const int width = c.bn * c.nsub;
       const int tiles = mp * ((d.N + width - 1) / width);
       const int waves = (tiles + 73) / 74;
-      double cost = static_cast<double>(waves) * (16384.0 + 64.0 * width);
+      double cost = static_cast<double>(waves) * std::max(a_bytes + 64.0 * width, 82.0 * width);
+      // measured (profiles/r01_gemm_shapes_tap_reuse.txt): with 3-tap stages only 3 stages of BLOCK_N = 256 fit and the
+      // variant gains nothing over per-tap loads
+      if (reuse && c.bn == 256) cost = static_cast<double>(waves) * 31000.0;
       if (c.nsub == 2) cost *= 1.0 + 24.0 / kblocks;  // un-overlapped epilogue ~ 24 K-block times (fit: profiles/r01_gemm_shapes_nsub2.txt)
       if (cost < best_cost) {
         best_cost = cost;
@@ -346,7 +370,7 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
   if (d.mode == GEMM_GEGLU) SDW_REQUIRE(bn % 64 == 0 && d.N % 64 == 0, "GEGLU needs 64-column pairs");
   if (d.mode == GEMM_QKV_VT) SDW_REQUIRE(d.vt && d.vt_col0 % 32 == 0 && d.vt_d > 0, "bad V^T split");
   L->bn = bn;
-  L->grid = dim3(m_tiles, (d.N + bn - 1) / bn, 1);
+  L->grid = dim3(m_tiles_f, (d.N + bn - 1) / bn, 1);
   {
     // store staging pays off when the epilogue, not the mainloop, bounds the tile (short K, wide N)
     static const int stage_env = [] { const char* e = std::getenv("SDW_STAGE"); return e ? std::atoi(e) : -1; }();
@@ -358,12 +382,12 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
   }
   L->cl = 2;
   if (ver == 2) {
-    p.m_pairs = (m_tiles + 1) / 2;
+    p.m_pairs = (m_tiles_f + 1) / 2;
     p.n_tiles = (d.N + bn * nsub - 1) / (bn * nsub);
     // 4-CTA clusters (activation-tile multicast across two N tiles) when there are >= 2 N tiles of a supported width
     static const int cl_env = [] { const char* e = std::getenv("SDW_GEMM_CL"); return e ? std::atoi(e) : 0; }();
     int cl = d.cl ? d.cl : (cl_env ? cl_env : 2);
-    if (cl == 4 && !(nsub == 1 && (bn == 160 || bn == 256) && p.n_tiles >= 2 && !d.b_batched)) cl = 2;
+    if (cl == 4 && !(nsub == 1 && (bn == 160 || bn == 256) && p.n_tiles >= 2 && !d.b_batched && !reuse)) cl = 2;
     L->cl = cl;
     if (cl == 4) {
       int maxc = g_plan_only ? 32 : (gemm2_init() == 0 ? gemm2_max_clusters4() : 32);
@@ -391,7 +415,7 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
     // degenerate extents still need a non-zero, 16B-multiple stride
     for (int i = 1; i < 4; ++i)
       if (strides[i] == 0) strides[i] = static_cast<uint64_t>(Cp);
-    uint32_t box[4] = {BK, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bb)};
+    uint32_t box[4] = {BK, static_cast<uint32_t>(bw), static_cast<uint32_t>(reuse ? bh + 2 : bh), static_cast<uint32_t>(bb)};
     if (int e = encode_map(&p.mapA[m], base, 4, dims, strides, box)) return e;
   }
   {

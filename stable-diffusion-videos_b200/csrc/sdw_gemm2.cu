@@ -25,34 +25,46 @@ static constexpr int G2_A_STAGE = 128 * 64 * 2;
 // NSUB = accumulators per activation tile: NSUB = 2 computes a 256 x (2*BN) tile per CTA pair — the A tile is pulled
 // from L2 once for twice the columns (the kernel is L2->SM bandwidth bound: profiles/r01_mma_eff_vs_blockN.txt) at the
 // price of single-buffered TMEM (2 * 2 * 160 > 512 columns), so it is used for long-K problems (3x3 convs) only.
-template <int BN, int NSUB>
+//
+// TR = 1 (tap reuse, 3x3 stride-1 convs on 16 x 8-pixel tiles): the kernel is bound by the operand bytes an SM ingests
+// per K block (~41 B/clk/SM: profiles/r01_gemm_shapes_cluster4_multicast.txt), and the three ky taps of one kx read
+// the same pixels shifted by whole image rows.  One TMA box of (8 + 2) rows x 16 px x 64 ch per (channel chunk, kx)
+// therefore serves three taps: tap ky's A operand is the same shared-memory tile entered 16 rows (2 KB, swizzle-atom
+// aligned) further down, so a pipeline stage is 20 KB of A + 3 weight tiles instead of 3 x 16 KB of A + 3 weight tiles.
+static constexpr int G2_TR_BW = 16, G2_TR_BH = 8;
+static constexpr int G2_A_STAGE_TR = (G2_TR_BH + 2) * G2_TR_BW * 128;
+template <int BN, int NSUB, int TR = 0>
 struct Gemm2Cfg {
   static constexpr int BH = BN / 2;
   static constexpr int B_SUB = BH * 128;           // one CTA's half of one BN-wide weight tile
-  static constexpr int B_STAGE = NSUB * B_SUB;
+  static constexpr int A_STAGE = TR ? G2_A_STAGE_TR : G2_A_STAGE;
+  static constexpr int TAPS = TR ? 3 : 1;          // taps per pipeline stage
+  static constexpr int B_STAGE = TAPS * NSUB * B_SUB;
   static constexpr int NBUF = (2 * NSUB * BN <= 512) ? 2 : 1;  // accumulator buffers in TMEM
   static constexpr int ACC_COLS = NSUB * BN;
   static constexpr int TMEM_COLS = NBUF * ACC_COLS <= 256 ? 256 : 512;
   static constexpr int EPI_STAGE = 8 * 2048;  // 2 KB store-coalescing buffer per epilogue warp
-  static constexpr int STAGES = (227 * 1024 - EPI_STAGE - 2048) / (G2_A_STAGE + B_STAGE) > 8
+  static constexpr int STAGES = (227 * 1024 - EPI_STAGE - 2048) / (A_STAGE + B_STAGE) > 8
                                     ? 8
-                                    : (227 * 1024 - EPI_STAGE - 2048) / (G2_A_STAGE + B_STAGE);
-  static constexpr int SMEM_BYTES = STAGES * (G2_A_STAGE + B_STAGE) + EPI_STAGE + 1024 + 256;
+                                    : (227 * 1024 - EPI_STAGE - 2048) / (A_STAGE + B_STAGE);
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + EPI_STAGE + 1024 + 256;
 };
 
 // CL = cluster size.  CL = 4: two CTA pairs of one cluster compute the two neighbouring N tiles of the same M pair; the
 // activation tile is loaded ONCE per cluster (TMA multicast from pair 0 into both pairs' shared memory), which removes
 // a third of the L2->SM operand traffic that bounds this kernel (profiles/r01_mma_eff_vs_blockN.txt).
-template <int BN, int NSUB, int CL>
+template <int BN, int NSUB, int CL, int TR = 0>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
     gemm2_tc_kernel(const __grid_constant__ GemmKParams p) {
-  using Cfg = Gemm2Cfg<BN, NSUB>;
+  static_assert(!(TR && CL != 2), "tap reuse is a CTA-pair variant");
+  using Cfg = Gemm2Cfg<BN, NSUB, TR>;
+  constexpr int A_STAGE = Cfg::A_STAGE;
   constexpr int NBUF = Cfg::NBUF;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * G2_A_STAGE;
+  uint8_t* smem_b = smem + STAGES * A_STAGE;
   uint8_t* epi_stage = smem_b + STAGES * Cfg::B_STAGE;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + Cfg::EPI_STAGE);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -71,7 +83,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
   constexpr int NPAIR = CL / 2;
   const int n_groups = (p.n_tiles + NPAIR - 1) / NPAIR;  // N tiles are handed out NPAIR at a time
   const int total_tiles = p.m_pairs * n_groups;
-  const int num_kb = p.ntaps * p.kchunks;
+  const int num_kb = TR ? 3 * p.kchunks : p.ntaps * p.kchunks;  // pipeline stages per tile
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.mapA[0]);
@@ -122,16 +134,33 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
         tile_coords(t, x0, y0, b0, n0);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE + Cfg::B_STAGE));
+          const uint32_t bar = mapa_rank(smem_u32(&full_bar[stage]), lead_rank);
+          if (TR) {
+            // stage = (channel chunk kc, column tap kx): one (bh+2)-row box + the weight tiles of taps (ky, kx), ky = 0..2
+            const int kc = kb / 3, kx = kb - kc * 3;
+            tma_load_4d_2sm(&p.mapA[0], bar, smem_a + stage * A_STAGE, kc * 64, x0 + kx - 1, y0 - 1, b0);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int sub = 0; sub < NSUB; ++sub)
+                tma_load_4d_2sm(&p.mapB, bar, smem_b + stage * Cfg::B_STAGE + (ky * NSUB + sub) * Cfg::B_SUB,
+                                ((ky * 3 + kx) * p.kchunks + kc) * 64, n0 + sub * BN + static_cast<int>(rank) * Cfg::BH, 0,
+                                0);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           const int tap = kb / p.kchunks;
           const int kc = kb - tap * p.kchunks;
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (G2_A_STAGE + Cfg::B_STAGE));
-          const uint32_t bar = mapa_rank(smem_u32(&full_bar[stage]), lead_rank);
           if (CL == 2) {
-            tma_load_4d_2sm(&p.mapA[p.tap_map[tap]], bar, smem_a + stage * G2_A_STAGE, kc * 64, x0 + p.tap_dx[tap],
+            tma_load_4d_2sm(&p.mapA[p.tap_map[tap]], bar, smem_a + stage * A_STAGE, kc * 64, x0 + p.tap_dx[tap],
                             y0 + p.tap_dy[tap], b0);
           } else if (pair_id == 0) {
             // one L2 read feeds CTA `rank` of both pairs; each pair's leader barrier gets the bytes
-            tma_load_4d_2sm_mc(&p.mapA[p.tap_map[tap]], bar, smem_a + stage * G2_A_STAGE, kc * 64, x0 + p.tap_dx[tap],
+            tma_load_4d_2sm_mc(&p.mapA[p.tap_map[tap]], bar, smem_a + stage * A_STAGE, kc * 64, x0 + p.tap_dx[tap],
                                y0 + p.tap_dy[tap], b0, static_cast<uint16_t>(0x5u << rank));
           }
 #pragma unroll
@@ -161,14 +190,27 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = make_desc_k_sw128(smem_u32(smem_a + stage * G2_A_STAGE));
+          const uint64_t da = make_desc_k_sw128(smem_u32(smem_a + stage * A_STAGE));
           const uint64_t db = make_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE));
+          if (TR) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+            for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-            for (int sub = 0; sub < NSUB; ++sub)
-              umma_f16_ss_2cta(tmem_acc + sub * BN, da + 2 * k, db + sub * (Cfg::B_SUB >> 4) + 2 * k, idesc,
-                               (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int sub = 0; sub < NSUB; ++sub)
+                  umma_f16_ss_2cta(tmem_acc + sub * BN, da + ky * ((G2_TR_BW * 128) >> 4) + 2 * k,
+                                   db + (ky * NSUB + sub) * (Cfg::B_SUB >> 4) + 2 * k, idesc, (kb | ky | k) != 0 ? 1u : 0u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+              for (int sub = 0; sub < NSUB; ++sub)
+                umma_f16_ss_2cta(tmem_acc + sub * BN, da + 2 * k, db + sub * (Cfg::B_SUB >> 4) + 2 * k, idesc,
+                                 (kb | k) != 0 ? 1u : 0u);
+            }
           }
           // frees this pair's stage; pair 1 additionally releases pair 0's (whose producer also fills pair 1's A)
           umma_commit_2cta(&empty_bar[stage], CL == 2 ? 0b11 : (pair_id == 0 ? 0b0011 : 0b1111));
@@ -206,10 +248,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
   }
 }
 
-template <int BN, int NSUB, int CL>
+template <int BN, int NSUB, int CL, int TR = 0>
 static int set_attr2() {
-  SDW_CUDA_OK(cudaFuncSetAttribute(gemm2_tc_kernel<BN, NSUB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Gemm2Cfg<BN, NSUB>::SMEM_BYTES));
+  SDW_CUDA_OK(cudaFuncSetAttribute(gemm2_tc_kernel<BN, NSUB, CL, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Gemm2Cfg<BN, NSUB, TR>::SMEM_BYTES));
   return 0;
 }
 
@@ -226,6 +268,11 @@ int gemm2_init() {
   if (int e = set_attr2<160, 2, 2>()) return e;
   if (int e = set_attr2<160, 1, 4>()) return e;
   if (int e = set_attr2<256, 1, 4>()) return e;
+  if (int e = set_attr2<128, 1, 2, 1>()) return e;
+  if (int e = set_attr2<160, 1, 2, 1>()) return e;
+  if (int e = set_attr2<192, 1, 2, 1>()) return e;
+  if (int e = set_attr2<256, 1, 2, 1>()) return e;
+  if (int e = set_attr2<160, 2, 2, 1>()) return e;
   {
     // how many 4-CTA clusters of this kernel the device can hold at once (GPC boundaries strand some SMs)
     cudaLaunchConfig_t cfg{};
@@ -252,6 +299,26 @@ int gemm2_init() {
 
 int launch_gemm2(const GemmLaunch& l, cudaStream_t stream) {
   if (int e = gemm2_init()) return e;
+  if (l.tr) {
+    if (l.cl != 2) {
+      set_error("tap reuse is a CTA-pair variant");
+      return 1;
+    }
+#define SDW_TR_CASE(BN_, NSUB_)                                                                                       \
+  SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<BN_, NSUB_, 2, 1>, l.grid, dim3(G2_THREADS), Gemm2Cfg<BN_, NSUB_, 1>::SMEM_BYTES, \
+                         stream, l.p))
+    if (l.nsub == 2 && l.bn == 160) SDW_TR_CASE(160, 2);
+    else if (l.nsub == 1 && l.bn == 128) SDW_TR_CASE(128, 1);
+    else if (l.nsub == 1 && l.bn == 160) SDW_TR_CASE(160, 1);
+    else if (l.nsub == 1 && l.bn == 192) SDW_TR_CASE(192, 1);
+    else if (l.nsub == 1 && l.bn == 256) SDW_TR_CASE(256, 1);
+    else {
+      set_error("bad BLOCK_N / nsub for the tap-reuse kernel");
+      return 1;
+    }
+#undef SDW_TR_CASE
+    return 0;
+  }
   if (l.cl == 4) {
     if (l.nsub != 1 || (l.bn != 160 && l.bn != 256)) {
       set_error("the 4-CTA cluster variant exists for BLOCK_N = 160 / 256, one accumulator");

@@ -76,6 +76,7 @@ struct alignas(64) GemmKParams {
   int b_batched;            // 1: weight map coords (.., y0, b0) = lattice (h, b) (batched matmul)
   int stage_stores;         // 1: bounce output chunks through shared memory for coalesced stores (wide-N GEMMs)
   int m_pairs, n_tiles;     // 2-CTA persistent kernel: tile grid (pairs of 128-row M tiles x BN-wide N tiles)
+  int tap_reuse;            // 1: 3x3 conv with one (bh+2)-row activation box per (channel chunk, kx) shared by the 3 ky taps
   // epilogue
   const float* bias;        // [N] or null
   const float* rowvec;      // [B][rowvec_ld] per-sample vector added per column (time-embedding proj) or null
@@ -101,6 +102,7 @@ struct GemmLaunch {
   int ver;  // 1: one 128xBN tile per CTA (sdw_gemm.cu); 2: persistent CTA pairs, 256xBN tiles (sdw_gemm2.cu)
   int nsub = 1;  // ver 2: accumulators per activation tile (2 -> 256 x 2*BN tiles, single-buffered TMEM)
   int cl = 2;    // ver 2: cluster size (4 -> two CTA pairs share each activation tile via TMA multicast)
+  int tr = 0;    // ver 2: 1 -> tap-reuse mainloop (3x3 stride-1 convs; GemmKParams::tap_reuse)
 };
 
 // Describes one implicit GEMM in host terms; plan_gemm() turns it into a launch.
@@ -136,6 +138,7 @@ struct GemmDesc {
   int ver = 0;  // 0 = auto, 1 / 2 force a kernel version
   int nsub = 0; // 0 = auto, 1 / 2: accumulators per activation tile in the 2-CTA kernel
   int cl = 0;   // 0 = auto, 2 / 4: cluster size of the 2-CTA kernel
+  int tr = 0;   // 0 = auto, 1 = never, 2 = require the tap-reuse mainloop (3x3 stride-1 conv, W % 16 == 0, H % 8 == 0)
 };
 
 int plan_gemm(const GemmDesc& d, GemmLaunch* out);

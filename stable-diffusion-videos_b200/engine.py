@@ -192,6 +192,12 @@ class Engine:
             N.check(N.lib().sdw_engine_debug_unet(self._h, N.ptr(x), int(step), N.ptr(c), N.ptr(out), N.stream_ptr()))
         return out.permute(0, 3, 1, 2).contiguous()
 
+    def debug_profile(self, path):
+        """Tooling: per-op CUDA-event times of one UNet forward + the VAE decode, written as TSV (section, idx, us, tag)."""
+        with torch.cuda.device(self.device):
+            N.check(N.lib().sdw_engine_debug_profile(self._h, str(path).encode(), N.stream_ptr()))
+            torch.cuda.synchronize()
+
     def debug_vae(self, latents):
         """VAE decode of [F,4,h,w] latents (pre-division by 0.18215 happens inside) -> (uint8 NHWC, fp32 NHWC raw)."""
         F = self.frames

@@ -21,7 +21,7 @@ def _tol(ref):
     return float(ref.abs().max()) * 2.0 ** -9 + 1e-3
 
 
-def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None, ver=0, nsub=0, cl=0):
+def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None, ver=0, nsub=0, cl=0, tr=0):
     """x: [B,H,W,C] fp16 cuda; returns NHWC fp16 output computed by the native kernel."""
     n = _native()
     B, H, W, Cc = x_nhwc.shape
@@ -61,6 +61,7 @@ def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn
         d.ver = ver
         d.nsub = nsub
         d.cl = cl
+        d.tr = tr
         n.gemm(d)
     torch.cuda.synchronize()
     return out
@@ -324,3 +325,34 @@ def test_gemm_4cta_cluster_multicast(B, H, W, Cc, N, conv, bn):
     assert torch.isfinite(out.float()).all()
     err = (out.float() - ref).abs().max().item()
     assert err <= _tol(ref), (err, _tol(ref))
+
+
+# ---- tap reuse: one 10-row activation box per (channel chunk, kx) feeds the three ky taps of a 3x3 stride-1 conv ---------
+@pytest.mark.parametrize("B,H,W,Cc,N,bn,nsub", [(4, 64, 64, 320, 320, 160, 1), (4, 64, 64, 320, 320, 160, 2),
+                                                 (2, 32, 32, 640, 640, 256, 1), (2, 16, 16, 128, 1280, 256, 1),
+                                                 (3, 16, 16, 64, 480, 128, 1), (1, 8, 16, 72, 200, 192, 1),
+                                                 (1, 128, 128, 128, 128, 128, 1), (1, 24, 48, 104, 320, 0, 0)])
+def test_gemm_conv3x3_tap_reuse(B, H, W, Cc, N, bn, nsub):
+    x = _rand(B, H, W, Cc, seed=71)
+    w = _rand(N, Cc, 3, 3, scale=(9 * Cc) ** -0.5, seed=72)
+    bias = _rand(N, seed=73).float()
+    resid = _rand(B, H, W, N, seed=74)
+    out = run_conv(x, w, 1, bias=bias, resid=resid, ver=2, bn=bn, nsub=nsub, tr=2)
+    ref = ref_conv(x, w, 1, bias=bias, resid=resid)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= _tol(ref), (err, _tol(ref))
+    # and it must agree with the per-tap mainloop to accumulation-order noise
+    out1 = run_conv(x, w, 1, bias=bias, resid=resid, ver=2, bn=bn, nsub=nsub, tr=1)
+    assert (out.float() - out1.float()).abs().max().item() <= _tol(ref)
+
+
+def test_gemm_tap_reuse_strided_input():
+    """input view = channel slice of a wider NHWC buffer (skip-concat destination), SiLU epilogue"""
+    big = _rand(2, 32, 32, 704, seed=75)
+    x = big[..., 64:704]
+    w = _rand(320, 640, 3, 3, scale=(9 * 640) ** -0.5, seed=76)
+    bias = _rand(320, seed=77).float()
+    out = run_conv(x, w, 1, bias=bias, act=1, ver=2, tr=2)
+    ref = ref_conv(x, w, 1, bias=bias, act=1)
+    assert (out.float() - ref).abs().max().item() <= _tol(ref)
