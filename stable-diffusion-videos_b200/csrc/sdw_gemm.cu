@@ -175,7 +175,7 @@ int gemm_init() {
 
 // rank-`rank` fp16 tensor map, dim 0 contiguous, SWIZZLE_128B, zero OOB fill.
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-               const uint32_t* box) {
+               const uint32_t* box, int swizzle_bytes) {
   if (int e = gemm_init()) return e;
   cuuint64_t gdim[5];
   cuuint64_t gstride[4];
@@ -204,7 +204,9 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
   }
   if (g_plan_only) return 0;
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstride, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
@@ -429,6 +431,58 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
       if (strides[i] == 0) strides[i] = static_cast<uint64_t>(ldb);
     uint32_t box[4] = {BK, static_cast<uint32_t>(ver == 2 ? bn / 2 : bn), 1, 1};
     if (int e = encode_map(&p.mapB, d.Wt, 4, dims, strides, box)) return e;
+  }
+  // ---- epilogue flavour and pipeline depth of the 2-CTA kernel ----------------------------------------------------
+  p.epi_tma = 0;
+  p.nstages = 0;
+  if (ver == 2) {
+    const int64_t osW = d.o_sW || d.o_sH || d.o_sB ? d.o_sW : d.ldc;
+    const int64_t osH = d.o_sW || d.o_sH || d.o_sB ? d.o_sH : OW * d.ldc;
+    const int64_t osB = d.o_sW || d.o_sH || d.o_sB ? d.o_sB : OH * OW * d.ldc;
+    const int64_t ldr = d.ldr ? d.ldr : d.ldc;
+    const int64_t rsW = d.r_sW || d.r_sH || d.r_sB ? d.r_sW : ldr;
+    const int64_t rsH = d.r_sW || d.r_sH || d.r_sB ? d.r_sH : OW * ldr;
+    const int64_t rsB = d.r_sW || d.r_sH || d.r_sB ? d.r_sB : OH * OW * ldr;
+    auto ok16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+    auto ok_strides = [&](int64_t sw, int64_t sh, int64_t sb) {
+      return sw > 0 && sw % 8 == 0 && (Hd == 1 || sh % 8 == 0) && (d.B == 1 || sb % 8 == 0);
+    };
+    const int ncols = d.mode == GEMM_GEGLU ? d.N / 2 : d.N;
+    bool can = L->cl == 2 && nsub == 1 && !d.b_batched && (d.mode == GEMM_PLAIN || d.mode == GEMM_GEGLU) && !d.rowvec &&
+               d.N % 8 == 0 && bn <= 256 && ok16(d.out) && ok_strides(osW, osH, osB) && (!d.bias || ok16(d.bias)) &&
+               (!d.resid || (ok16(d.resid) && ok_strides(rsW, rsH, rsB) && d.mode == GEMM_PLAIN));
+    if (d.et == 2) SDW_REQUIRE(can, "the TMA epilogue needs the CTA-pair kernel, plain/GEGLU mode, no row vector and 16-byte aligned views");
+    static const int et_env = [] { const char* e = std::getenv("SDW_EPI_TMA"); return e ? std::atoi(e) : -1; }();
+    const int kblocks = p.ntaps * kchunks;
+    // short-K GEMMs are bound by their epilogue (profiles/r01_ncu_epilogue_shortk.md); long-K ones hide the classic
+    // epilogue behind the mainloop and keep the deeper operand pipeline instead
+    const bool want = d.et == 2 || (d.et == 0 && (et_env < 0 ? kblocks <= 24 : et_env != 0));
+    p.epi_tma = can && want ? 1 : 0;
+    const int a_stage = reuse ? 20480 : 16384;
+    const int b_stage = (reuse ? 3 : 1) * nsub * (bn / 2) * 128;
+    const int epi_bytes = p.epi_tma ? G2_EPI_OUT + G2_EPI_BIAS + (d.resid ? G2_RES_STAGES * G2_RES_STAGE : 0) : G2_EPI_OLD;
+    p.nstages = std::min(8, (G2_SMEM_USABLE - G2_BAR_BYTES - epi_bytes) / (a_stage + b_stage));
+    SDW_REQUIRE(p.nstages >= 2, "no room for a two-stage operand pipeline");
+    if (p.epi_tma) {
+      // output lattice: column, then the tile lattice (w, h, b) with the parity scatter folded into base + strides
+      const int sw_ = std::min(bw, 32), sh_ = std::min(bh, 32 / sw_), sb_ = 32 / (sw_ * sh_);
+      uint64_t dims[4] = {static_cast<uint64_t>(ncols), static_cast<uint64_t>(Wd), static_cast<uint64_t>(Hd),
+                          static_cast<uint64_t>(d.B)};
+      auto fix = [&](uint64_t* st) {  // extents of one still need a legal stride
+        for (int i = 2; i < 4; ++i)
+          if (st[i] == 0 || st[i] % 8 != 0) st[i] = st[1] * static_cast<uint64_t>(Wd);
+      };
+      uint64_t so[4] = {1, static_cast<uint64_t>(osW * p.os), static_cast<uint64_t>(osH * p.os), static_cast<uint64_t>(osB)};
+      fix(so);
+      uint32_t box_o[4] = {32, static_cast<uint32_t>(sw_), static_cast<uint32_t>(sh_), static_cast<uint32_t>(sb_)};
+      if (int e = encode_map(&p.mapOut, d.out + p.oy * osH + p.ox * osW, 4, dims, so, box_o, 64)) return e;
+      if (d.resid) {
+        uint64_t sr[4] = {1, static_cast<uint64_t>(rsW * p.os), static_cast<uint64_t>(rsH * p.os), static_cast<uint64_t>(rsB)};
+        fix(sr);
+        uint32_t box_r[4] = {32, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bb)};
+        if (int e = encode_map(&p.mapRes, d.resid + p.oy * rsH + p.ox * rsW, 4, dims, sr, box_r, 64)) return e;
+      }
+    }
   }
   p.bias = d.bias;
   p.rowvec = d.rowvec;

@@ -43,11 +43,10 @@ struct Gemm2Cfg {
   static constexpr int NBUF = (2 * NSUB * BN <= 512) ? 2 : 1;  // accumulator buffers in TMEM
   static constexpr int ACC_COLS = NSUB * BN;
   static constexpr int TMEM_COLS = NBUF * ACC_COLS <= 256 ? 256 : 512;
-  static constexpr int EPI_STAGE = 8 * 2048;  // 2 KB store-coalescing buffer per epilogue warp
-  static constexpr int STAGES = (227 * 1024 - EPI_STAGE - 2048) / (A_STAGE + B_STAGE) > 8
-                                    ? 8
-                                    : (227 * 1024 - EPI_STAGE - 2048) / (A_STAGE + B_STAGE);
-  static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + EPI_STAGE + 1024 + 256;
+  // shared memory: [barriers 1 KB][nstages x A][nstages x B][epilogue buffers]; the planner sizes nstages from what the
+  // chosen epilogue leaves (sdw_internal.h: G2_*), so the carve-up below is a run-time one
+  static constexpr int MAX_STAGES = 8;
+  static constexpr int SMEM_BYTES = G2_SMEM_DYN;
 };
 
 // CL = cluster size.  CL = 4: two CTA pairs of one cluster compute the two neighbouring N tiles of the same M pair; the
@@ -60,17 +59,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
   using Cfg = Gemm2Cfg<BN, NSUB, TR>;
   constexpr int A_STAGE = Cfg::A_STAGE;
   constexpr int NBUF = Cfg::NBUF;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = p.nstages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE;
-  uint8_t* epi_stage = smem_b + STAGES * Cfg::B_STAGE;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + Cfg::EPI_STAGE);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;  // [2]
-  uint64_t* tmem_empty = tmem_full + 2;      // [2]  (leader's copy is the one in use)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + Cfg::MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::MAX_STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;               // [2]  (leader's copy is the one in use)
+  uint64_t* res_full = tmem_empty + 2;                // [G2_RES_STAGES]  residual ring (TMA epilogue)
+  uint64_t* res_empty = res_full + G2_RES_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty + G2_RES_STAGES);
+  uint8_t* smem_a = smem + G2_BAR_BYTES;
+  uint8_t* smem_b = smem_a + STAGES * A_STAGE;
+  uint8_t* epi_stage = smem_b + STAGES * Cfg::B_STAGE;  // classic: 8 x 2 KB; TMA: 8 x 4 KB slabs, 8 x 1 KB bias, ring
+  uint8_t* epi_bias = epi_stage + G2_EPI_OUT;
+  uint8_t* res_ring = epi_bias + G2_EPI_BIAS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();  // rank in the cluster
@@ -96,6 +99,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 16);  // 8 epilogue warps x 2 CTAs
+    }
+    for (int r = 0; r < G2_RES_STAGES; ++r) {
+      mbar_init(&res_full[r], 1);
+      mbar_init(&res_empty[r], 4);  // the four warps (one per TMEM lane quarter) that own the chunk's parity
+    }
+    if (p.epi_tma) {
+      tma_prefetch_desc(&p.mapOut);
+      if (p.resid) tma_prefetch_desc(&p.mapRes);
     }
     fence_barrier_init();
   }
@@ -222,22 +233,48 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
         umma_commit_2cta(&tmem_full[a], static_cast<uint16_t>(0b11u << (2 * pair_id)));
       }
     }
+  } else if (warp == 2) {
+    // =========================== residual producer (TMA epilogue, both CTAs) =========
+    // [128 rows x 32 columns] chunks of this CTA's residual tile, in the order the epilogue consumes them; runs ahead
+    // of the epilogue by up to G2_RES_STAGES chunks, across tile boundaries
+    if (NSUB == 1 && p.epi_tma && p.resid && lane == 0) {
+      uint32_t gc = 0;
+      for (int t = cluster_id; t < total_tiles; t += nclusters) {
+        int x0, y0, b0, n0;
+        tile_coords(t, x0, y0, b0, n0);
+        const int nch = (max(0, min(BN, p.N - n0)) + 31) >> 5;
+        for (int c = 0; c < nch; ++c, ++gc) {
+          const uint32_t slot = gc % G2_RES_STAGES;
+          mbar_wait(&res_empty[slot], ((gc / G2_RES_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&res_full[slot], G2_RES_STAGE);
+          tma_load_4d(&p.mapRes, &res_full[slot], res_ring + slot * G2_RES_STAGE, n0 + c * 32, x0, y0, b0);
+        }
+      }
+    }
   } else if (warp >= 4) {
     // =========================== epilogue (both CTAs, own 128 rows) ==================
     int it = 0;
+    EpiTmaState est;
     for (int t = cluster_id; t < total_tiles; t += nclusters, ++it) {
       int x0, y0, b0, n0;
       tile_coords(t, x0, y0, b0, n0);
       const int a = it % NBUF;
       // the two warps of a lane quarter interleave 32-column chunks: twice the loads / stores in flight
+      if (NSUB == 1 && p.epi_tma) {
+        gemm_epilogue_tma<BN>(p, tmem_base + a * Cfg::ACC_COLS, warp, lane, x0, y0, b0, n0, &tmem_full[a], (it / NBUF) & 1,
+                              (warp - 4) >> 2, epi_stage + (warp - 4) * 4096,
+                              reinterpret_cast<float*>(epi_bias + (warp - 4) * 1024), res_ring, res_full, res_empty, est);
+      } else {
 #pragma unroll
-      for (int sub = 0; sub < NSUB; ++sub)
-        gemm_epilogue<BN>(p, tmem_base + a * Cfg::ACC_COLS + sub * BN, warp, lane, x0, y0, b0, n0 + sub * BN,
-                          &tmem_full[a], (it / NBUF) & 1, (warp - 4) >> 2, 2, epi_stage + (warp - 4) * 2048);
+        for (int sub = 0; sub < NSUB; ++sub)
+          gemm_epilogue<BN>(p, tmem_base + a * Cfg::ACC_COLS + sub * BN, warp, lane, x0, y0, b0, n0 + sub * BN,
+                            &tmem_full[a], (it / NBUF) & 1, (warp - 4) >> 2, 2, epi_stage + (warp - 4) * 2048);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[a]), lead_rank));
     }
+    if (p.epi_tma && lane == 0) bulk_wait_group<0>();  // every output slab has reached global memory
   }
 
   tc_fence_before();

@@ -236,7 +236,8 @@ __device__ __forceinline__ void epi_geglu(const GemmKParams& p, uint32_t taddr, 
         }
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = a[j] * gelu_fast_f(g[j]);
+        for (int j = 0; j < 4; ++j)
+          upk2(geglu2(pk2(0.5f * a[2 * j], 0.5f * a[2 * j + 1]), g[2 * j], g[2 * j + 1]), o[2 * j], o[2 * j + 1]);
         w[j8].x = pack_h2(o[0], o[1]);
         w[j8].y = pack_h2(o[2], o[3]);
         w[j8].z = pack_h2(o[4], o[5]);
@@ -354,6 +355,158 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, uint32_t tme
       store8(out_row + nn, o, vec_out, nvalid);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA epilogue (2-CTA kernel, short-K GEMMs).  The classic epilogue above keeps every global access on the warp's
+// critical path: bias and residual loads behind each TMEM wait, 16-byte row-owner stores to 32 cache lines per
+// instruction.  With five K blocks per tile that chain, not the MMA, set the tile time (profiles/r01_ncu_epilogue_shortk.md:
+// 8.6 us per 256 x 160 tile against a 1.7 us operand-ingest floor).  Here
+//   * the bias slice of the tile is copied to shared memory once per tile (before the accumulator is awaited),
+//   * the residual tile arrives in a 4-deep ring of [128 rows x 32 columns] chunks filled by TMA from a producer
+//     thread that runs ahead across tiles (consumers: the 4 warps that own this chunk's parity),
+//   * each warp writes its 32-row x 32-column output slab to shared memory (64B-swizzled, conflict-free) and one lane
+//     hands it to a TMA store; rows / columns outside the tensor are clipped by the tensor map.
+// State carried across tiles: `res_chunk` (ring position at tile start) and `nstore` (output double-buffer position).
+// ---------------------------------------------------------------------------------------------
+struct EpiTmaState {
+  uint32_t res_chunk = 0;
+  uint32_t nstore = 0;
+};
+
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_tma(const GemmKParams& p, uint32_t tmem_acc, int warp, int lane, int x0,
+                                                  int y0, int b0, int n0, uint64_t* tmem_full_bar, uint32_t full_parity,
+                                                  int cpar, uint8_t* out_stage, float* bias_s, const uint8_t* res_ring,
+                                                  uint64_t* res_full, uint64_t* res_empty, EpiTmaState& st) {
+  const int quarter = warp & 3;
+  const int nmax = max(0, min(BN, p.N - n0));  // valid accumulator columns (multiple of 8)
+  const bool geglu = p.mode == GEMM_GEGLU;
+  // ---- bias slice -> shared memory (GEGLU: value columns carry the 0.5 of GELU) ----
+  __syncwarp();
+#pragma unroll
+  for (int i = lane * 4; i < BN; i += 128) {
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias && i < nmax) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+    if (geglu && (i & 32) == 0) {
+      b4.x *= 0.5f; b4.y *= 0.5f; b4.z *= 0.5f; b4.w *= 0.5f;
+    }
+    *reinterpret_cast<float4*>(bias_s + i) = b4;
+  }
+  __syncwarp();
+  // this warp's 32-row slab of the tile in lattice coordinates
+  const int row0 = quarter * 32;
+  const int sx = x0 + row0 % p.bw, sy = y0 + (row0 / p.bw) % p.bh, sb = b0 + row0 / (p.bw * p.bh);
+  const int sw = (lane >> 1) & 3;  // 64B-swizzle phase of this thread's row (slab and ring bases are 512B aligned)
+
+  mbar_wait(tmem_full_bar, full_parity);
+  tc_fence_after();
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+  const uint64_t alpha2 = pk2(p.alpha, p.alpha);
+
+  if (geglu) {
+    const uint64_t alpha_h = pk2(0.5f * p.alpha, 0.5f * p.alpha);
+#pragma unroll 1
+    for (int c = cpar; c * 64 < nmax; c += 2) {
+      uint8_t* ob = out_stage + (st.nstore & 1) * 2048;
+      if (lane == 0) bulk_wait_group_read<1>();  // the slab written two stores ago has left shared memory
+      __syncwarp();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t va[16], vg[16];
+        tmem_ld_32x16(taddr + c * 64 + half * 16, va);
+        tmem_ld_32x16(taddr + c * 64 + 32 + half * 16, vg);
+        tmem_ld_wait();
+        const float* ba = bias_s + c * 64 + half * 16;
+        const float* bg = ba + 32;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int e = q * 8 + 2 * j;
+            const float2 bav = *reinterpret_cast<const float2*>(ba + e);
+            const float2 bgv = *reinterpret_cast<const float2*>(bg + e);
+            const uint64_t ah = fma2(pk2(__uint_as_float(va[e]), __uint_as_float(va[e + 1])), alpha_h, pk2(bav.x, bav.y));
+            float g0, g1;
+            upk2(fma2(pk2(__uint_as_float(vg[e]), __uint_as_float(vg[e + 1])), alpha2, pk2(bgv.x, bgv.y)), g0, g1);
+            float o0, o1;
+            upk2(geglu2(ah, g0, g1), o0, o1);
+            w[j] = pack_h2(o0, o1);
+          }
+          *reinterpret_cast<uint4*>(ob + lane * 64 + (((half * 2 + q) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&p.mapOut, ob, (n0 >> 1) + c * 32, sx, sy, sb);
+        bulk_commit_group();
+      }
+      ++st.nstore;
+    }
+    return;
+  }
+
+  const int nch = (nmax + 31) >> 5;
+  const bool silu = p.act == 1;
+#pragma unroll 1
+  for (int c = cpar; c < nch; c += 2) {
+    uint8_t* ob = out_stage + (st.nstore & 1) * 2048;
+    if (lane == 0) bulk_wait_group_read<1>();
+    __syncwarp();
+    const uint8_t* rs = nullptr;
+    uint32_t slot = 0;
+    if (p.resid) {
+      const uint32_t gc = st.res_chunk + c;
+      slot = gc % G2_RES_STAGES;
+      mbar_wait(&res_full[slot], (gc / G2_RES_STAGES) & 1);
+      rs = res_ring + slot * G2_RES_STAGE + (row0 + lane) * 64;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[16];
+      tmem_ld_32x16(taddr + c * 32 + half * 16, v);
+      tmem_ld_wait();
+      const float* bs = bias_s + c * 32 + half * 16;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int j8 = half * 2 + q;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 bv = *reinterpret_cast<const float2*>(bs + q * 8 + 2 * j);
+          upk2(fma2(pk2(__uint_as_float(v[q * 8 + 2 * j]), __uint_as_float(v[q * 8 + 2 * j + 1])), alpha2, pk2(bv.x, bv.y)),
+               o[2 * j], o[2 * j + 1]);
+        }
+        if (silu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = silu_f(o[j]);
+        }
+        if (rs) {
+          const uint4 r4 = *reinterpret_cast<const uint4*>(rs + ((j8 ^ sw) << 4));
+          const __half2* h = reinterpret_cast<const __half2*>(&r4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            o[2 * j] += f.x;
+            o[2 * j + 1] += f.y;
+          }
+        }
+        *reinterpret_cast<uint4*>(ob + lane * 64 + ((j8 ^ sw) << 4)) =
+            make_uint4(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]), pack_h2(o[4], o[5]), pack_h2(o[6], o[7]));
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();  // also orders every lane's ring reads before the release below
+    if (lane == 0) {
+      if (p.resid) mbar_arrive(&res_empty[slot]);
+      tma_store_4d(&p.mapOut, ob, n0 + c * 32, sx, sy, sb);
+      bulk_commit_group();
+    }
+    ++st.nstore;
+  }
+  st.res_chunk += nch;
 }
 
 }  // namespace sdw

@@ -77,6 +77,12 @@ struct alignas(64) GemmKParams {
   int stage_stores;         // 1: bounce output chunks through shared memory for coalesced stores (wide-N GEMMs)
   int m_pairs, n_tiles;     // 2-CTA persistent kernel: tile grid (pairs of 128-row M tiles x BN-wide N tiles)
   int tap_reuse;            // 1: 3x3 conv with one (bh+2)-row activation box per (channel chunk, kx) shared by the 3 ky taps
+  // TMA epilogue (2-CTA kernel, short-K GEMMs): output chunks leave through TMA stores, the residual tile arrives
+  // through a TMA-fed shared-memory ring, the bias is staged per warp (sdw_gemm_epi.cuh: gemm_epilogue_tma)
+  CUtensorMap mapOut;       // (columns, w, h, b) lattice of the output, box (32, slab_w, slab_h, slab_b), 64B swizzle
+  CUtensorMap mapRes;       // ... of the residual, box (32, bw, bh, bb)
+  int epi_tma;
+  int nstages;              // mainloop pipeline depth (what the epilogue buffers leave of the 227 KB)
   // epilogue
   const float* bias;        // [N] or null
   const float* rowvec;      // [B][rowvec_ld] per-sample vector added per column (time-embedding proj) or null
@@ -139,6 +145,7 @@ struct GemmDesc {
   int nsub = 0; // 0 = auto, 1 / 2: accumulators per activation tile in the 2-CTA kernel
   int cl = 0;   // 0 = auto, 2 / 4: cluster size of the 2-CTA kernel
   int tr = 0;   // 0 = auto, 1 = never, 2 = require the tap-reuse mainloop (3x3 stride-1 conv, W % 16 == 0, H % 8 == 0)
+  int et = 0;   // 0 = auto, 1 = never, 2 = require the TMA epilogue
 };
 
 int plan_gemm(const GemmDesc& d, GemmLaunch* out);
@@ -148,8 +155,16 @@ int gemm2_init();
 int gemm2_max_clusters4();
 void set_plan_only(bool on);
 int gemm_init();  // resolves the driver entry point, sets smem attributes
+// shared-memory budget of the 2-CTA kernel (sdw_gemm2.cu): barriers, then the operand ring, then the epilogue buffers
+constexpr int G2_SMEM_DYN = 227 * 1024;                    // requested dynamic shared memory
+constexpr int G2_SMEM_USABLE = G2_SMEM_DYN - 1024;         // after the 1 KB alignment slack
+constexpr int G2_BAR_BYTES = 1024;
+constexpr int G2_EPI_OLD = 8 * 2048;                       // 2 KB store-coalescing buffer per epilogue warp
+constexpr int G2_EPI_OUT = 8 * 2 * 2048;                   // TMA epilogue: two 32-row x 64-byte output slabs per warp
+constexpr int G2_EPI_BIAS = 8 * 1024;                      //   per-warp bias copy (<= 256 fp32 columns)
+constexpr int G2_RES_STAGES = 4, G2_RES_STAGE = 128 * 64;  //   residual ring: [128 rows x 32 columns] fp16 chunks
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-               const uint32_t* box);
+               const uint32_t* box, int swizzle_bytes = 128);
 
 // ---------------------------------------------------------------------------
 // fused attention (sdw_attn.cu)

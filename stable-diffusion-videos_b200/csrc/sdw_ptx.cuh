@@ -97,6 +97,23 @@ __device__ __forceinline__ void tma_load_4d(const void* map, uint64_t* bar, void
       : "memory");
 }
 
+// TMA store (shared::cta -> global through a tensor map; rows / columns outside the tensor are clipped) and its
+// bulk-group bookkeeping (issued and waited on by the same thread)
+__device__ __forceinline__ void tma_store_4d(const void* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {  // <= N groups still READING shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ----------------------------------------------------------------------------
 // tcgen05: TMEM allocation, fences, MMA, commit, TMEM loads
 // ----------------------------------------------------------------------------
@@ -288,6 +305,57 @@ __device__ __forceinline__ float gelu_fast_f(float g) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-(z * z) * 1.4426950408889634f));
   const float erf_abs = fmaf(-q, e, 1.f);
   return 0.5f * g * (1.f + copysignf(erf_abs, g));
+}
+// packed fp32x2 math (sm_100a FFMA2 / FMUL2 / FADD2): one issue slot for two values
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// (2 * ah) * gelu(g) for two lanes, ah = HALF the value operand (the 0.5 of GELU is folded into it by the caller).
+// Same Abramowitz-Stegun 7.1.26 erf as gelu_fast_f, rearranged so that no sign handling is left:
+//   g * (1 + erf(g / sqrt2)) = g + |g| * erf(|g| / sqrt2),  erf(z) = 1 - q(t) e^{-z^2},  t = 1 / (1 + p z)
+// ~10 issue slots per value (2 MUFU) instead of ~39 in scalar form — the GEGLU epilogue was instruction bound
+// (profiles/r01_ncu_epilogue_shortk.md).
+__device__ __forceinline__ uint64_t geglu2(uint64_t ah, float g0, float g1) {
+  const uint64_t g = pk2(g0, g1);
+  const uint64_t z = pk2(fabsf(g0), fabsf(g1));  // |g|
+  float d0, d1;
+  upk2(fma2(z, pk2(0.3275911f * 0.70710678118654752f, 0.3275911f * 0.70710678118654752f), pk2(1.f, 1.f)), d0, d1);
+  float t0, t1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t = pk2(t0, t1);
+  uint64_t q = fma2(pk2(-1.061405429f, -1.061405429f), t, pk2(1.453152027f, 1.453152027f));  // -q(t): signs flipped
+  q = fma2(q, t, pk2(-1.421413741f, -1.421413741f));
+  q = fma2(q, t, pk2(0.284496736f, 0.284496736f));
+  q = fma2(q, t, pk2(-0.254829592f, -0.254829592f));
+  q = mul2(q, t);
+  float x0, x1;
+  upk2(mul2(mul2(z, z), pk2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f)), x0, x1);  // -z^2/2 * log2(e)
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+  const uint64_t erf_abs = fma2(q, pk2(e0, e1), pk2(1.f, 1.f));  // 1 - q e
+  return mul2(ah, fma2(z, erf_abs, g));
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);

@@ -21,7 +21,7 @@ def _tol(ref):
     return float(ref.abs().max()) * 2.0 ** -9 + 1e-3
 
 
-def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None, ver=0, nsub=0, cl=0, tr=0):
+def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None, ver=0, nsub=0, cl=0, tr=0, et=0, out_buf=None, out_c0=0):
     """x: [B,H,W,C] fp16 cuda; returns NHWC fp16 output computed by the native kernel."""
     n = _native()
     B, H, W, Cc = x_nhwc.shape
@@ -34,7 +34,10 @@ def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn
     else:
         OH, OW = H, W
     ncols = N // 2 if mode == 1 else N
-    out = torch.full((B, OH, OW, ncols), float("nan"), dtype=torch.float16, device="cuda")
+    if out_buf is None:
+        out = torch.full((B, OH, OW, ncols), float("nan"), dtype=torch.float16, device="cuda")
+    else:  # channel slice [out_c0, out_c0 + ncols) of a wider NHWC buffer (the skip-concat destinations)
+        out = out_buf[..., out_c0:out_c0 + ncols]
     parities = [(0, 0), (0, 1), (1, 0), (1, 1)] if conv == 3 else [(0, 0)]
     for (py, px) in parities:
         d = n.GemmDesc()
@@ -53,7 +56,7 @@ def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn
             d.resid = resid.data_ptr()
             d.ldr = resid.shape[-1]
         d.out = out.data_ptr()
-        d.ldc = ncols
+        d.ldc = out.stride(2)
         d.mode = mode
         d.act = act
         d.alpha = 1.0
@@ -62,6 +65,7 @@ def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn
         d.nsub = nsub
         d.cl = cl
         d.tr = tr
+        d.et = et
         n.gemm(d)
     torch.cuda.synchronize()
     return out
@@ -355,4 +359,59 @@ def test_gemm_tap_reuse_strided_input():
     bias = _rand(320, seed=77).float()
     out = run_conv(x, w, 1, bias=bias, act=1, ver=2, tr=2)
     ref = ref_conv(x, w, 1, bias=bias, act=1)
+    assert (out.float() - ref).abs().max().item() <= _tol(ref)
+
+
+# ---- TMA epilogue: bias in shared memory, residual through a TMA-fed ring, output slabs through TMA stores ---------------
+@pytest.mark.parametrize("B,H,W,Cc,N,conv,bn,act,res", [
+    (1, 1, 5000, 320, 320, 0, 160, 0, True),     # token lattice, ragged last tile, residual (attention out-projection)
+    (1, 1, 4096, 1280, 320, 0, 0, 0, True),      # ff.out
+    (2, 32, 32, 640, 640, 0, 160, 0, True),      # 1x1 conv on an image lattice (proj_out)
+    (2, 16, 16, 128, 1280, 0, 256, 1, False),    # SiLU, no residual, BLOCK_N 256
+    (3, 8, 8, 64, 200, 0, 128, 0, True),         # batch-folded tiles (bb = 2), ragged N, odd tile count
+    (2, 64, 64, 64, 320, 2, 160, 0, True),       # stride-2 conv
+    (2, 16, 16, 64, 640, 3, 160, 0, True),       # folded upsample: parity-scattered stores + residual reads
+    (4, 64, 64, 320, 320, 1, 160, 0, True),      # 3x3 with tap reuse and the TMA epilogue together
+    (1, 1, 300, 64, 768, 0, 192, 0, False),
+])
+def test_gemm_tma_epilogue(B, H, W, Cc, N, conv, bn, act, res):
+    x = _rand(B, H, W, Cc, seed=81)
+    k = 3 if conv else 1
+    w = _rand(N, Cc, k, k, scale=(k * k * Cc) ** -0.5, seed=82)
+    bias = _rand(N, seed=83).float()
+    oh, ow = (H // 2, W // 2) if conv == 2 else ((2 * H, 2 * W) if conv == 3 else (H, W))
+    resid = _rand(B, oh, ow, N, seed=84) if res else None
+    out = run_conv(x, w, conv, bias=bias, resid=resid, act=act, ver=2, bn=bn, et=2)
+    ref = ref_conv(x, w if conv else w.reshape(N, Cc), conv, bias=bias, resid=resid, act=act)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= _tol(ref), (err, _tol(ref))
+    out1 = run_conv(x, w, conv, bias=bias, resid=resid, act=act, ver=2, bn=bn, et=1)
+    assert (out.float() - out1.float()).abs().max().item() <= _tol(ref)
+
+
+def test_gemm_tma_epilogue_concat_slice_and_no_bias():
+    """output = channel slice of a wider buffer; neighbours must stay untouched (TMA clipping at the column extent)"""
+    x = _rand(2, 32, 32, 320, seed=85)
+    w = _rand(320, 320, 1, 1, scale=320 ** -0.5, seed=86)
+    buf = torch.full((2, 32, 32, 960), 7.0, dtype=torch.float16, device="cuda")
+    out = run_conv(x, w, 0, ver=2, et=2, out_buf=buf, out_c0=320)
+    ref = ref_conv(x, w.reshape(320, 320), 0)
+    assert (out.float() - ref).abs().max().item() <= _tol(ref)
+    assert (buf[..., :320] == 7.0).all() and (buf[..., 640:] == 7.0).all()
+
+
+@pytest.mark.parametrize("M,K,Ch", [(1024, 320, 1280), (900, 640, 2560), (256, 1280, 5120)])
+def test_geglu_tma_epilogue(M, K, Ch):
+    x = _rand(1, 1, M, K, seed=87)
+    w = _rand(2 * Ch, K, scale=K ** -0.5, seed=88)
+    bias = _rand(2 * Ch, seed=89).float()
+    blk = torch.arange(2 * Ch, device="cuda")
+    b64, within = blk // 64, blk % 64
+    src = torch.where(within < 32, b64 * 32 + within, Ch + b64 * 32 + within - 32)
+    out = run_conv(x, w, 0, bias=bias[src].contiguous(), mode=1, ver=2, et=2)
+    h = x.float().reshape(M, K) @ w.float().t() + bias
+    a, g = h.chunk(2, dim=-1)
+    ref = (a * Fn.gelu(g)).reshape(1, 1, M, Ch)
+    assert torch.isfinite(out.float()).all()
     assert (out.float() - ref).abs().max().item() <= _tol(ref)
