@@ -174,7 +174,9 @@ typedef struct sdw_gemm_desc {
   int32_t nsub;              /* 0 auto, 1 / 2: accumulators per activation tile in the CTA-pair kernel */
   int32_t cl;                /* 0 auto, 2 / 4: cluster size (4: activation tile multicast to two CTA pairs) */
   int32_t tr;                /* 0 auto, 1 never, 2 require: 3x3 taps reuse one activation box in shared memory */
-  int32_t et;                /* 0 auto, 1 never, 2 require: TMA-store epilogue with a TMA-fed residual ring */
+  int32_t et;                /* 0 auto, 1 never, 2 require: TMA-store epilogue with a TMA-fed residual ring.  With mode 2 the
+                              * V^T rows are written through TMA, which clips the token extent at 16-byte granularity: the
+                              * vt_ld padding up to the next multiple of 8 tokens may receive finite filler values */
 } sdw_gemm_desc;
 
 int sdw_gemm(const sdw_gemm_desc* desc, void* stream);

@@ -205,7 +205,8 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
   if (g_plan_only) return 0;
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstride, bx, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                           : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -447,16 +448,21 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
     auto ok_strides = [&](int64_t sw, int64_t sh, int64_t sb) {
       return sw > 0 && sw % 8 == 0 && (Hd == 1 || sh % 8 == 0) && (d.B == 1 || sb % 8 == 0);
     };
-    const int ncols = d.mode == GEMM_GEGLU ? d.N / 2 : d.N;
-    bool can = L->cl == 2 && nsub == 1 && !d.b_batched && (d.mode == GEMM_PLAIN || d.mode == GEMM_GEGLU) && !d.rowvec &&
+    const int ncols = d.mode == GEMM_GEGLU ? d.N / 2 : (d.mode == GEMM_QKV_VT ? d.vt_col0 : d.N);
+    // V^T scatter through TMA: token lattice (H == 1, 128-token tiles), 32-column chunks never straddle vt_col0
+    const bool vt_ok = d.mode != GEMM_QKV_VT ||
+                       (Hd == 1 && bw == BM && d.conv == 0 && d.vt_col0 % 32 == 0 && d.vt_ld % 8 == 0 && ok16(d.vt) &&
+                        d.vt_ntok == Wd && !d.resid);
+    bool can = L->cl == 2 && nsub == 1 && !d.b_batched && vt_ok && (!d.rowvec || d.rowvec_ld == 0) &&
                d.N % 8 == 0 && bn <= 256 && ok16(d.out) && ok_strides(osW, osH, osB) && (!d.bias || ok16(d.bias)) &&
                (!d.resid || (ok16(d.resid) && ok_strides(rsW, rsH, rsB) && d.mode == GEMM_PLAIN));
     if (d.et == 2) SDW_REQUIRE(can, "the TMA epilogue needs the CTA-pair kernel, plain/GEGLU mode, no row vector and 16-byte aligned views");
     static const int et_env = [] { const char* e = std::getenv("SDW_EPI_TMA"); return e ? std::atoi(e) : -1; }();
     const int kblocks = p.ntaps * kchunks;
-    // short-K GEMMs are bound by their epilogue (profiles/r01_ncu_epilogue_shortk.md); long-K ones hide the classic
-    // epilogue behind the mainloop and keep the deeper operand pipeline instead
-    const bool want = d.et == 2 || (d.et == 0 && (et_env < 0 ? kblocks <= 24 : et_env != 0));
+    // short-K GEMMs are bound by their epilogue (profiles/r01_ncu_epilogue_shortk.md) and gain up to 2x; long-K ones
+    // lose one operand stage to the epilogue buffers but still come out ahead end to end (bench: 8.49 -> 8.56 frames/s),
+    // so the TMA epilogue is used wherever it is eligible.  SDW_EPI_TMA=0 disables it, =2 restricts it to <= 24 K blocks.
+    const bool want = d.et == 2 || (d.et == 0 && (et_env < 0 || et_env == 1 || (et_env == 2 && kblocks <= 24)));
     p.epi_tma = can && want ? 1 : 0;
     const int a_stage = reuse ? 20480 : 16384;
     const int b_stage = (reuse ? 3 : 1) * nsub * (bn / 2) * 128;
@@ -476,6 +482,14 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
       fix(so);
       uint32_t box_o[4] = {32, static_cast<uint32_t>(sw_), static_cast<uint32_t>(sh_), static_cast<uint32_t>(sb_)};
       if (int e = encode_map(&p.mapOut, d.out + p.oy * osH + p.ox * osW, 4, dims, so, box_o, 64)) return e;
+      if (d.mode == GEMM_QKV_VT) {
+        const int vrows = d.N - d.vt_col0;  // heads * d rows of V^T per sample
+        uint64_t dv[3] = {static_cast<uint64_t>(Wd), static_cast<uint64_t>(vrows), static_cast<uint64_t>(d.B)};
+        uint64_t sv[3] = {1, static_cast<uint64_t>(d.vt_ld), static_cast<uint64_t>(d.vt_ld) * static_cast<uint64_t>(d.vt_heads) * d.vt_d};
+        uint32_t bv[3] = {32, 32, 1};
+        SDW_REQUIRE(vrows == d.vt_heads * d.vt_d, "V^T rows must be heads x d");
+        if (int e = encode_map(&p.mapVt, d.vt, 3, dv, sv, bv, 0)) return e;
+      }
       if (d.resid) {
         uint64_t sr[4] = {1, static_cast<uint64_t>(rsW * p.os), static_cast<uint64_t>(rsH * p.os), static_cast<uint64_t>(rsB)};
         fix(sr);

@@ -388,6 +388,10 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKParams& p, uint32_t
   for (int i = lane * 4; i < BN; i += 128) {
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias && i < nmax) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+    if (p.rowvec && i < nmax) {  // time-embedding row, the same for every sample (rowvec_ld == 0: planner-checked)
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.rowvec + n0 + i));
+      b4.x += r4.x; b4.y += r4.y; b4.z += r4.z; b4.w += r4.w;
+    }
     if (geglu && (i & 32) == 0) {
       b4.x *= 0.5f; b4.y *= 0.5f; b4.z *= 0.5f; b4.w *= 0.5f;
     }
@@ -450,11 +454,36 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKParams& p, uint32_t
 
   const int nch = (nmax + 31) >> 5;
   const bool silu = p.act == 1;
+  const bool vt_mode = p.mode == GEMM_QKV_VT;
 #pragma unroll 1
   for (int c = cpar; c < nch; c += 2) {
     uint8_t* ob = out_stage + (st.nstore & 1) * 2048;
     if (lane == 0) bulk_wait_group_read<1>();
     __syncwarp();
+    if (vt_mode && n0 + c * 32 >= p.vt_col0) {
+      // V columns leave transposed: slab[row = column of this chunk][token = lane] (32 x 64 B, unswizzled), one TMA
+      // store into V^T (token contiguous).  A warp-wide 2-byte store row is 64 contiguous bytes: conflict-free.
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[16];
+        tmem_ld_32x16(taddr + c * 32 + half * 16, v);
+        tmem_ld_wait();
+        const float* bs = bias_s + c * 32 + half * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float o = fmaf(__uint_as_float(v[j]), p.alpha, bs[j]);
+          *reinterpret_cast<__half*>(ob + (half * 16 + j) * 64 + lane * 2) = __float2half_rn(o);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&p.mapVt, ob, sx, n0 + c * 32 - p.vt_col0, sb);
+        bulk_commit_group();
+      }
+      ++st.nstore;
+      continue;
+    }
     const uint8_t* rs = nullptr;
     uint32_t slot = 0;
     if (p.resid) {

@@ -81,6 +81,7 @@ struct alignas(64) GemmKParams {
   // through a TMA-fed shared-memory ring, the bias is staged per warp (sdw_gemm_epi.cuh: gemm_epilogue_tma)
   CUtensorMap mapOut;       // (columns, w, h, b) lattice of the output, box (32, slab_w, slab_h, slab_b), 64B swizzle
   CUtensorMap mapRes;       // ... of the residual, box (32, bw, bh, bb)
+  CUtensorMap mapVt;        // GEMM_QKV_VT: V^T as (token, head * d + dd, sample), box (32 tokens, 32 rows), no swizzle
   int epi_tma;
   int nstages;              // mainloop pipeline depth (what the epilogue buffers leave of the 227 KB)
   // epilogue

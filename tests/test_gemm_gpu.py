@@ -415,3 +415,36 @@ def test_geglu_tma_epilogue(M, K, Ch):
     ref = (a * Fn.gelu(g)).reshape(1, 1, M, Ch)
     assert torch.isfinite(out.float()).all()
     assert (out.float() - ref).abs().max().item() <= _tol(ref)
+
+
+@pytest.mark.parametrize("Bn,Ntok,Cc,heads,et", [(2, 300, 320, 8, 2), (2, 300, 320, 8, 1), (3, 1024, 640, 8, 2), (1, 256, 1280, 8, 2)])
+def test_qkv_vt_tma_epilogue(Bn, Ntok, Cc, heads, et):
+    """fused QKV projection: Q|K columns through TMA row slabs, V columns transposed in shared memory -> V^T."""
+    n = _native()
+    d = Cc // heads
+    ld = (Ntok + 7) // 8 * 8
+    x = _rand(Bn, 1, Ntok, Cc, seed=91)
+    wqkv = _rand(3 * Cc, Cc, scale=Cc ** -0.5, seed=92)
+    bias = _rand(3 * Cc, seed=93).float()
+    wp = n.pack_weight(wqkv)
+    qk = torch.full((Bn, Ntok, 2 * Cc), 3.0, dtype=torch.float16, device="cuda")
+    vt = torch.full((Bn, heads, d, ld), 5.0, dtype=torch.float16, device="cuda")
+    g = n.GemmDesc()
+    g.A = x.data_ptr(); g.C, g.W, g.H, g.B = Cc, Ntok, 1, Bn
+    g.sW, g.sH, g.sB = Cc, Ntok * Cc, Ntok * Cc
+    g.Wt = wp.data_ptr(); g.N = 3 * Cc
+    g.bias = bias.data_ptr()
+    g.out = qk.data_ptr(); g.ldc = 2 * Cc
+    g.mode = 2; g.alpha = 1.0; g.ver = 2; g.et = et
+    g.vt_col0, g.vt_d, g.vt_heads, g.vt_ntok = 2 * Cc, d, heads, Ntok
+    g.vt = vt.data_ptr(); g.vt_ld = ld
+    n.gemm(g)
+    torch.cuda.synchronize()
+    ref = x.float().reshape(Bn, Ntok, Cc) @ wqkv.float().t() + bias
+    q_ref, k_ref, v_ref = ref.split(Cc, dim=-1)
+    assert (qk.float() - torch.cat([q_ref, k_ref], -1)).abs().max().item() <= _tol(ref)
+    vt_ref = v_ref.reshape(Bn, Ntok, heads, d).permute(0, 2, 3, 1)
+    assert (vt[..., :Ntok].float() - vt_ref).abs().max().item() <= _tol(ref)
+    # TMA clips the contiguous (token) extent at 16-byte granularity: the row padding up to the next multiple of 8 tokens
+    # may receive finite filler values (sdwalk.h documents this); it must never be NaN / inf
+    assert torch.isfinite(vt.float()).all()
