@@ -117,5 +117,18 @@ def pack_weight_up4(w):
     return out
 
 
+def groupnorm(x, B, P, Cc, G, gamma, beta, eps, silu, y):
+    """x, y: fp16 [B][P][ld] views whose last dim may be a channel slice of a wider buffer (ld = stride of dim -2)."""
+    require_cuda(x, y, gamma, beta)
+    check(lib().sdw_groupnorm(ptr(x), C.c_int64(x.stride(-2)), C.c_int(B), C.c_int64(P), C.c_int(Cc), C.c_int(G), ptr(gamma),
+                              ptr(beta), C.c_float(eps), C.c_int(int(silu)), ptr(y), C.c_int64(y.stride(-2)), stream_ptr()))
+
+
+def layernorm(x, rows, Cc, gamma, beta, eps, y):
+    require_cuda(x, y, gamma, beta)
+    check(lib().sdw_layernorm(ptr(x), C.c_int64(x.stride(-2)), C.c_int64(rows), C.c_int(Cc), ptr(gamma), ptr(beta),
+                              C.c_float(eps), ptr(y), C.c_int64(y.stride(-2)), stream_ptr()))
+
+
 def gemm(desc):
     check(lib().sdw_gemm(C.byref(desc), stream_ptr()))

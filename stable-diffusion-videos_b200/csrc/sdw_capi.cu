@@ -84,6 +84,23 @@ int sdw_attention(const void* q, int64_t q_ld, const void* k, int64_t k_ld, cons
   return launch_attention(L, static_cast<cudaStream_t>(stream));
 }
 
+int sdw_groupnorm(const void* x, int64_t ldx, int B, int64_t P, int C, int G, const float* gamma, const float* beta,
+                  float eps, int silu, void* y, int64_t ldy, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float2* ws = nullptr;  // workspace of the three-kernel path (the engine keeps one in its arena)
+  SDW_CUDA_OK(cudaMallocAsync(&ws, gn_workspace_bytes(B), st));
+  const int rc = groupnorm(static_cast<const __half*>(x), ldx, B, P, C, G, gamma, beta, eps, silu, static_cast<__half*>(y),
+                           ldy, ws, st);
+  cudaFreeAsync(ws, st);
+  return rc;
+}
+
+int sdw_layernorm(const void* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                  void* y, int64_t ldy, void* stream) {
+  return layernorm(static_cast<const __half*>(x), ldx, rows, C, gamma, beta, eps, static_cast<__half*>(y), ldy,
+                   static_cast<cudaStream_t>(stream));
+}
+
 int sdw_pack_weight_up4(const void* w_oihw, int N, int C, void* out, void* stream) {
   return pack_weight_up4(w_oihw, N, C, out, static_cast<cudaStream_t>(stream));
 }

@@ -218,7 +218,7 @@ struct Engine {
     tag_next = "groupnorm C" + std::to_string(x.C) + " " + std::to_string(x.B) + "x" + std::to_string(x.H) + "x" + std::to_string(x.W);
     emit([=](cudaStream_t st, int) {
       return groupnorm(x.p, x.ld, x.B, static_cast<int64_t>(x.H) * x.W, x.C, G, g, b, eps, silu, out.p, out.ld, ws, st);
-    }, 3);
+    }, groupnorm_launches());
   }
   void ln(const T& x, const std::string& name, const T& out) {
     const float* g = vec(name + ".weight", x.C);
@@ -440,6 +440,7 @@ struct Engine {
       const float* b = vec("conv_in.bias", ch[0]);
       const T o = h;
       const int cin = cfg.in_channels, n = ch[0];
+      tag_next = "conv_in 4->C (CUDA cores)";
       emit([=](cudaStream_t st, int) { return conv_in_small(xin.p, xin.ld, xin.B, xin.H, xin.W, cin, w, b, n, o.p, o.ld, st); });
     }
     // down path
@@ -513,6 +514,7 @@ struct Engine {
       const float* b = vec("conv_out.bias", cfg.out_channels);
       float* e_out = eps;
       const int oc = cfg.out_channels;
+      tag_next = "conv_out C->4 (CUDA cores)";
       emit([=](cudaStream_t st, int) { return conv_out_small(n.p, n.ld, n.B, n.H, n.W, n.C, w, b, oc, e_out, nullptr, st); });
     }
     return 0;
@@ -533,6 +535,7 @@ struct Engine {
       const float* b = vec("vae.post_quant_conv.bias", lc);
       const float* xs = x;
       const float inv = 1.f / cfg.vae_scaling_factor;
+      tag_next = "vae_in (scale + post_quant 1x1)";
       emit([=](cudaStream_t st, int) { return vae_in(xs, inv, w, b, F, lc, H0, W0, z.p, st); });
     }
     T h = act(F, H0, W0, ctop);
@@ -540,6 +543,7 @@ struct Engine {
       const __half* w = w_raw("vae.decoder.conv_in.weight", static_cast<int64_t>(ctop) * lc * 9);
       const float* b = vec("vae.decoder.conv_in.bias", ctop);
       const T o = h;
+      tag_next = "vae conv_in 4->C (CUDA cores)";
       emit([=](cudaStream_t st, int) { return conv_in_small(z.p, z.ld, F, H0, W0, lc, w, b, ctop, o.p, o.ld, st); });
     }
     // mid block
@@ -607,6 +611,7 @@ struct Engine {
       uint8_t* o8 = out_u8;
       float* of = out_img_f32;
       const int oc = cfg.vae_out_channels;
+      tag_next = "vae conv_out C->3 + uint8 (CUDA cores)";
       emit([=](cudaStream_t st, int) { return conv_out_small(n.p, n.ld, n.B, n.H, n.W, n.C, w, b, oc, of, o8, st); });
     }
     return 0;

@@ -7,7 +7,11 @@
 #include "sdw_internal.h"
 #include "sdw_ptx.cuh"
 
+#include <cooperative_groups.h>
+#include <cstdlib>
+
 namespace sdw {
+namespace cg = cooperative_groups;
 
 // =============================================================================================
 // GroupNorm: three small deterministic kernels.
@@ -192,6 +196,153 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused GroupNorm: one thread-block cluster per sample (looping over samples), statistics and normalisation in ONE
+// launch.  Each CTA sums its pixel slice (same fixed-order arithmetic as gn_partial_det_kernel), the per-CTA partials
+// are exchanged through distributed shared memory and reduced in rank order by every CTA, and the slice is normalised
+// right away — while it is still in L2, because only (clusters in flight) x (one sample) of the tensor is live at a
+// time.  Against the three-kernel version this drops one HBM read of the tensor and two launches
+// (64x64x320, batch 32: 82 us -> see profiles/r01_op_profile_*.txt).
+// ---------------------------------------------------------------------------------------------
+static constexpr int GNF_THREADS = 512;
+
+__global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const __half* __restrict__ x, int64_t ldx, int B, int C,
+                                                               int G, int64_t P, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float eps, int silu,
+                                                               __half* __restrict__ y, int64_t ldy) {
+  extern __shared__ float sm[];  // [rows][C] sums, [rows][C] squares
+  __shared__ float2 s_part[GN_MAX_GROUPS];
+  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cs = static_cast<int>(cluster.num_blocks());
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int cluster_id = blockIdx.x / cs, nclusters = gridDim.x / cs;
+  pdl_wait();
+  pdl_launch_dependents();
+  const int cg_ = C / G;
+  const int vecs = C / 8;
+  const int rows = max(1, min(min(GNF_THREADS / vecs, 16), 6144 / C));
+  float* ssum = sm;
+  float* ssq = sm + rows * C;
+  const int64_t ppc = (P + cs - 1) / cs;
+  const int64_t p0 = min(P, static_cast<int64_t>(rank) * ppc), p1 = min(P, p0 + ppc);
+  const float count = static_cast<float>(P) * cg_;
+
+  for (int b = cluster_id; b < B; b += nclusters) {
+    const __half* xb = x + static_cast<int64_t>(b) * P * ldx;
+    __half* yb = y + static_cast<int64_t>(b) * P * ldy;
+    // ---- phase 1: per-channel sums over this CTA's pixels ----
+    for (int item = threadIdx.x; item < rows * vecs; item += blockDim.x) {
+      const int v = item % vecs, prow = item / vecs;
+      float s[8], q[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+      auto acc8 = [&](const uint4& u) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          s[2 * j] += f.x;
+          q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
+          s[2 * j + 1] += f.y;
+          q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
+        }
+      };
+      int64_t p = p0 + prow;
+      for (; p + 3 * rows < p1; p += 4 * rows) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (p + k * rows) * ldx + v * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc8(u[k]);
+      }
+      for (; p < p1; p += rows) acc8(*reinterpret_cast<const uint4*>(xb + p * ldx + v * 8));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ssum[prow * C + v * 8 + j] = s[j];
+        ssq[prow * C + v * 8 + j] = q[j];
+      }
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      float a = 0.f, c = 0.f;
+      for (int r = 0; r < rows; ++r)
+        for (int j = 0; j < cg_; ++j) {
+          a += ssum[r * C + g * cg_ + j];
+          c += ssq[r * C + g * cg_ + j];
+        }
+      s_part[g] = make_float2(a, c);
+    }
+    cluster.sync();  // every CTA's partials are visible cluster-wide
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      float a = 0.f, c = 0.f;
+      for (int r = 0; r < cs; ++r) {  // rank order: bit-reproducible
+        const float2 pr = *cluster.map_shared_rank(&s_part[g], r);
+        a += pr.x;
+        c += pr.y;
+      }
+      const float mean = a / count;
+      const float var = fmaxf(c / count - mean * mean, 0.f);
+      s_mean[g] = mean;
+      s_rstd[g] = rsqrtf(var + eps);
+    }
+    cluster.sync();  // peers are done reading s_part (it is rewritten for the next sample); s_mean / s_rstd visible
+    // ---- phase 2: normalise this CTA's pixels (they are still in L2) ----
+    const int64_t items = (p1 - p0) * vecs;
+    auto apply8 = [&](const uint4& u, int v, int64_t p) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        o[2 * j] = f.x;
+        o[2 * j + 1] = f.y;
+      }
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      int g = (v * 8) / cg_;
+      int rem = v * 8 - g * cg_;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = (o[j] - s_mean[g]) * s_rstd[g] * gg[j] + bb[j];
+        if (silu) t = __fdividef(t, 1.f + __expf(-t));
+        o[j] = t;
+        if (++rem == cg_) {
+          rem = 0;
+          ++g;
+        }
+      }
+      *reinterpret_cast<uint4*>(yb + p * ldy + v * 8) =
+          make_uint4(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]), pack_h2(o[4], o[5]), pack_h2(o[6], o[7]));
+    };
+    int64_t it = threadIdx.x;
+    for (; it + 3 * blockDim.x < items; it += 4 * blockDim.x) {
+      uint4 u[4];
+      int vv[4];
+      int64_t pp[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t i2 = it + k * blockDim.x;
+        vv[k] = static_cast<int>(i2 % vecs);
+        pp[k] = p0 + i2 / vecs;
+        u[k] = *reinterpret_cast<const uint4*>(xb + pp[k] * ldx + vv[k] * 8);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) apply8(u[k], vv[k], pp[k]);
+    }
+    for (; it < items; it += blockDim.x) {
+      const int v = static_cast<int>(it % vecs);
+      const int64_t p = p0 + it / vecs;
+      apply8(*reinterpret_cast<const uint4*>(xb + p * ldx + v * 8), v, p);
+    }
+    __syncthreads();  // ssum / ssq / s_mean are rewritten by the next sample
+  }
+}
+
 // chunks per sample: enough blocks to fill the machine (B * nchunks >= ~4 waves) while keeping >= 16 pixels each
 int gn_chunks(int64_t P, int B) {
   int64_t want = (148 * 4 + B - 1) / B;
@@ -204,10 +355,46 @@ int gn_chunks(int64_t P, int B) {
 // workspace: partials [B][nchunks][G] float2 followed by stats [B][G] float2
 size_t gn_workspace_bytes(int B) { return (static_cast<size_t>(B) * GN_MAX_CHUNKS * GN_MAX_GROUPS + B * GN_MAX_GROUPS) * sizeof(float2); }
 
+static bool gn_fused_enabled() {
+  static const int fused_env = [] { const char* e = std::getenv("SDW_GN_FUSED"); return e ? std::atoi(e) : 1; }();
+  return fused_env != 0;
+}
+int groupnorm_launches() { return gn_fused_enabled() ? 1 : 3; }
+
 int groupnorm(const __half* x, int64_t ldx, int B, int64_t P, int C, int G, const float* gamma, const float* beta,
               float eps, int silu, __half* y, int64_t ldy, float2* partial_ws, cudaStream_t stream) {
   SDW_REQUIRE(C % 8 == 0 && C % G == 0 && G <= GN_MAX_GROUPS, "GroupNorm: C % 8, C % G, G <= 64");
   SDW_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, "GroupNorm: row pitch must be a multiple of 8");
+  if (gn_fused_enabled()) {
+    // clusters of 8 CTAs, one sample per cluster at a time; at most 18 clusters (148 SMs) so that the live part of the
+    // tensor (clusters x one sample) stays L2-resident between the two phases
+    const int cs = P >= 8 * 16 ? 8 : (P >= 2 * 16 ? 2 : 1);
+    const int nclusters = std::min(B, 148 / cs);
+    const int vecs = C / 8;
+    const int rows = std::max(1, std::min(std::min(GNF_THREADS / vecs, 16), 6144 / C));
+    const size_t smem = static_cast<size_t>(2) * rows * C * sizeof(float);
+    SDW_REQUIRE(smem <= 48 * 1024, "GroupNorm: channel count too large for the stats pass");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nclusters * cs);
+    cfg.blockDim = dim3(GNF_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    int nattr = 1;
+    if (pdl_enabled()) {
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      nattr = 2;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = nattr;
+    SDW_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel, x, ldx, B, C, G, P, gamma, beta, eps, silu, y, ldy));
+    return 0;
+  }
   const int nchunks = gn_chunks(P, B);
   const int ppc = static_cast<int>((P + nchunks - 1) / nchunks);
   const int vecs = C / 8;
@@ -400,48 +587,66 @@ int softmax_rows(__half* s, int64_t ld, int64_t rows, int n, cudaStream_t stream
 // w layout: [N][Cin][3][3] fp16 (the checkpoint's OIHW), bias fp32.
 // =============================================================================================
 template <int CIN>
-__global__ void __launch_bounds__(1024) conv_in_kernel(const __half* __restrict__ x, int64_t ldx, int B, int H, int W,
+__global__ void __launch_bounds__(512) conv_in_kernel(const __half* __restrict__ x, int64_t ldx, int B, int H, int W,
                                                        const __half* __restrict__ w, const float* __restrict__ bias,
                                                        int N, __half* __restrict__ y, int64_t ldy,
                                                        int pix_per_block) {
-  extern __shared__ float patch[];  // [pix_per_block][9*CIN]
+  // patch[pair][k] = (x of pixel 2*pair, x of pixel 2*pair + 1) for the 9*CIN taps: one 16-byte broadcast read feeds two
+  // packed FMAs (two taps x two pixels); thread = output channel, its 9*CIN weights live in registers
+  constexpr int K = 9 * CIN;
+  extern __shared__ float2 patch2[];  // [pix_per_block / 2][K]
   const int64_t P = static_cast<int64_t>(B) * H * W;
   const int64_t p0 = static_cast<int64_t>(blockIdx.x) * pix_per_block;
   const int np = static_cast<int>(min(static_cast<int64_t>(pix_per_block), P - p0));
-  for (int i = threadIdx.x; i < np * 9 * CIN; i += blockDim.x) {
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < pix_per_block * K; i += blockDim.x) {
     const int c = i % CIN;
     const int tap = (i / CIN) % 9;
-    const int lp = i / (9 * CIN);
+    const int lp = i / K;
     const int64_t p = p0 + lp;
-    const int xw = static_cast<int>(p % W), yh = static_cast<int>((p / W) % H);
-    const int64_t b = p / (static_cast<int64_t>(W) * H);
-    const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
     float v = 0.f;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __half2float(x[((b * H + yy) * W + xx) * ldx + c]);
-    patch[lp * 9 * CIN + tap * CIN + c] = v;
+    if (lp < np) {
+      const int xw = static_cast<int>(p % W), yh = static_cast<int>((p / W) % H);
+      const int64_t b = p / (static_cast<int64_t>(W) * H);
+      const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __half2float(x[((b * H + yy) * W + xx) * ldx + c]);
+    }
+    reinterpret_cast<float*>(patch2)[((lp >> 1) * K + tap * CIN + c) * 2 + (lp & 1)] = v;
   }
   __syncthreads();
   const int n = threadIdx.x;
   if (n >= N) return;
-  float wr[9 * CIN];
+  uint64_t wr[K];
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-    for (int c = 0; c < CIN; ++c) wr[tap * CIN + c] = __half2float(w[(static_cast<int64_t>(n) * CIN + c) * 9 + tap]);
+    for (int c = 0; c < CIN; ++c) {
+      const float wv = __half2float(w[(static_cast<int64_t>(n) * CIN + c) * 9 + tap]);
+      wr[tap * CIN + c] = pk2(wv, wv);
+    }
   const float bn = bias ? bias[n] : 0.f;
-  for (int lp = 0; lp < np; ++lp) {
-    float acc = bn;
+  for (int pr = 0; pr * 2 < np; ++pr) {
+    uint64_t acc = pk2(bn, bn);
+    const float4* row = reinterpret_cast<const float4*>(patch2 + pr * K);
 #pragma unroll
-    for (int k = 0; k < 9 * CIN; ++k) acc = fmaf(patch[lp * 9 * CIN + k], wr[k], acc);
-    y[(p0 + lp) * ldy + n] = __float2half_rn(acc);
+    for (int k = 0; k < K / 2; ++k) {
+      const float4 v = row[k];
+      acc = fma2(pk2(v.x, v.y), wr[2 * k], acc);
+      acc = fma2(pk2(v.z, v.w), wr[2 * k + 1], acc);
+    }
+    float a0, a1;
+    upk2(acc, a0, a1);
+    y[(p0 + 2 * pr) * ldy + n] = __float2half_rn(a0);
+    if (2 * pr + 1 < np) y[(p0 + 2 * pr + 1) * ldy + n] = __float2half_rn(a1);
   }
 }
 
 int conv_in_small(const __half* x, int64_t ldx, int B, int H, int W, int Cin, const __half* w, const float* bias,
                   int N, __half* y, int64_t ldy, cudaStream_t stream) {
   SDW_REQUIRE(Cin == 4, "conv_in: latent channel count must be 4");
-  SDW_REQUIRE(N <= 1024, "conv_in: N <= 1024");
-  const int ppb = 16;
+  SDW_REQUIRE(N <= 512, "conv_in: N <= 512");
+  const int ppb = 64;
   const int64_t P = static_cast<int64_t>(B) * H * W;
   const int threads = (N + 31) / 32 * 32;
   conv_in_kernel<4><<<static_cast<unsigned>((P + ppb - 1) / ppb), threads, ppb * 36 * sizeof(float), stream>>>(
@@ -456,70 +661,118 @@ int conv_in_small(const __half* x, int64_t ldx, int B, int H, int W, int Cin, co
 //   out_f32  : fp32 NHWC [P][NOUT] (UNet eps)          — optional
 //   out_u8   : uint8 NHWC [P][NOUT] = round(clamp(v/2+0.5,0,1)*255) (VAE frame; P:435-438 + numpy_to_pil) — optional
 // =============================================================================================
-template <int NOUT>
+// A block owns a TS x TS pixel tile: its (TS+2)^2 halo is staged once in shared memory (the row-per-warp version
+// re-read every input pixel nine times from L2: 245 us for the UNet's 320->4 conv, ~6 ms for the VAE's 128->3), the
+// weights sit next to it; a warp computes 8 pixels at a time, lanes split the channels, one tap's weights in registers.
+template <int NOUT, int TS>
 __global__ void __launch_bounds__(256) conv_out_kernel(const __half* __restrict__ x, int64_t ldx, int B, int H, int W,
                                                        int C, const __half* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ out_f32,
                                                        uint8_t* __restrict__ out_u8) {
-  extern __shared__ __half ws[];  // [NOUT][9][C]
+  constexpr int HT = TS + 2;
+  extern __shared__ __align__(16) uint8_t co_smem[];
+  __half* halo = reinterpret_cast<__half*>(co_smem);  // [HT*HT][C]
+  __half* ws = halo + HT * HT * C;                     // [NOUT][9][C]
+  const int tiles_x = (W + TS - 1) / TS, tiles_y = (H + TS - 1) / TS;
+  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y;
+  const int64_t b = blockIdx.x / (tiles_x * tiles_y);
+  const int x0 = tx * TS, y0 = ty * TS;
   for (int i = threadIdx.x; i < NOUT * 9 * C; i += blockDim.x) {
     const int c = i % C, tap = (i / C) % 9, n = i / (9 * C);
     ws[i] = w[(static_cast<int64_t>(n) * C + c) * 9 + tap];
   }
+  pdl_wait();
+  pdl_launch_dependents();
+  const int c8n = C / 8;
+  for (int i = threadIdx.x; i < HT * HT * c8n; i += blockDim.x) {
+    const int c8 = i % c8n, hp = i / c8n;
+    const int yy = y0 + hp / HT - 1, xx = x0 + hp % HT - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+      v = *reinterpret_cast<const uint4*>(x + ((b * H + yy) * W + xx) * ldx + c8 * 8);
+    *reinterpret_cast<uint4*>(halo + hp * C + c8 * 8) = v;
+  }
   __syncthreads();
-  const int64_t P = static_cast<int64_t>(B) * H * W;
-  const int lane = threadIdx.x & 31;
-  const int warps = blockDim.x >> 5;
-  for (int64_t p = static_cast<int64_t>(blockIdx.x) * warps + (threadIdx.x >> 5); p < P;
-       p += static_cast<int64_t>(gridDim.x) * warps) {
-    const int xw = static_cast<int>(p % W), yh = static_cast<int>((p / W) % H);
-    const int64_t b = p / (static_cast<int64_t>(W) * H);
-    float acc[NOUT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // group g of warp `warp`: pixels q = (g * 8 + warp) * 8 + j, j < 8 — eight consecutive pixels of one tile row
+  for (int g = 0; g * 64 + warp * 8 < TS * TS; ++g) {
+    const int q0 = (g * 8 + warp) * 8;
+    const int py = q0 / TS, px0 = q0 % TS;
+    float acc[8][NOUT];
 #pragma unroll
-    for (int n = 0; n < NOUT; ++n) acc[n] = 0.f;
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n) acc[j][n] = 0.f;
     for (int tap = 0; tap < 9; ++tap) {
-      const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      const __half* xp = x + ((b * H + yy) * W + xx) * ldx;
+      const __half* hrow = halo + ((py + tap / 3) * HT + px0 + tap % 3) * C;
       for (int c = lane * 2; c < C; c += 64) {
-        const float2 xv = __half22float2(*reinterpret_cast<const __half2*>(xp + c));
+        float2 wv[NOUT];
 #pragma unroll
-        for (int n = 0; n < NOUT; ++n) {
-          const float2 wv = __half22float2(*reinterpret_cast<const __half2*>(&ws[(n * 9 + tap) * C + c]));
-          acc[n] = fmaf(xv.x, wv.x, acc[n]);
-          acc[n] = fmaf(xv.y, wv.y, acc[n]);
+        for (int n = 0; n < NOUT; ++n) wv[n] = __half22float2(*reinterpret_cast<const __half2*>(&ws[(n * 9 + tap) * C + c]));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 xv = __half22float2(*reinterpret_cast<const __half2*>(hrow + j * C + c));
+#pragma unroll
+          for (int n = 0; n < NOUT; ++n) {
+            acc[j][n] = fmaf(xv.x, wv[n].x, acc[j][n]);
+            acc[j][n] = fmaf(xv.y, wv[n].y, acc[j][n]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int n = 0; n < NOUT; ++n) acc[n] = warp_sum(acc[n]);
-    if (lane == 0) {
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int n = 0; n < NOUT; ++n) {
-        const float v = acc[n] + (bias ? bias[n] : 0.f);
-        if (out_f32) out_f32[p * NOUT + n] = v;
-        if (out_u8) {
-          const float q = fminf(fmaxf(v * 0.5f + 0.5f, 0.f), 1.f);
-          out_u8[p * NOUT + n] = static_cast<uint8_t>(rintf(q * 255.f));
+      for (int n = 0; n < NOUT; ++n) acc[j][n] = warp_sum(acc[j][n]);
+    // lane j < 8 writes pixel j
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (lane == j) {
+        const int yy = y0 + py, xx = x0 + px0 + j;
+        if (yy < H && xx < W) {
+          const int64_t p = (b * H + yy) * W + xx;
+#pragma unroll
+          for (int n = 0; n < NOUT; ++n) {
+            const float v = acc[j][n] + (bias ? bias[n] : 0.f);
+            if (out_f32) out_f32[p * NOUT + n] = v;
+            if (out_u8) {
+              const float q = fminf(fmaxf(v * 0.5f + 0.5f, 0.f), 1.f);
+              out_u8[p * NOUT + n] = static_cast<uint8_t>(rintf(q * 255.f));
+            }
+          }
         }
       }
     }
   }
 }
 
+template <int NOUT, int TS>
+static int launch_conv_out(const __half* x, int64_t ldx, int B, int H, int W, int C, const __half* w, const float* bias,
+                           float* out_f32, uint8_t* out_u8, cudaStream_t stream) {
+  const size_t smem = (static_cast<size_t>((TS + 2) * (TS + 2)) + NOUT * 9) * C * sizeof(__half);
+  SDW_REQUIRE(smem <= 227 * 1024, "conv_out: channel count too large for the halo tile");
+  static bool attr_done = false;
+  if (!attr_done) {
+    SDW_CUDA_OK(cudaFuncSetAttribute(conv_out_kernel<NOUT, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  const int64_t blocks = static_cast<int64_t>(B) * ((H + TS - 1) / TS) * ((W + TS - 1) / TS);
+  conv_out_kernel<NOUT, TS><<<static_cast<unsigned>(blocks), 256, smem, stream>>>(x, ldx, B, H, W, C, w, bias, out_f32, out_u8);
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int conv_out_small(const __half* x, int64_t ldx, int B, int H, int W, int C, const __half* w, const float* bias,
                    int nout, float* out_f32, uint8_t* out_u8, cudaStream_t stream) {
   SDW_REQUIRE(nout == 3 || nout == 4, "conv_out: 3 or 4 output channels");
-  SDW_REQUIRE(C % 2 == 0, "conv_out: even channel count");
-  const int64_t P = static_cast<int64_t>(B) * H * W;
-  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((P + 7) / 8, 148 * 8));
-  const size_t smem = static_cast<size_t>(nout) * 9 * C * sizeof(__half);
+  SDW_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "conv_out: 16-byte aligned channel rows");
+  // 16 x 16 tiles when their halo fits comfortably (C <= 128), 8 x 8 otherwise
+  const bool big = C <= 128 && H >= 16 && W >= 16;
   if (nout == 4)
-    conv_out_kernel<4><<<blocks, 256, smem, stream>>>(x, ldx, B, H, W, C, w, bias, out_f32, out_u8);
-  else
-    conv_out_kernel<3><<<blocks, 256, smem, stream>>>(x, ldx, B, H, W, C, w, bias, out_f32, out_u8);
-  SDW_CUDA_OK(cudaGetLastError());
-  return 0;
+    return big ? launch_conv_out<4, 16>(x, ldx, B, H, W, C, w, bias, out_f32, out_u8, stream)
+               : launch_conv_out<4, 8>(x, ldx, B, H, W, C, w, bias, out_f32, out_u8, stream);
+  return big ? launch_conv_out<3, 16>(x, ldx, B, H, W, C, w, bias, out_f32, out_u8, stream)
+             : launch_conv_out<3, 8>(x, ldx, B, H, W, C, w, bias, out_f32, out_u8, stream);
 }
 
 // =============================================================================================
