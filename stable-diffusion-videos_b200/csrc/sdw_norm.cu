@@ -201,8 +201,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
 // launch.  Each CTA sums its pixel slice (same fixed-order arithmetic as gn_partial_det_kernel), the per-CTA partials
 // are exchanged through distributed shared memory and reduced in rank order by every CTA, and the slice is normalised
 // right away — while it is still in L2, because only (clusters in flight) x (one sample) of the tensor is live at a
-// time.  Against the three-kernel version this drops one HBM read of the tensor and two launches
-// (64x64x320, batch 32: 82 us -> see profiles/r01_op_profile_*.txt).
+// time.  It drops one HBM read of the tensor and two launches, but MEASURED SLOWER than the three-kernel version
+// (64x64x320, batch 32: 130 us vs 82 us; VAE 512x512x128: 2.1 ms vs 0.82 ms — 18 clusters of 8 CTAs keep too few
+// loads in flight and 32 samples need two rounds), so it is opt-in: SDW_GN_FUSED=1.  Tests cover both.
 // ---------------------------------------------------------------------------------------------
 static constexpr int GNF_THREADS = 512;
 
@@ -356,7 +357,7 @@ int gn_chunks(int64_t P, int B) {
 size_t gn_workspace_bytes(int B) { return (static_cast<size_t>(B) * GN_MAX_CHUNKS * GN_MAX_GROUPS + B * GN_MAX_GROUPS) * sizeof(float2); }
 
 static bool gn_fused_enabled() {
-  static const int fused_env = [] { const char* e = std::getenv("SDW_GN_FUSED"); return e ? std::atoi(e) : 1; }();
+  static const int fused_env = [] { const char* e = std::getenv("SDW_GN_FUSED"); return e ? std::atoi(e) : 0; }();
   return fused_env != 0;
 }
 int groupnorm_launches() { return gn_fused_enabled() ? 1 : 3; }
@@ -677,9 +678,12 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const __half* __restrict_
   const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y;
   const int64_t b = blockIdx.x / (tiles_x * tiles_y);
   const int x0 = tx * TS, y0 = ty * TS;
+  // OIHW -> [n][tap][c]: walk the SOURCE linearly (coalesced 2-byte loads; the gather form cost one 32-byte sector per
+  // element and, at 23 KB of weights per block, was what bounded this kernel)
   for (int i = threadIdx.x; i < NOUT * 9 * C; i += blockDim.x) {
-    const int c = i % C, tap = (i / C) % 9, n = i / (9 * C);
-    ws[i] = w[(static_cast<int64_t>(n) * C + c) * 9 + tap];
+    const int n = i / (9 * C), rem = i - n * 9 * C;
+    const int c = rem / 9, tap = rem - c * 9;
+    ws[(n * 9 + tap) * C + c] = w[i];
   }
   pdl_wait();
   pdl_launch_dependents();
