@@ -68,9 +68,16 @@ __device__ __forceinline__ float ex2_poly(float t) {
   return __int_as_float(__float_as_int(q) + (__float_as_int(xr) << 23));
 }
 
-template <int DKA, int DVP, int BKV, int ST, int SB, int POLY = 4>  // POLY: every POLY-th exp on the FMA pipe (0 = none)
+// SPLIT = 1 (BKV = 128, one S buffer, two CTAs per SM): S_j is produced and consumed as two 64-column halves with their
+// own full / free barriers.  With a single S buffer the softmax warps used to idle from their last read of S_j until
+// S_{j+1} had been issued (after ALL rows were done) and completed — a third of their stall samples in
+// profiles/r01_ncu_attn_lazy.md.  Now S_{j+1}[0] is issued as soon as every row has read S_j[0], i.e. half a tile
+// before it is needed, and the softmax treats each half as its own online-softmax step (P of half 0 is rescaled in
+// shared memory in the rare case half 1 raises the row maximum past the lazy threshold).
+template <int DKA, int DVP, int BKV, int ST, int SB, int POLY = 4, int SPLIT = 0>  // POLY: every POLY-th exp on the FMA pipe (0 = none)
 __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::NCTA)
     attn_fwd_kernel(const __grid_constant__ AttnKParams p) {
+  static_assert(!SPLIT || (SB == 1 && BKV == 128 && DKA == 1), "the split-S pipeline is the BKV = 128, single-buffer variant");
   using Cfg = AttnCfg<DKA, DVP, BKV, ST, SB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -85,7 +92,8 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::N
   uint64_t* s_full = kv_empty + ST;  // [2]
   uint64_t* p_ready = s_full + 2;
   uint64_t* pv_done = p_ready + 1;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint64_t* s_free = pv_done + 1;  // [2]  (SPLIT)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * ATT_BQ;
@@ -105,6 +113,8 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::N
     mbar_init(&s_full[1], 1);
     mbar_init(p_ready, 128);
     mbar_init(pv_done, 1);
+    mbar_init(&s_free[0], 128);
+    mbar_init(&s_free[1], 128);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -157,15 +167,44 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::N
         }
         umma_commit(&s_full[j % SB]);
       };
+      constexpr uint32_t idesc_h = make_idesc_f16(ATT_BQ, 64);
+      auto issue_half = [&](int j, int h) {  // S_j[:, 64h .. 64h+63] = Q K_j[64h .. 64h+63]^T
+        const int s = j % ST;
+        if (h == 0) {
+          mbar_wait(&kv_full[s], (j / ST) & 1);
+          tc_fence_after();
+        }
+        const uint32_t k_addr = smem_u32(k_smem + s * Cfg::K_STAGE) + h * (64 * 128);
+        for (int ks = 0; ks < p.dk_steps; ++ks) {
+          const uint64_t da = make_desc_k_sw128(q_addr + (ks & 3) * 32);
+          const uint64_t db = make_desc_k_sw128(k_addr + (ks & 3) * 32);
+          umma_f16_ss(tmem + h * 64, da, db, idesc_h, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[h]);
+      };
       mbar_wait(q_full, 0);
       tc_fence_after();
-      issue_s(0);
-      if (SB == 2 && ntiles > 1) issue_s(1);
+      if (SPLIT) {
+        issue_half(0, 0);
+        issue_half(0, 1);
+      } else {
+        issue_s(0);
+        if (SB == 2 && ntiles > 1) issue_s(1);
+      }
       for (int j = 0; j < ntiles; ++j) {
+        if (SPLIT && j + 1 < ntiles) {
+          // each half of S_{j+1} goes out as soon as every row has read that half of S_j
+          mbar_wait(&s_free[0], j & 1);
+          tc_fence_after();
+          issue_half(j + 1, 0);
+          mbar_wait(&s_free[1], j & 1);
+          tc_fence_after();
+          issue_half(j + 1, 1);
+        }
         mbar_wait(p_ready, j & 1);
         tc_fence_after();
         // single S buffer: the softmax has consumed S_j (p_ready), so S_{j+1} goes first and overlaps PV_j
-        if (SB == 1 && j + 1 < ntiles) issue_s(j + 1);
+        if (!SPLIT && SB == 1 && j + 1 < ntiles) issue_s(j + 1);
         const int s = j % ST;
         const uint32_t v_addr = smem_u32(v_smem + s * Cfg::V_STAGE);
 #pragma unroll
@@ -199,6 +238,143 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::N
     //         — warp-uniformly — whenever any row's tile max exceeds its reference by more than 2^LAZY_LOG2
     //         (S_j is still intact in TMEM, so the tile is simply re-read).
     constexpr float LAZY_LOG2 = 8.f;
+    if constexpr (SPLIT != 0) {
+      for (int j = 0; j < ntiles; ++j) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&s_full[h], j & 1);
+          tc_fence_after();
+          const uint32_t t_s = tmem + lane_base + h * 64;
+          const int c0 = j * BKV + h * 64;
+          const bool ragged = c0 + 64 > p.Nk;
+          bool need_slow = (j == 0 && h == 0) || ragged;
+          float alpha = 1.f;
+          uint32_t pkh[32];  // P of this row and half, packed fp16 pairs
+          if (!need_slow) {
+            // ---------------- fast path: reference max, 32-column chunks pipelined against the MUFU work ----------------
+            const float mb = m_run * sl2;
+            const uint64_t sl2_2 = pk2(sl2, sl2), nmb_2 = pk2(-mb, -mb);
+            uint64_t sm2[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
+            float mx[2] = {-INFINITY, -INFINITY};
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32(t_s, va);
+            tmem_ld_wait();
+            tmem_ld_32x32(t_s + 32, vb);  // in flight while chunk 0 is exponentiated
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t(&cur)[32] = c ? vb : va;
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float x0 = __uint_as_float(cur[i]), x1 = __uint_as_float(cur[i + 1]);
+                mx[0] = fmaxf(mx[0], x0);
+                mx[1] = fmaxf(mx[1], x1);
+                float t0, t1;
+                upk2(fma2(pk2(x0, x1), sl2_2, nmb_2), t0, t1);
+                const float e0 = ex2f(t0), e1 = ex2f(t1);
+                sm2[(i >> 1) & 1] = add2(sm2[(i >> 1) & 1], pk2(e0, e1));
+                pkh[c * 16 + (i >> 1)] = pack_h2(e0, e1);
+              }
+              if (c == 0) tmem_ld_wait();
+            }
+            const float m_t = fmaxf(mx[0], mx[1]);
+            need_slow = __any_sync(0xffffffffu, (m_t - m_run) * sl2 > LAZY_LOG2);
+            if (!need_slow) {
+              float s0, s1, s2, s3;
+              upk2(sm2[0], s0, s1);
+              upk2(sm2[1], s2, s3);
+              l_run += (s0 + s1) + (s2 + s3);
+            }
+          }
+          if (need_slow) {
+            // ---------------- slow path: exact online softmax on this half (S is still intact in TMEM) ----------------
+            float v[64];
+            {
+              uint32_t vu[2][32];
+              tmem_ld_32x32(t_s, vu[0]);
+              tmem_ld_32x32(t_s + 32, vu[1]);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(vu[i / 32][i % 32]);
+            }
+            if (ragged) {
+#pragma unroll
+              for (int i = 0; i < 64; ++i)
+                if (c0 + i >= p.Nk) v[i] = -INFINITY;
+            }
+            float mx[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+            for (int i = 4; i < 64; ++i) mx[i & 3] = fmaxf(mx[i & 3], v[i]);
+            const float m_t = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+            const float m_new = fmaxf(m_run, m_t);  // finite: half 0 of tile 0 always holds a valid key
+            alpha = ex2f((m_run - m_new) * sl2);
+            const float mb = m_new * sl2;
+            const uint64_t sl2_2 = pk2(sl2, sl2), nmb_2 = pk2(-mb, -mb);
+            uint64_t sm2[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
+#pragma unroll
+            for (int i = 0; i < 64; i += 2) {
+              float t0, t1;
+              upk2(fma2(pk2(v[i], v[i + 1]), sl2_2, nmb_2), t0, t1);
+              const float e0 = ex2f(t0), e1 = ex2f(t1);
+              sm2[(i >> 1) & 1] = add2(sm2[(i >> 1) & 1], pk2(e0, e1));
+              pkh[i >> 1] = pack_h2(e0, e1);
+            }
+            float s0, s1, s2, s3;
+            upk2(sm2[0], s0, s1);
+            upk2(sm2[1], s2, s3);
+            l_run = fmaf(l_run, alpha, (s0 + s1) + (s2 + s3));
+            m_run = m_new;
+          }
+          // every tcgen05.ld of this half has completed: the MMA warp may overwrite it with S_{j+1}
+          tc_fence_before();
+          mbar_arrive(&s_free[h]);
+          if (h == 0 && j > 0) {
+            // P smem and the O accumulator are free once PV_{j-1} has completed
+            mbar_wait(pv_done, (j - 1) & 1);
+            tc_fence_after();
+          }
+          if (need_slow && __any_sync(0xffffffffu, alpha != 1.f)) {
+            if (j > 0) {
+#pragma unroll
+              for (int c = 0; c < DVP / 16; ++c) {
+                uint32_t o[16];
+                tmem_ld_32x16(t_o + c * 16, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st_32x16(t_o + c * 16, o);
+              }
+              tmem_st_wait();
+            }
+            if (h == 1) {
+              // half 0 of this tile was exponentiated against the old maximum: bring it to the new one
+              const __half2 a2 = __float2half2_rn(alpha);
+#pragma unroll
+              for (int c8 = 0; c8 < 8; ++c8) {
+                uint4* q = reinterpret_cast<uint4*>(p_row + ((c8 ^ sw) << 4));
+                uint4 u = *q;
+                __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hh[i] = __hmul2(hh[i], a2);
+                *q = u;
+              }
+            }
+          }
+          // P half -> shared memory, K-major SWIZZLE_128B: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            uint4 u;
+            u.x = pkh[c8 * 4 + 0];
+            u.y = pkh[c8 * 4 + 1];
+            u.z = pkh[c8 * 4 + 2];
+            u.w = pkh[c8 * 4 + 3];
+            *reinterpret_cast<uint4*>(p_row + h * (ATT_BQ * 128) + ((c8 ^ sw) << 4)) = u;
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(p_ready);
+      }
+    } else {
     uint32_t pk[BKV / 2];  // P_j of this row, packed fp16 pairs
 
     for (int j = 0; j < ntiles; ++j) {
@@ -319,6 +495,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::N
       tc_fence_before();
       mbar_arrive(p_ready);
     }
+    }  // !SPLIT
     // ---- epilogue: O / l -> fp16 ------------------------------------------------------------
     mbar_wait(pv_done, (ntiles - 1) & 1);
     tc_fence_after();
@@ -373,9 +550,9 @@ struct AttnLaunchImpl {
   int variant;
 };
 
-template <int DKA, int DVP, int BKV, int ST, int SB, int POLY = 4>
+template <int DKA, int DVP, int BKV, int ST, int SB, int POLY = 4, int SPLIT = 0>
 static int attn_set_attr() {
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<DKA, DVP, BKV, ST, SB, POLY>,
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<DKA, DVP, BKV, ST, SB, POLY, SPLIT>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<DKA, DVP, BKV, ST, SB>::SMEM));
   return 0;
 }
@@ -393,6 +570,10 @@ static int attn_init() {
   if (int e = attn_set_attr<1, 48, 128, 2, 1, 0>()) return e;
   if (int e = attn_set_attr<1, 48, 128, 2, 1, 8>()) return e;
   if (int e = attn_set_attr<2, 80, 64, 2, 1, 0>()) return e;
+  if (int e = attn_set_attr<1, 16, 128, 2, 1, 0, 1>()) return e;
+  if (int e = attn_set_attr<1, 32, 128, 2, 1, 0, 1>()) return e;
+  if (int e = attn_set_attr<1, 48, 128, 2, 1, 0, 1>()) return e;
+  if (int e = attn_set_attr<1, 64, 128, 2, 1, 0, 1>()) return e;
   g_attn_init = true;
   return 0;
 }
@@ -400,6 +581,14 @@ static int attn_init() {
 bool attn_supported(int d) { return d % 8 == 0 && d >= 8 && d <= 160; }
 
 static int variant_for(int d) {
+  // split-S pipeline (variants 10-13): correct, but measured 5 % SLOWER than the whole-tile variants (self-attention
+  // 64x64, d = 40, batch 32: 1838 vs 1746 us, profiles/r01_attn_bench_split_s.txt) — the softmax warps' S waits were a
+  // symptom, the MUFU + TMEM-read floor is what binds — so it is opt-in: SDW_ATTN_SPLIT=1
+  static const bool split = [] { const char* e = std::getenv("SDW_ATTN_SPLIT"); return e && e[0] == '1'; }();
+  static const bool legacy = [] {
+    return std::getenv("SDW_ATTN_BKV64") != nullptr || std::getenv("SDW_ATTN_POLY") != nullptr;
+  }();
+  if (split && !legacy && d <= 64) return d <= 16 ? 10 : (d <= 32 ? 11 : (d <= 48 ? 12 : 13));
   if (d <= 16) return 0;
   if (d <= 32) return 1;
   static const bool bkv64 = [] { const char* e = std::getenv("SDW_ATTN_BKV64"); return e && e[0] == '1'; }();
@@ -427,7 +616,7 @@ int plan_attention(const AttnDesc& a, AttnLaunch* L) {
   std::memset(I, 0, sizeof(*I));
   I->variant = variant_for(a.d);
   const int bkv = (I->variant == 5 || I->variant == 6 || I->variant == 9) ? 64 : 128;
-  const int dvp_tab[10] = {16, 32, 48, 64, 80, 160, 48, 48, 48, 80};
+  const int dvp_tab[14] = {16, 32, 48, 64, 80, 160, 48, 48, 48, 80, 16, 32, 48, 64};
   const int dvp = dvp_tab[I->variant];
   AttnKParams& p = I->p;
   p.Nq = a.Nq; p.Nk = a.Nk; p.d = a.d; p.heads = a.heads;
@@ -476,6 +665,10 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     case 7: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 2, 1, 0>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 2, 1>::SMEM, stream, I->p)); break;
     case 8: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 2, 1, 8>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 2, 1>::SMEM, stream, I->p)); break;
     case 9: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<2, 80, 64, 2, 1, 0>, I->grid, dim3(ATT_THREADS), AttnCfg<2, 80, 64, 2, 1>::SMEM, stream, I->p)); break;
+    case 10: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 16, 128, 2, 1, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 16, 128, 2, 1>::SMEM, stream, I->p)); break;
+    case 11: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 32, 128, 2, 1, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 32, 128, 2, 1>::SMEM, stream, I->p)); break;
+    case 12: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 2, 1, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 2, 1>::SMEM, stream, I->p)); break;
+    case 13: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 64, 128, 2, 1, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 64, 128, 2, 1>::SMEM, stream, I->p)); break;
     default: set_error("bad attention variant"); return 1;
   }
   SDW_CUDA_OK(cudaGetLastError());

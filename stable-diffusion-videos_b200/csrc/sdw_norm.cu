@@ -675,26 +675,65 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const __half* __restrict_
   __half* halo = reinterpret_cast<__half*>(co_smem);  // [HT*HT][C]
   __half* ws = halo + HT * HT * C;                     // [NOUT][9][C]
   const int tiles_x = (W + TS - 1) / TS, tiles_y = (H + TS - 1) / TS;
-  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y;
-  const int64_t b = blockIdx.x / (tiles_x * tiles_y);
-  const int x0 = tx * TS, y0 = ty * TS;
-  // OIHW -> [n][tap][c]: walk the SOURCE linearly (coalesced 2-byte loads; the gather form cost one 32-byte sector per
-  // element and, at 23 KB of weights per block, was what bounded this kernel)
-  for (int i = threadIdx.x; i < NOUT * 9 * C; i += blockDim.x) {
-    const int n = i / (9 * C), rem = i - n * 9 * C;
-    const int c = rem / 9, tap = rem - c * 9;
-    ws[(n * 9 + tap) * C + c] = w[i];
+  const int ntiles = B * tiles_x * tiles_y;
+  // OIHW -> [n][tap][c], once per (persistent) block: 16-byte loads along the source, eight in flight per thread
+  {
+    const int nvec = NOUT * 9 * C / 8;  // C % 8 == 0
+    for (int v0 = threadIdx.x; v0 < nvec; v0 += 4 * blockDim.x) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int v = v0 + k * blockDim.x;
+        u[k] = v < nvec ? __ldg(reinterpret_cast<const uint4*>(w) + v) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int v = v0 + k * blockDim.x;
+        if (v >= nvec) continue;
+        const __half* h = reinterpret_cast<const __half*>(&u[k]);
+        int i = v * 8;
+        int n = i / (9 * C), rem = i - n * 9 * C;
+        int c = rem / 9, tap = rem - c * 9;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          ws[(n * 9 + tap) * C + c] = h[e];
+          if (++tap == 9) {
+            tap = 0;
+            if (++c == C) {
+              c = 0;
+              ++n;
+            }
+          }
+        }
+      }
+    }
   }
   pdl_wait();
   pdl_launch_dependents();
   const int c8n = C / 8;
-  for (int i = threadIdx.x; i < HT * HT * c8n; i += blockDim.x) {
-    const int c8 = i % c8n, hp = i / c8n;
-    const int yy = y0 + hp / HT - 1, xx = x0 + hp % HT - 1;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-      v = *reinterpret_cast<const uint4*>(x + ((b * H + yy) * W + xx) * ldx + c8 * 8);
-    *reinterpret_cast<uint4*>(halo + hp * C + c8 * 8) = v;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y;
+  const int64_t b = tile / (tiles_x * tiles_y);
+  const int x0 = tx * TS, y0 = ty * TS;
+  __syncthreads();  // the previous tile's halo has been consumed (and the weights are staged)
+  for (int i0 = threadIdx.x; i0 < HT * HT * c8n; i0 += 4 * blockDim.x) {
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * blockDim.x;
+      v[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < HT * HT * c8n) {
+        const int c8 = i % c8n, hp = i / c8n;
+        const int yy = y0 + hp / HT - 1, xx = x0 + hp % HT - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+          v[k] = *reinterpret_cast<const uint4*>(x + ((b * H + yy) * W + xx) * ldx + c8 * 8);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * blockDim.x;
+      if (i < HT * HT * c8n) *reinterpret_cast<uint4*>(halo + (i / c8n) * C + (i % c8n) * 8) = v[k];
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -748,6 +787,7 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const __half* __restrict_
       }
     }
   }
+  }  // tile loop
 }
 
 template <int NOUT, int TS>
@@ -760,7 +800,8 @@ static int launch_conv_out(const __half* x, int64_t ldx, int B, int H, int W, in
     SDW_CUDA_OK(cudaFuncSetAttribute(conv_out_kernel<NOUT, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  const int64_t blocks = static_cast<int64_t>(B) * ((H + TS - 1) / TS) * ((W + TS - 1) / TS);
+  const int64_t tiles = static_cast<int64_t>(B) * ((H + TS - 1) / TS) * ((W + TS - 1) / TS);
+  const int64_t blocks = std::min<int64_t>(tiles, 148 * 2);  // persistent: the weights are staged once per block
   conv_out_kernel<NOUT, TS><<<static_cast<unsigned>(blocks), 256, smem, stream>>>(x, ldx, B, H, W, C, w, bias, out_f32, out_u8);
   SDW_CUDA_OK(cudaGetLastError());
   return 0;

@@ -56,3 +56,29 @@ def test_flash_attention_peaky_scores():
     out, ref = _run(1, 4, 512, 512, 40, seed=3, scale=4.0)
     assert torch.isfinite(out).all()
     assert float((out - ref).abs().max()) <= 2.0 ** -7 * float(ref.abs().max()) + 2e-3
+
+
+def test_attention_split_s_variant_subprocess():
+    """the opt-in split-S pipeline (SDW_ATTN_SPLIT=1) against torch, incl. a ragged key count and a max that keeps rising"""
+    import os
+    import subprocess
+    import sys
+    code = ("import torch, ctypes as C\n"
+            "from stable_diffusion_videos_b200 import _native as n\n"
+            "torch.manual_seed(0)\n"
+            "for (B,h,Nq,Nk,d) in [(2,8,1024,1024,40),(1,4,300,77,40),(1,2,256,700,64),(1,2,128,1000,32)]:\n"
+            "    Cc=h*d; q=torch.randn(B,Nq,Cc,device='cuda').half(); k=torch.randn(B,Nk,Cc,device='cuda').half()\n"
+            "    k = k * torch.linspace(0.2, 3.0, Nk, device='cuda')[None,:,None].half()\n"
+            "    v=torch.randn(B,Nk,Cc,device='cuda').half(); ld=(Nk+7)//8*8\n"
+            "    vt=torch.zeros(B,h,d,ld,device='cuda',dtype=torch.float16); vt[...,:Nk]=v.reshape(B,Nk,h,d).permute(0,2,3,1)\n"
+            "    out=torch.empty(B,Nq,Cc,device='cuda',dtype=torch.float16)\n"
+            "    n.check(n.lib().sdw_attention(n.ptr(q),C.c_int64(Cc),n.ptr(k),C.c_int64(Cc),n.ptr(vt),C.c_int64(ld),B,Nq,Nk,h,d,n.ptr(out),C.c_int64(Cc),n.stream_ptr()))\n"
+            "    torch.cuda.synchronize()\n"
+            "    qf=q.float().reshape(B,Nq,h,d).permute(0,2,1,3); kf=k.float().reshape(B,Nk,h,d).permute(0,2,1,3); vf=v.float().reshape(B,Nk,h,d).permute(0,2,1,3)\n"
+            "    ref=(torch.softmax(qf@kf.transpose(-1,-2)*d**-0.5,-1)@vf).permute(0,2,1,3).reshape(B,Nq,Cc)\n"
+            "    err=(out.float()-ref).abs().max().item(); assert err <= 2**-8*ref.abs().max().item()+1e-3, (err, B,h,Nq,Nk,d)\n"
+            "print('ok')\n")
+    env = dict(os.environ, SDW_ATTN_SPLIT="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
