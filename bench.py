@@ -22,8 +22,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, from profiles/r01_ncu_gemm_conv_*.csv (batch 16)
-DOMINANT_KERNEL_DRAM_BYTES = 49.5e6
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed ncu --set full capture
+# profiles/r01_ncu_gemm2_conv_tapreuse_raw.csv (same shape, batch 60)
+DOMINANT_KERNEL_DRAM_BYTES = 452.1e6
 FLOP_PER_FRAME = {"sd14": 2 * 51 * 0.8033e12 + 2.5145e12}  # SURVEY.md §8d algorithmic FLOPs (84.45 T)
 UNET_FLOP_B1 = 0.8033e12
 VAE_FLOP = 2.5145e12
@@ -115,7 +116,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--frames-per-call", type=int, default=int(os.environ.get("SDW_BENCH_F", "16")))
+    ap.add_argument("--frames-per-call", type=int, default=int(os.environ.get("SDW_BENCH_F", "30")))
     ap.add_argument("--inference-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
@@ -275,9 +276,36 @@ def main():
             k1.record()
             torch.cuda.synchronize()
             tot += k0.elapsed_time(k1)
-        kern = {"name": "gemm2_tc_kernel<160> conv3x3 64x64 320->320 bias+residual", "batch": Bn,
+        kern = {"name": "gemm2_tc_kernel<160, tap-reuse> conv3x3 64x64 320->320 bias+residual", "batch": Bn,
                 "flop_per_launch": 2.0 * Bn * 64 * 64 * 320 * 2880, "us_per_launch": tot / reps * 1e3}
-        del xk, wk, rk, ok, flush
+        del xk, wk, rk, ok
+        # the heaviest single launch of the step: self-attention at the 64x64 level (8 heads x 40), same timing method
+        Cc, Nt = 320, 4096
+        qa = torch.randn(Bn, Nt, Cc, device=dev).half()
+        ka = torch.randn(Bn, Nt, Cc, device=dev).half()
+        vta = torch.randn(Bn, 8, 40, Nt, device=dev).half()
+        oa = torch.empty(Bn, Nt, Cc, device=dev, dtype=torch.float16)
+
+        def attn():
+            _native.check(_native.lib().sdw_attention(_native.ptr(qa), C.c_int64(Cc), _native.ptr(ka), C.c_int64(Cc),
+                                                      _native.ptr(vta), C.c_int64(Nt), Bn, Nt, Nt, 8, 40, _native.ptr(oa),
+                                                      C.c_int64(Cc), _native.stream_ptr()))
+        for _ in range(2):
+            attn()
+        torch.cuda.synchronize()
+        tot_a = 0.0
+        for _ in range(5):
+            flush.zero_()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            attn()
+            k1.record()
+            torch.cuda.synchronize()
+            tot_a += k0.elapsed_time(k1)
+        attn_us = tot_a / 5 * 1e3
+        attn_flop = 4.0 * Bn * 8 * Nt * Nt * 40
+        attn_exps = float(Bn) * 8 * Nt * Nt
+        del qa, ka, vta, oa, flush
 
     if rank != 0:
         return
@@ -302,7 +330,13 @@ def main():
                              "peak; traffic = dram read+write bytes per launch from the committed ncu --set full "
                              "capture (profiles/), at that capture's batch",
                      "whole_sampler": {"achieved": achieved_tf, "peak": peak_tf, "frac": achieved_tf / peak_tf,
-                                       "note": "frames x 84.45 TFLOP / time / gpus vs sustained peak"}},
+                                       "note": "frames x 84.45 TFLOP / time / gpus vs sustained peak"},
+                     "attention": {"kernel": "attn_fwd_kernel self-attention 64x64, 8 heads x 40", "kernel_batch": Bn,
+                                   "us_per_launch": attn_us, "achieved": attn_flop / (attn_us * 1e-6) / 1e12,
+                                   "peak": burst_tf, "unit": "TFLOP/s", "frac": attn_flop / (attn_us * 1e-6) / 1e12 / burst_tf,
+                                   "mufu_floor_us": attn_exps / (16.0 * 148 * 1.85e9) * 1e6,
+                                   "note": "heaviest single launch (~24 % of the step); bound by one MUFU.EX2 per score "
+                                           "(16/clk/SM) and the fp32 TMEM read of S, not by the tensor pipe"}},
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches_per_call * K,
         "clocks": clk,

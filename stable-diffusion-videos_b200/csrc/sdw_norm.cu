@@ -173,26 +173,39 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
     w.w = pack_h2(o[6], o[7]);
     *reinterpret_cast<uint4*>(yb + p * ldy + v * 8) = w;
   };
-  // 4 independent 16-byte loads in flight per thread
-  int64_t it = threadIdx.x;
-  for (; it + 3 * blockDim.x < items; it += 4 * blockDim.x) {
+  // 4 independent 16-byte loads in flight per thread.  (pixel, vector) of item `it` advance incrementally: the 64-bit
+  // div / mod per item this loop used to do cost more issue slots than the normalisation itself
+  const int dv = static_cast<int>(blockDim.x) % vecs, dp = static_cast<int>(blockDim.x) / vecs;
+  int v = static_cast<int>(threadIdx.x) % vecs;
+  int64_t pl = static_cast<int>(threadIdx.x) / vecs;  // pixel relative to p0
+  const int64_t npix = p1 - p0;
+  auto advance = [&](int& vv, int64_t& pp) {
+    vv += dv;
+    pp += dp;
+    if (vv >= vecs) {
+      vv -= vecs;
+      ++pp;
+    }
+  };
+  while (true) {
     uint4 u[4];
     int vv[4];
     int64_t pp[4];
+    int n = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int64_t i2 = it + k * blockDim.x;
-      vv[k] = static_cast<int>(i2 % vecs);
-      pp[k] = p0 + i2 / vecs;
-      u[k] = *reinterpret_cast<const uint4*>(xb + pp[k] * ldx + vv[k] * 8);
+      vv[k] = v;
+      pp[k] = pl;
+      if (pl < npix) {
+        u[k] = *reinterpret_cast<const uint4*>(xb + (p0 + pl) * ldx + v * 8);
+        n = k + 1;
+      }
+      advance(v, pl);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) apply8(u[k], vv[k], pp[k]);
-  }
-  for (; it < items; it += blockDim.x) {
-    const int v = static_cast<int>(it % vecs);
-    const int64_t p = p0 + it / vecs;
-    apply8(*reinterpret_cast<const uint4*>(xb + p * ldx + v * 8), v, p);
+    for (int k = 0; k < 4; ++k)
+      if (k < n) apply8(u[k], vv[k], p0 + pp[k]);
+    if (n < 4) break;
   }
 }
 
@@ -346,7 +359,7 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const __half* __r
 
 // chunks per sample: enough blocks to fill the machine (B * nchunks >= ~4 waves) while keeping >= 16 pixels each
 int gn_chunks(int64_t P, int B) {
-  int64_t want = (148 * 4 + B - 1) / B;
+  int64_t want = (148 * 7 + B - 1) / B;  // 7 blocks of the stats kernel fit an SM (30 KB of shared memory each)
   int64_t n = std::min<int64_t>(want, P / 16);
   if (n < 1) n = 1;
   if (n > GN_MAX_CHUNKS) n = GN_MAX_CHUNKS;
@@ -407,8 +420,10 @@ int groupnorm(const __half* x, int64_t ldx, int B, int64_t P, int C, int G, cons
   const int BG = B * G;
   SDW_CUDA_OK(launch_pdl(gn_finalize_kernel, dim3((BG + 7) / 8), dim3(256), 0, stream, partial_ws, nchunks, G, BG,
                          static_cast<float>(P) * (C / G), eps, stats));
-  int ppb = static_cast<int>(std::max<int64_t>(1, 4096 / C));  // ~4K elements per block pass
-  ppb *= 8;
+  // one full wave: 148 SMs x 8 resident 256-thread blocks, split evenly over the samples (the former fixed ~100-pixel
+  // tiles gave 1376 blocks = 1.16 waves at 64x64x320, batch 32: the second wave ran 16 % full)
+  const int64_t per_sample = std::max<int64_t>(1, (148 * 8) / B);
+  const int ppb = static_cast<int>(std::max<int64_t>(1, (P + per_sample - 1) / per_sample));
   const unsigned tiles = static_cast<unsigned>((P + ppb - 1) / ppb);
   SDW_CUDA_OK(launch_pdl(gn_apply_kernel, dim3(tiles, B), dim3(256), 0, stream, x, ldx, C, G, P, stats, gamma, beta, silu,
                          y, ldy, ppb));
