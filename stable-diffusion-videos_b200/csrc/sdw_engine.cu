@@ -105,6 +105,44 @@ struct Engine {
     t.p = static_cast<__half*>(alloc(static_cast<size_t>(B) * H * W * C * 2));
     return t;
   }
+  // ---- activation liveness.  The launch plan is a fixed sequence on one stream, so lifetimes are known at build time:
+  //   * block temporaries (everything a ResBlock / transformer block allocates besides its output) live in a SCRATCH
+  //     stack that is rewound when the block has been emitted (Scope);
+  //   * the VAE decoder is a pure chain, its block outputs alternate between two PING-PONG slots;
+  //   * weights, tables, skip-concat buffers, UNet block outputs and I/O stay in the persistent bump region.
+  // Layout: [persistent | ping | pong | scratch]; the dry run measures the four sizes, the bound run places the bases.
+  size_t soff = 0, speak = 0, pers_bytes = 0, pp_peak[2] = {0, 0};
+  int pp_count = 0;
+  uint8_t* sbase = nullptr;
+  uint8_t* pp_base[2] = {nullptr, nullptr};
+  void* salloc(size_t bytes, size_t align = 1024) {
+    soff = (soff + align - 1) / align * align;
+    void* p = dry ? nullptr : sbase + soff;
+    soff += bytes;
+    speak = std::max(speak, soff);
+    return p;
+  }
+  T tmp(int B, int H, int W, int C) {
+    T t;
+    t.B = B; t.H = H; t.W = W; t.C = C; t.ld = C;
+    t.p = static_cast<__half*>(salloc(static_cast<size_t>(B) * H * W * C * 2));
+    return t;
+  }
+  T pingpong(int B, int H, int W, int C) {  // the tensor allocated two calls ago is dead by construction (pure chain)
+    const int slot = pp_count++ & 1;
+    const size_t bytes = static_cast<size_t>(B) * H * W * C * 2;
+    pp_peak[slot] = std::max(pp_peak[slot], bytes);
+    T t;
+    t.B = B; t.H = H; t.W = W; t.C = C; t.ld = C;
+    t.p = dry ? nullptr : reinterpret_cast<__half*>(pp_base[slot]);
+    return t;
+  }
+  struct Scope {
+    Engine* e;
+    size_t mark;
+    explicit Scope(Engine* eng) : e(eng), mark(eng->soff) {}
+    ~Scope() { e->soff = mark; }
+  };
   static T slice(const T& big, int c0, int C) {
     T t = big;
     t.p = big.p ? big.p + c0 : nullptr;
@@ -273,9 +311,10 @@ struct Engine {
 
   // ---- model pieces ----------------------------------------------------------
   int resnet(const std::string& pre, const T& x, int cout, bool has_temb, float eps, const T& out) {
-    T n1 = act(x.B, x.H, x.W, x.C);
+    Scope scope(this);
+    T n1 = tmp(x.B, x.H, x.W, x.C);
     gn(x, pre + ".norm1", eps, 1, n1);
-    T h1 = act(x.B, x.H, x.W, cout);
+    T h1 = tmp(x.B, x.H, x.W, cout);
     const __half* w1 = w_packed(pre + ".conv1.weight", cout, x.C, 3);
     const float* b1 = vec(pre + ".conv1.bias", cout);
     const float* table = nullptr;
@@ -289,7 +328,7 @@ struct Engine {
       table = tp.table;
     }
     if (int e = conv(n1, w1, b1, cout, 1, h1, nullptr, table)) return e;
-    T n2 = act(x.B, x.H, x.W, cout);
+    T n2 = tmp(x.B, x.H, x.W, cout);
     gn(h1, pre + ".norm2", eps, 1, n2);
     const __half* w2 = w_packed(pre + ".conv2.weight", cout, cout, 3);
     const float* b2 = vec(pre + ".conv2.bias", cout);
@@ -297,7 +336,7 @@ struct Engine {
     if (x.C != cout) {
       const __half* ws = w_packed(pre + ".conv_shortcut.weight", cout, x.C, 1);
       const float* bs = vec(pre + ".conv_shortcut.bias", cout);
-      T sc = act(x.B, x.H, x.W, cout);
+      T sc = tmp(x.B, x.H, x.W, cout);
       if (int e = conv(x, ws, bs, cout, 0, sc)) return e;
       res = sc;
     }
@@ -309,12 +348,13 @@ struct Engine {
   int transformer(const std::string& pre, const T& x, int heads, const T& out) {
     const int C = x.C, d = C / heads, Bq = x.B, Nq = x.H * x.W;
     const int tokens = cfg.ctx_tokens, D = cfg.cross_attention_dim;
-    T g0 = act(x.B, x.H, x.W, C);
+    Scope scope(this);
+    T g0 = tmp(x.B, x.H, x.W, C);
     gn(x, pre + ".norm", 1e-6f, 0, g0);
-    T hA = act(x.B, x.H, x.W, C);
+    T hA = tmp(x.B, x.H, x.W, C);
     if (int e = conv(g0, w_packed(pre + ".proj_in.weight", C, C, 1), vec(pre + ".proj_in.bias", C), C, 0, hA)) return e;
     const std::string tb = pre + ".transformer_blocks.0";
-    T t1 = act(x.B, x.H, x.W, C);
+    T t1 = tmp(x.B, x.H, x.W, C);
     // --- self attention
     ln(hA, tb + ".norm1", t1);
     __half* wqkv = static_cast<__half*>(alloc(static_cast<size_t>(3) * C * ((C + 63) / 64 * 64) * 2));
@@ -322,9 +362,9 @@ struct Engine {
     w_packed(tb + ".attn1.to_q.weight", C, C, 1, 0, wqkv, true);
     w_packed(tb + ".attn1.to_k.weight", C, C, 1, 0, wqkv ? wqkv + static_cast<size_t>(C) * cp : nullptr, true);
     w_packed(tb + ".attn1.to_v.weight", C, C, 1, 0, wqkv ? wqkv + static_cast<size_t>(2) * C * cp : nullptr, true);
-    T qk = act(x.B, x.H, x.W, 2 * C);
+    T qk = tmp(x.B, x.H, x.W, 2 * C);
     const int64_t vt_ld = (Nq + 7) / 8 * 8;
-    __half* vt = static_cast<__half*>(alloc(static_cast<size_t>(Bq) * heads * d * vt_ld * 2));
+    __half* vt = static_cast<__half*>(salloc(static_cast<size_t>(Bq) * heads * d * vt_ld * 2));
     {
       GemmDesc g;
       g.A = t1.p; g.C = C; g.W = Nq; g.H = 1; g.B = Bq;
@@ -335,15 +375,15 @@ struct Engine {
       g.vt_col0 = 2 * C; g.vt_d = d; g.vt_heads = heads; g.vt_ntok = Nq; g.vt = vt; g.vt_ld = vt_ld;
       if (int e = emit_gemm(g)) return e;
     }
-    T ao = act(x.B, x.H, x.W, C);
+    T ao = tmp(x.B, x.H, x.W, C);
     if (int e = attention(qk.p, qk.ld, qk.p ? qk.p + C : nullptr, qk.ld, vt, vt_ld, Bq, Nq, Nq, heads, d, ao)) return e;
-    T hB = act(x.B, x.H, x.W, C);
+    T hB = tmp(x.B, x.H, x.W, C);
     if (int e = linear(ao, w_packed(tb + ".attn1.to_out.0.weight", C, C, 1), vec(tb + ".attn1.to_out.0.bias", C), C,
                        hB, &hA))
       return e;
     // --- cross attention (K/V of the text context are step-invariant: computed in the prologue)
     ln(hB, tb + ".norm2", t1);
-    T q2 = act(x.B, x.H, x.W, C);
+    T q2 = tmp(x.B, x.H, x.W, C);
     if (int e = linear(t1, w_packed(tb + ".attn2.to_q.weight", C, C, 1), nullptr, C, q2)) return e;
     const int dcp = (D + 63) / 64 * 64;
     __half* wkv = static_cast<__half*>(alloc(static_cast<size_t>(2) * C * dcp * 2));
@@ -370,17 +410,17 @@ struct Engine {
       if (e) return e;
     }
     if (int e = attention(q2.p, q2.ld, kx, C, vx, vx_ld, Bq, Nq, tokens, heads, d, ao)) return e;
-    T hC = act(x.B, x.H, x.W, C);
+    T hC = tmp(x.B, x.H, x.W, C);
     if (int e = linear(ao, w_packed(tb + ".attn2.to_out.0.weight", C, C, 1), vec(tb + ".attn2.to_out.0.bias", C), C,
                        hC, &hB))
       return e;
     // --- feed-forward (GEGLU)
     ln(hC, tb + ".norm3", t1);
-    T ff = act(x.B, x.H, x.W, 4 * C);
+    T ff = tmp(x.B, x.H, x.W, 4 * C);
     if (int e = linear(t1, w_packed(tb + ".ff.net.0.proj.weight", 8 * C, C, 1, 1),
                        vec(tb + ".ff.net.0.proj.bias", 8 * C, 8 * C), 8 * C, ff, nullptr, GEMM_GEGLU))
       return e;
-    T hD = act(x.B, x.H, x.W, C);
+    T hD = tmp(x.B, x.H, x.W, C);
     if (int e = linear(ff, w_packed(tb + ".ff.net.2.weight", C, 4 * C, 1), vec(tb + ".ff.net.2.bias", C), C, hD, &hC))
       return e;
     return conv(hD, w_packed(pre + ".proj_out.weight", C, C, 1), vec(pre + ".proj_out.bias", C), C, 0, out, &x);
@@ -529,7 +569,7 @@ struct Engine {
     const int* ch = cfg.vae_block_out_channels;
     const int ctop = ch[nlev - 1];
     // post_quant_conv (1x1, lc -> lc) on latents / scaling_factor
-    T z = act(F, H0, W0, lc);
+    T z = pingpong(F, H0, W0, lc);
     {
       const __half* w = w_raw("vae.post_quant_conv.weight", static_cast<int64_t>(lc) * lc);
       const float* b = vec("vae.post_quant_conv.bias", lc);
@@ -538,7 +578,7 @@ struct Engine {
       tag_next = "vae_in (scale + post_quant 1x1)";
       emit([=](cudaStream_t st, int) { return vae_in(xs, inv, w, b, F, lc, H0, W0, z.p, st); });
     }
-    T h = act(F, H0, W0, ctop);
+    T h = pingpong(F, H0, W0, ctop);
     {
       const __half* w = w_raw("vae.decoder.conv_in.weight", static_cast<int64_t>(ctop) * lc * 9);
       const float* b = vec("vae.decoder.conv_in.bias", ctop);
@@ -548,11 +588,12 @@ struct Engine {
     }
     // mid block
     {
-      T a = act(F, H0, W0, ctop);
+      T a = pingpong(F, H0, W0, ctop);
       if (int e = resnet("vae.decoder.mid_block.resnets.0", h, ctop, false, 1e-6f, a)) return e;
       // single-head attention, d = C
       const std::string ap = "vae.decoder.mid_block.attentions.0";
-      T g0 = act(F, H0, W0, ctop);
+      Scope scope(this);
+      T g0 = tmp(F, H0, W0, ctop);
       gn(a, ap + ".group_norm", 1e-6f, 0, g0);
       const int C = ctop, Nq = H0 * W0, cp = (C + 63) / 64 * 64;
       __half* wqkv = static_cast<__half*>(alloc(static_cast<size_t>(3) * C * cp * 2));
@@ -563,9 +604,9 @@ struct Engine {
       params[ap + ".to_q.bias"] = ParamSlot{P_VEC, bqkv, 0, 0, 0, 0, 0, C};
       params[ap + ".to_k.bias"] = ParamSlot{P_VEC, bqkv ? bqkv + C : nullptr, 0, 0, 0, 0, 0, C};
       params[ap + ".to_v.bias"] = ParamSlot{P_VEC, bqkv ? bqkv + 2 * C : nullptr, 0, 0, 0, 0, 0, C};
-      T qk = act(F, H0, W0, 2 * C);
+      T qk = tmp(F, H0, W0, 2 * C);
       const int64_t vt_ld = (Nq + 7) / 8 * 8;
-      __half* vt = static_cast<__half*>(alloc(static_cast<size_t>(F) * C * vt_ld * 2));
+      __half* vt = static_cast<__half*>(salloc(static_cast<size_t>(F) * C * vt_ld * 2));
       {
         GemmDesc g;
         g.A = g0.p; g.C = C; g.W = Nq; g.H = 1; g.B = F;
@@ -576,12 +617,12 @@ struct Engine {
         g.vt_col0 = 2 * C; g.vt_d = C; g.vt_heads = 1; g.vt_ntok = Nq; g.vt = vt; g.vt_ld = vt_ld;
         if (int e = emit_gemm(g)) return e;
       }
-      T ao = act(F, H0, W0, C);
+      T ao = tmp(F, H0, W0, C);
       if (int e = attention(qk.p, qk.ld, qk.p ? qk.p + C : nullptr, qk.ld, vt, vt_ld, F, Nq, Nq, 1, C, ao)) return e;
-      T b = act(F, H0, W0, C);
+      T b = pingpong(F, H0, W0, C);
       if (int e = linear(ao, w_packed(ap + ".to_out.0.weight", C, C, 1), vec(ap + ".to_out.0.bias", C), C, b, &a))
         return e;
-      T c = act(F, H0, W0, C);
+      T c = pingpong(F, H0, W0, C);
       if (int e = resnet("vae.decoder.mid_block.resnets.1", b, ctop, false, 1e-6f, c)) return e;
       h = c;
     }
@@ -591,19 +632,19 @@ struct Engine {
       cout = ch[nlev - 1 - i];
       const std::string bp = "vae.decoder.up_blocks." + std::to_string(i);
       for (int j = 0; j <= cfg.vae_layers_per_block; ++j) {
-        T o = act(h.B, h.H, h.W, cout);
+        T o = pingpong(h.B, h.H, h.W, cout);
         if (int e = resnet(bp + ".resnets." + std::to_string(j), h, cout, false, 1e-6f, o)) return e;
         h = o;
       }
       if (i < nlev - 1) {
-        T o = act(h.B, h.H * 2, h.W * 2, cout);
+        T o = pingpong(h.B, h.H * 2, h.W * 2, cout);
         if (int e = conv(h, w_packed_up4(bp + ".upsamplers.0.conv.weight", cout, cout),
                          vec(bp + ".upsamplers.0.conv.bias", cout), cout, 3, o))
           return e;
         h = o;
       }
     }
-    T n = act(h.B, h.H, h.W, h.C);
+    T n = pingpong(h.B, h.H, h.W, h.C);
     gn(h, "vae.decoder.conv_norm_out", 1e-6f, 1, n);
     {
       const __half* w = w_raw("vae.decoder.conv_out.weight", static_cast<int64_t>(cfg.vae_out_channels) * h.C * 9);
@@ -621,6 +662,15 @@ struct Engine {
     dry = dry_run;
     base = static_cast<uint8_t*>(arena);
     off = 0;
+    soff = 0;
+    pp_count = 0;
+    if (dry) {
+      speak = pp_peak[0] = pp_peak[1] = 0;
+    } else {  // sizes measured by the dry run
+      pp_base[0] = base + pers_bytes;
+      pp_base[1] = pp_base[0] + (pp_peak[0] + 1023) / 1024 * 1024;
+      sbase = pp_base[1] + (pp_peak[1] + 1023) / 1024 * 1024;
+    }
     params.clear();
     prologue.clear(); unet_ops.clear(); vae_ops.clear(); tprojs.clear();
     n_launch_prologue = n_launch_unet = n_launch_vae = 0;
@@ -641,10 +691,17 @@ struct Engine {
     out_u8 = static_cast<uint8_t*>(alloc(static_cast<size_t>(F) * OH * OW * cfg.vae_out_channels));
     out_img_f32 = static_cast<float*>(alloc(static_cast<size_t>(F) * OH * OW * cfg.vae_out_channels * 4));
     gn_ws = static_cast<float2*>(alloc(gn_workspace_bytes(std::max(Bn, F))));
-    // attention score scratch: largest of UNet level-0 self attention and the VAE mid attention
+    // attention score scratch of the UNFUSED path: the VAE mid attention (d = 512), and UNet level-0 self attention only
+    // when its head dim has no fused kernel (or SDW_NO_FLASH)
     {
       const int64_t n0 = static_cast<int64_t>(H) * W;
-      int64_t unet_s = static_cast<int64_t>(Bn) * cfg.attention_heads[0] * n0 * ((n0 + 7) / 8 * 8);
+      int64_t unet_s = 0;
+      for (int l = 0; l < cfg.num_levels; ++l) {
+        const int hl = std::max(1, cfg.attention_heads[l]);
+        if (use_flash && attn_supported(cfg.block_out_channels[l] / hl)) continue;
+        const int64_t nl = static_cast<int64_t>(H >> l) * (W >> l);
+        unet_s = std::max(unet_s, static_cast<int64_t>(Bn) * hl * nl * ((nl + 7) / 8 * 8));
+      }
       int64_t vae_s = static_cast<int64_t>(F) * n0 * ((n0 + 7) / 8 * 8);
       S_elems = static_cast<size_t>(std::max(unet_s, vae_s));
       S = static_cast<__half*>(alloc(S_elems * 2));
@@ -655,7 +712,10 @@ struct Engine {
     temb = static_cast<float*>(alloc(static_cast<size_t>(cfg.max_steps) * temb_ch() * 4));
     if (int e = build_unet()) return e;
     if (int e = build_vae()) return e;
-    if (dry) arena_bytes = off + 4096;
+    if (dry) {
+      pers_bytes = (off + 4095) / 4096 * 4096;
+      arena_bytes = pers_bytes + (pp_peak[0] + 1023) / 1024 * 1024 + (pp_peak[1] + 1023) / 1024 * 1024 + speak + 4096;
+    }
     return 0;
   }
 };
