@@ -117,69 +117,59 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float2* __restri
   }
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, int64_t ldx, int C, int G,
-                                                       int64_t P, const float2* __restrict__ stats,
-                                                       const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, int silu,
-                                                       __half* __restrict__ y, int64_t ldy, int pix_per_block) {
-  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+__global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __half* __restrict__ x, int64_t ldx, int C, int G,
+                                                          int64_t P, const float2* __restrict__ stats,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, int silu,
+                                                          __half* __restrict__ y, int64_t ldy, int pix_per_block) {
+  // per-channel affine of this sample, folded once per block: y = x * sa[c] + sb[c],
+  //   sa = rstd_g * gamma_c, sb = beta_c - mean_g * rstd_g * gamma_c   (no group bookkeeping in the streaming loop)
+  extern __shared__ float gn_aff[];  // [C] sa, [C] sb
+  float* sa = gn_aff;
+  float* sb = gn_aff + C;
   pdl_wait();
   pdl_launch_dependents();
   const int b = blockIdx.y;
   const int cg = C / G;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    const float2 st = stats[b * G + g];
-    s_mean[g] = st.x;
-    s_rstd[g] = st.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float2 st = stats[b * G + c / cg];
+    const float a = st.y * gamma[c];
+    sa[c] = a;
+    sb[c] = fmaf(-st.x, a, beta[c]);
   }
   __syncthreads();
   const int vecs = C / 8;
   const int64_t p0 = static_cast<int64_t>(blockIdx.x) * pix_per_block;
   const int64_t p1 = min(P, p0 + pix_per_block);
-  const int64_t items = (p1 - p0) * vecs;
   const __half* xb = x + static_cast<int64_t>(b) * P * ldx;
   __half* yb = y + static_cast<int64_t>(b) * P * ldy;
   auto apply8 = [&](const uint4& u, int v, int64_t p) {
     const __half2* h = reinterpret_cast<const __half2*>(&u);
+    const float4 a0 = *reinterpret_cast<const float4*>(sa + v * 8), a1 = *reinterpret_cast<const float4*>(sa + v * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(sb + v * 8), b1 = *reinterpret_cast<const float4*>(sb + v * 8 + 4);
+    const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     float o[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = __half22float2(h[j]);
-      o[2 * j] = f.x;
-      o[2 * j + 1] = f.y;
+      o[2 * j] = fmaf(f.x, aa[2 * j], bb[2 * j]);
+      o[2 * j + 1] = fmaf(f.y, aa[2 * j + 1], bb[2 * j + 1]);
     }
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
-    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    int g = (v * 8) / cg;          // one division per 8 channels; the group index then advances incrementally
-    int rem = v * 8 - g * cg;
+    if (silu) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = (o[j] - s_mean[g]) * s_rstd[g] * gg[j] + bb[j];
-      if (silu) t = __fdividef(t, 1.f + __expf(-t));
-      o[j] = t;
-      if (++rem == cg) {
-        rem = 0;
-        ++g;
-      }
+      for (int j = 0; j < 8; ++j) o[j] = __fdividef(o[j], 1.f + __expf(-o[j]));
     }
-    uint4 w;
-    w.x = pack_h2(o[0], o[1]);
-    w.y = pack_h2(o[2], o[3]);
-    w.z = pack_h2(o[4], o[5]);
-    w.w = pack_h2(o[6], o[7]);
-    *reinterpret_cast<uint4*>(yb + p * ldy + v * 8) = w;
+    *reinterpret_cast<uint4*>(yb + p * ldy + v * 8) =
+        make_uint4(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]), pack_h2(o[4], o[5]), pack_h2(o[6], o[7]));
   };
   // 4 independent 16-byte loads in flight per thread.  (pixel, vector) of item `it` advance incrementally: the 64-bit
   // div / mod per item this loop used to do cost more issue slots than the normalisation itself
   const int dv = static_cast<int>(blockDim.x) % vecs, dp = static_cast<int>(blockDim.x) / vecs;
   int v = static_cast<int>(threadIdx.x) % vecs;
-  int64_t pl = static_cast<int>(threadIdx.x) / vecs;  // pixel relative to p0
-  const int64_t npix = p1 - p0;
-  auto advance = [&](int& vv, int64_t& pp) {
+  int pl = static_cast<int>(threadIdx.x) / vecs;  // pixel relative to p0
+  const int npix = static_cast<int>(p1 - p0);
+  auto advance = [&](int& vv, int& pp) {
     vv += dv;
     pp += dp;
     if (vv >= vecs) {
@@ -187,25 +177,44 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
       ++pp;
     }
   };
-  while (true) {
+  // software pipeline: batch k+1 (4 x 16 B per thread) is in flight while batch k is normalised — with a single batch
+  // the ~64 KB an SM had in flight during the load phases only could not cover the HBM latency-bandwidth product
+  struct Batch {
     uint4 u[4];
     int vv[4];
-    int64_t pp[4];
-    int n = 0;
+    int pp[4];
+    int n;
+  };
+  Batch A, Bt;
+  auto load_batch = [&](Batch& t) {
+    t.n = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      vv[k] = v;
-      pp[k] = pl;
+      t.vv[k] = v;
+      t.pp[k] = pl;
       if (pl < npix) {
-        u[k] = *reinterpret_cast<const uint4*>(xb + (p0 + pl) * ldx + v * 8);
-        n = k + 1;
+        t.u[k] = *reinterpret_cast<const uint4*>(xb + (p0 + pl) * ldx + v * 8);
+        t.n = k + 1;
       }
       advance(v, pl);
     }
+  };
+  auto run_batch = [&](const Batch& t) {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (k < n) apply8(u[k], vv[k], p0 + pp[k]);
-    if (n < 4) break;
+      if (k < t.n) apply8(t.u[k], t.vv[k], p0 + t.pp[k]);
+  };
+  load_batch(A);
+#pragma unroll 1
+  while (true) {
+    if (A.n == 4) load_batch(Bt);
+    else Bt.n = 0;
+    run_batch(A);
+    if (Bt.n == 0) break;
+    if (Bt.n == 4) load_batch(A);
+    else A.n = 0;
+    run_batch(Bt);
+    if (A.n == 0) break;
   }
 }
 
@@ -422,11 +431,11 @@ int groupnorm(const __half* x, int64_t ldx, int B, int64_t P, int C, int G, cons
                          static_cast<float>(P) * (C / G), eps, stats));
   // one full wave: 148 SMs x 8 resident 256-thread blocks, split evenly over the samples (the former fixed ~100-pixel
   // tiles gave 1376 blocks = 1.16 waves at 64x64x320, batch 32: the second wave ran 16 % full)
-  const int64_t per_sample = std::max<int64_t>(1, (148 * 8) / B);
+  const int64_t per_sample = std::max<int64_t>(1, (148 * 3) / B);  // 3 resident blocks per SM (launch bounds)
   const int ppb = static_cast<int>(std::max<int64_t>(1, (P + per_sample - 1) / per_sample));
   const unsigned tiles = static_cast<unsigned>((P + ppb - 1) / ppb);
-  SDW_CUDA_OK(launch_pdl(gn_apply_kernel, dim3(tiles, B), dim3(256), 0, stream, x, ldx, C, G, P, stats, gamma, beta, silu,
-                         y, ldy, ppb));
+  SDW_CUDA_OK(launch_pdl(gn_apply_kernel, dim3(tiles, B), dim3(256), static_cast<size_t>(2) * C * sizeof(float), stream, x, ldx,
+                         C, G, P, stats, gamma, beta, silu, y, ldy, ppb));
   return 0;
 }
 
