@@ -542,6 +542,306 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::N
 }
 
 // =============================================================================================
+// attn_pair_kernel — head dim <= 64, BKV = 128, two threads per query row.
+//
+// attn_fwd_kernel keeps the MUFU pipe only 57 % busy at head dim 40 with one softmax warp per scheduler and CTA
+// (profiles/r01_ncu_attn_lazy.md).  Hypothesis tested here: the per-row chain TMEM load -> FFMA2 -> MUFU -> pack is
+// latency bound and more warps would fill the pipe.  Result: same speed (see variant_for) — kept as an opt-in variant.  EIGHT
+// softmax warps per CTA (two CTAs per SM -> four per scheduler) split every row in two 64-column halves.  Both
+// threads of a row share the reference maximum m_run, so the fast path needs no communication at all; the slow-path
+// decision and the exact row maximum are agreed through shared memory and one 256-thread named barrier; the row sums
+// stay per thread and meet in the epilogue.  P, the PV product and the O accumulator are unchanged (one 128 x 128 P
+// tile, one accumulator), so the MMA warp is the same as in attn_fwd_kernel with a single S buffer.
+// =============================================================================================
+static constexpr int ATTP_THREADS = 320;  // warp 0 producer, warp 1 MMA, warps 2-9 softmax
+
+__device__ __forceinline__ void bar_sync_softmax() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int DVP>
+__global__ void __launch_bounds__(ATTP_THREADS, 2) attn_pair_kernel(const __grid_constant__ AttnKParams p) {
+  constexpr int BKV = 128, ST = 2;
+  using Cfg = AttnCfg<1, DVP, BKV, ST, 1>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* p_smem = q_smem + Cfg::Q_BYTES;
+  uint8_t* k_smem = p_smem + Cfg::P_BYTES;
+  uint8_t* v_smem = k_smem + ST * Cfg::K_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + ST * Cfg::V_STAGE);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + ST;
+  uint64_t* s_full = kv_empty + ST;
+  uint64_t* p_ready = s_full + 1;
+  uint64_t* pv_done = p_ready + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 1);
+  int* s_vote = reinterpret_cast<int*>(tmem_ptr_smem + 2);  // [8]
+  // [128][2] exchange of partial row maxima (slow path) / row sums (epilogue).  It overlays the head of the P tile,
+  // which is idle whenever PV_{j-1} has completed and this tile's P rows have not been written yet.
+  float* s_x = reinterpret_cast<float*>(p_smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int ntiles = (p.Nk + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.mapQ);
+    tma_prefetch_desc(&p.mapK);
+    tma_prefetch_desc(&p.mapV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 256);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Cfg::Q_BYTES);
+      tma_load_4d(&p.mapQ, q_full, q_smem, 0, q0, head, b);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j % ST;
+        mbar_wait(&kv_empty[s], ((j / ST) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], Cfg::K_STAGE + Cfg::V_STAGE);
+        const int kv0 = j * BKV;
+        tma_load_4d(&p.mapK, &kv_full[s], k_smem + s * Cfg::K_STAGE, 0, kv0, head, b);
+#pragma unroll
+        for (int a = 0; a < BKV / 64; ++a)
+          tma_load_4d(&p.mapV, &kv_full[s], v_smem + s * Cfg::V_STAGE + a * (DVP * 128), kv0 + a * 64, 0, head, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_f16(ATT_BQ, BKV);
+      constexpr uint32_t idesc_o = make_idesc_f16(ATT_BQ, DVP);
+      const uint32_t q_addr = smem_u32(q_smem);
+      const uint32_t p_addr = smem_u32(p_smem);
+      auto issue_s = [&](int j) {
+        const int s = j % ST;
+        mbar_wait(&kv_full[s], (j / ST) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(k_smem + s * Cfg::K_STAGE);
+        for (int ks = 0; ks < p.dk_steps; ++ks)
+          umma_f16_ss(tmem, make_desc_k_sw128(q_addr + ks * 32), make_desc_k_sw128(k_addr + ks * 32), idesc_s,
+                      ks != 0 ? 1u : 0u);
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < ntiles; ++j) {
+        mbar_wait(p_ready, j & 1);
+        tc_fence_after();
+        if (j + 1 < ntiles) issue_s(j + 1);  // every row has consumed S_j: S_{j+1} goes first and overlaps PV_j
+        const int s = j % ST;
+        const uint32_t v_addr = smem_u32(v_smem + s * Cfg::V_STAGE);
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          const uint64_t da = make_desc_k_sw128(p_addr + (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32);
+          const uint64_t db = make_desc_k_sw128(v_addr + (ks >> 2) * (DVP * 128) + (ks & 3) * 32);
+          umma_f16_ss(tmem + Cfg::O_COL, da, db, idesc_o, (j | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(pv_done);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    // ============================ softmax: thread = (row, 64-column half) ============================
+    const int quarter = warp & 3;
+    const int hh = warp >= 6 ? 1 : 0;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_s = tmem + lane_base + hh * 64;
+    const uint32_t t_o = tmem + lane_base + Cfg::O_COL;
+    float m_run = -INFINITY, l_part = 0.f;
+    const float sl2 = p.scale_log2e;
+    uint8_t* p_row = p_smem + hh * (ATT_BQ * 128) + r * 128;
+    const int sw = r & 7;
+    constexpr float LAZY_LOG2 = 8.f;
+
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int c0 = j * BKV + hh * 64;  // first key of this thread's half
+      const bool ragged = j * BKV + BKV > p.Nk;
+      bool need_slow = (j == 0) || ragged;  // CTA-uniform
+      float alpha = 1.f;
+      uint32_t pk[32];
+      if (!need_slow) {
+        // ---- fast path: reference max, 16-column TMEM chunks pipelined against the exponentials ----
+        const float mb = m_run * sl2;
+        const uint64_t sl2_2 = pk2(sl2, sl2), nmb_2 = pk2(-mb, -mb);
+        uint64_t sm2 = pk2(0.f, 0.f);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        uint32_t va[16], vb[16];
+        tmem_ld_32x16(t_s, va);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t(&cur)[16] = (c & 1) ? vb : va;
+          uint32_t(&nxt)[16] = (c & 1) ? va : vb;
+          if (c + 1 < 4) tmem_ld_32x16(t_s + (c + 1) * 16, nxt);
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float x0 = __uint_as_float(cur[i]), x1 = __uint_as_float(cur[i + 1]);
+            mx0 = fmaxf(mx0, x0);
+            mx1 = fmaxf(mx1, x1);
+            float t0, t1;
+            upk2(fma2(pk2(x0, x1), sl2_2, nmb_2), t0, t1);
+            const float e0 = ex2f(t0), e1 = ex2f(t1);
+            sm2 = add2(sm2, pk2(e0, e1));
+            pk[c * 8 + (i >> 1)] = pack_h2(e0, e1);
+          }
+          if (c + 1 < 4) tmem_ld_wait();
+        }
+        const bool vote = __any_sync(0xffffffffu, (fmaxf(mx0, mx1) - m_run) * sl2 > LAZY_LOG2);
+        if (lane == 0) s_vote[warp - 2] = vote ? 1 : 0;
+        bar_sync_softmax();
+        int any = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) any |= s_vote[w];
+        need_slow = any != 0;
+        if (!need_slow) {
+          float s0, s1;
+          upk2(sm2, s0, s1);
+          l_part += s0 + s1;
+        }
+      }
+      if (need_slow) {
+        // ---- slow path (tile 0, ragged tiles, a row max moved past the lazy threshold): exact, two TMEM passes ----
+        if (j > 0) {
+          mbar_wait(pv_done, (j - 1) & 1);  // the P tile doubles as the exchange buffer
+          tc_fence_after();
+        }
+        float pm = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[16];
+          tmem_ld_32x16(t_s + c * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (!ragged || c0 + c * 16 + i < p.Nk) pm = fmaxf(pm, __uint_as_float(v[i]));
+        }
+        s_x[r * 2 + hh] = pm;
+        bar_sync_softmax();
+        const float m_t = fmaxf(s_x[r * 2], s_x[r * 2 + 1]);
+        bar_sync_softmax();  // all exchange reads precede the P rows that overwrite them
+        const float m_new = fmaxf(m_run, m_t);  // finite: tile 0 always holds a valid key
+        alpha = ex2f((m_run - m_new) * sl2);
+        const float mb = m_new * sl2;
+        const uint64_t sl2_2 = pk2(sl2, sl2), nmb_2 = pk2(-mb, -mb);
+        uint64_t sm2 = pk2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[16];
+          tmem_ld_32x16(t_s + c * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float x0 = __uint_as_float(v[i]), x1 = __uint_as_float(v[i + 1]);
+            if (ragged) {
+              if (c0 + c * 16 + i >= p.Nk) x0 = -INFINITY;
+              if (c0 + c * 16 + i + 1 >= p.Nk) x1 = -INFINITY;
+            }
+            float t0, t1;
+            upk2(fma2(pk2(x0, x1), sl2_2, nmb_2), t0, t1);
+            const float e0 = ex2f(t0), e1 = ex2f(t1);
+            sm2 = add2(sm2, pk2(e0, e1));
+            pk[c * 8 + (i >> 1)] = pack_h2(e0, e1);
+          }
+        }
+        float s0, s1;
+        upk2(sm2, s0, s1);
+        l_part = fmaf(l_part, alpha, s0 + s1);
+        m_run = m_new;
+      }
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);  // P smem and the O accumulator are free once PV_{j-1} has completed
+        tc_fence_after();
+        if (need_slow && __any_sync(0xffffffffu, alpha != 1.f)) {
+          // the two threads of a row share the O columns: 16-column chunk c belongs to half (c & 1)
+#pragma unroll
+          for (int c = 0; c < DVP / 16; ++c) {
+            if ((c & 1) != hh) continue;
+            uint32_t o[16];
+            tmem_ld_32x16(t_o + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x16(t_o + c * 16, o);
+          }
+          tmem_st_wait();
+        }
+      }
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8)
+        *reinterpret_cast<uint4*>(p_row + ((c8 ^ sw) << 4)) =
+            make_uint4(pk[c8 * 4 + 0], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+    }
+    // ---- epilogue: O / (l_a + l_b) -> fp16, the pair splits the 16-column chunks ----
+    mbar_wait(pv_done, (ntiles - 1) & 1);
+    tc_fence_after();
+    s_x[r * 2 + hh] = l_part;
+    bar_sync_softmax();
+    const float inv_l = 1.f / (s_x[r * 2] + s_x[r * 2 + 1]);
+    const int row = q0 + r;
+    __half* orow = p.out + (static_cast<int64_t>(b) * p.Nq + row) * p.out_ld + head * p.d;
+    const bool vec_ok = ((p.out_ld & 7) == 0) && ((p.d & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+#pragma unroll
+    for (int c = 0; c < DVP / 16; ++c) {
+      if ((c & 1) != hh) continue;  // warp-uniform
+      uint32_t o[16];
+      tmem_ld_32x16(t_o + c * 16, o);
+      tmem_ld_wait();
+      if (row < p.Nq) {
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          const int dd = c * 16 + h8 * 8;
+          if (dd >= p.d) break;
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[h8 * 8 + i]) * inv_l;
+          if (vec_ok && dd + 8 <= p.d) {
+            *reinterpret_cast<uint4*>(orow + dd) =
+                make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (dd + i < p.d) orow[dd + i] = __float2half_rn(f[i]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, Cfg::TMEM_COLS);
+  }
+}
+
+// =============================================================================================
 // host
 // =============================================================================================
 struct AttnLaunchImpl {
@@ -570,6 +870,10 @@ static int attn_init() {
   if (int e = attn_set_attr<1, 48, 128, 2, 1, 0>()) return e;
   if (int e = attn_set_attr<1, 48, 128, 2, 1, 8>()) return e;
   if (int e = attn_set_attr<2, 80, 64, 2, 1, 0>()) return e;
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pair_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<1, 16, 128, 2, 1>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<1, 32, 128, 2, 1>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pair_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<1, 48, 128, 2, 1>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<1, 64, 128, 2, 1>::SMEM));
   if (int e = attn_set_attr<1, 16, 128, 2, 1, 0, 1>()) return e;
   if (int e = attn_set_attr<1, 32, 128, 2, 1, 0, 1>()) return e;
   if (int e = attn_set_attr<1, 48, 128, 2, 1, 0, 1>()) return e;
@@ -589,6 +893,11 @@ static int variant_for(int d) {
     return std::getenv("SDW_ATTN_BKV64") != nullptr || std::getenv("SDW_ATTN_POLY") != nullptr;
   }();
   if (split && !legacy && d <= 64) return d <= 16 ? 10 : (d <= 32 ? 11 : (d <= 48 ? 12 : 13));
+  // two threads per query row (variants 14-17): correct, but not faster than one thread per row (self-attention 64x64,
+  // d = 40, batch 32: 1786 vs 1746 us, profiles/r01_attn_bench_pair.txt) — more softmax warps do not help either — so it
+  // is opt-in: SDW_ATTN_PAIR=1
+  static const bool pair = [] { const char* e = std::getenv("SDW_ATTN_PAIR"); return e && e[0] == '1'; }();
+  if (pair && !legacy && d <= 64) return d <= 16 ? 14 : (d <= 32 ? 15 : (d <= 48 ? 16 : 17));
   if (d <= 16) return 0;
   if (d <= 32) return 1;
   static const bool bkv64 = [] { const char* e = std::getenv("SDW_ATTN_BKV64"); return e && e[0] == '1'; }();
@@ -616,7 +925,7 @@ int plan_attention(const AttnDesc& a, AttnLaunch* L) {
   std::memset(I, 0, sizeof(*I));
   I->variant = variant_for(a.d);
   const int bkv = (I->variant == 5 || I->variant == 6 || I->variant == 9) ? 64 : 128;
-  const int dvp_tab[14] = {16, 32, 48, 64, 80, 160, 48, 48, 48, 80, 16, 32, 48, 64};
+  const int dvp_tab[18] = {16, 32, 48, 64, 80, 160, 48, 48, 48, 80, 16, 32, 48, 64, 16, 32, 48, 64};
   const int dvp = dvp_tab[I->variant];
   AttnKParams& p = I->p;
   p.Nq = a.Nq; p.Nk = a.Nk; p.d = a.d; p.heads = a.heads;
@@ -669,6 +978,10 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     case 11: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 32, 128, 2, 1, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 32, 128, 2, 1>::SMEM, stream, I->p)); break;
     case 12: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 2, 1, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 2, 1>::SMEM, stream, I->p)); break;
     case 13: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 64, 128, 2, 1, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 64, 128, 2, 1>::SMEM, stream, I->p)); break;
+    case 14: SDW_CUDA_OK(launch_pdl(attn_pair_kernel<16>, I->grid, dim3(ATTP_THREADS), AttnCfg<1, 16, 128, 2, 1>::SMEM, stream, I->p)); break;
+    case 15: SDW_CUDA_OK(launch_pdl(attn_pair_kernel<32>, I->grid, dim3(ATTP_THREADS), AttnCfg<1, 32, 128, 2, 1>::SMEM, stream, I->p)); break;
+    case 16: SDW_CUDA_OK(launch_pdl(attn_pair_kernel<48>, I->grid, dim3(ATTP_THREADS), AttnCfg<1, 48, 128, 2, 1>::SMEM, stream, I->p)); break;
+    case 17: SDW_CUDA_OK(launch_pdl(attn_pair_kernel<64>, I->grid, dim3(ATTP_THREADS), AttnCfg<1, 64, 128, 2, 1>::SMEM, stream, I->p)); break;
     default: set_error("bad attention variant"); return 1;
   }
   SDW_CUDA_OK(cudaGetLastError());

@@ -58,7 +58,7 @@ def test_flash_attention_peaky_scores():
     assert float((out - ref).abs().max()) <= 2.0 ** -7 * float(ref.abs().max()) + 2e-3
 
 
-def test_attention_split_s_variant_subprocess():
+def test_attention_opt_in_variants_subprocess():
     """the opt-in split-S pipeline (SDW_ATTN_SPLIT=1) against torch, incl. a ragged key count and a max that keeps rising"""
     import os
     import subprocess
@@ -78,7 +78,8 @@ def test_attention_split_s_variant_subprocess():
             "    ref=(torch.softmax(qf@kf.transpose(-1,-2)*d**-0.5,-1)@vf).permute(0,2,1,3).reshape(B,Nq,Cc)\n"
             "    err=(out.float()-ref).abs().max().item(); assert err <= 2**-8*ref.abs().max().item()+1e-3, (err, B,h,Nq,Nk,d)\n"
             "print('ok')\n")
-    env = dict(os.environ, SDW_ATTN_SPLIT="1")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "ok" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+    for var in ("SDW_ATTN_SPLIT", "SDW_ATTN_PAIR"):  # split-S pipeline; two threads per query row
+        env = dict(os.environ, **{var: "1"})
+        r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "ok" in r.stdout, (var, r.stdout[-500:], r.stderr[-2000:])
