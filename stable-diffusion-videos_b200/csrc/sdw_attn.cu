@@ -35,18 +35,21 @@ struct alignas(64) AttnKParams {
 
 // SB = number of S accumulator buffers: 2 (double-buffered, one CTA per SM) or 1 (TMEM 256 columns and <= 113 KB of
 // shared memory, so TWO CTAs share an SM: one CTA's softmax overlaps the other's MMAs and both keep the MUFU pipe fed)
-template <int DKA, int DVP, int BKV, int ST, int SB>
+// PT = 1: P stays in tensor memory (BKV / 2 extra columns, fp16 pairs) and PV runs as a TS-mode MMA: no P tile in
+// shared memory, no generic->async proxy fence, half the shared-memory traffic per KV tile.
+template <int DKA, int DVP, int BKV, int ST, int SB, int PT = 0>
 struct AttnCfg {
   static constexpr int Q_BYTES = DKA * ATT_BQ * 128;
   static constexpr int K_STAGE = DKA * BKV * 128;
   static constexpr int V_STAGE = (BKV / 64) * DVP * 128;
-  static constexpr int P_BYTES = (BKV / 64) * ATT_BQ * 128;
+  static constexpr int P_BYTES = PT ? 0 : (BKV / 64) * ATT_BQ * 128;
   static constexpr int SMEM = Q_BYTES + P_BYTES + ST * (K_STAGE + V_STAGE) + 1024 + 256;
-  static constexpr int NEED = SB * BKV + DVP;
+  static constexpr int P_COL = SB * BKV;                       // PT: P_j as packed fp16 pairs
+  static constexpr int NEED = SB * BKV + DVP + (PT ? BKV / 2 : 0);
   static constexpr int TMEM_COLS = NEED <= 128 ? 128 : (NEED <= 256 ? 256 : 512);
   static constexpr int NCTA = SMEM <= 64 * 1024 && TMEM_COLS <= 128 ? 3 : (SMEM <= 114 * 1024 && TMEM_COLS <= 256 ? 2 : 1);  // CTAs per SM
-  static constexpr int O_COL = SB * BKV;
-  static_assert(SB * BKV + DVP <= TMEM_COLS, "TMEM budget");
+  static constexpr int O_COL = SB * BKV + (PT ? BKV / 2 : 0);
+  static_assert(NEED <= TMEM_COLS, "TMEM budget");
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -74,11 +77,12 @@ __device__ __forceinline__ float ex2_poly(float t) {
 // profiles/r01_ncu_attn_lazy.md.  Now S_{j+1}[0] is issued as soon as every row has read S_j[0], i.e. half a tile
 // before it is needed, and the softmax treats each half as its own online-softmax step (P of half 0 is rescaled in
 // shared memory in the rare case half 1 raises the row maximum past the lazy threshold).
-template <int DKA, int DVP, int BKV, int ST, int SB, int POLY = 4, int SPLIT = 0>  // POLY: every POLY-th exp on the FMA pipe (0 = none)
-__global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::NCTA)
+template <int DKA, int DVP, int BKV, int ST, int SB, int POLY = 4, int SPLIT = 0, int PT = 0>  // POLY: every POLY-th exp on the FMA pipe (0 = none)
+__global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT>::NCTA)
     attn_fwd_kernel(const __grid_constant__ AttnKParams p) {
   static_assert(!SPLIT || (SB == 1 && BKV == 128 && DKA == 1), "the split-S pipeline is the BKV = 128, single-buffer variant");
-  using Cfg = AttnCfg<DKA, DVP, BKV, ST, SB>;
+  static_assert(!PT || !SPLIT, "P-in-TMEM is a variant of the whole-tile pipeline");
+  using Cfg = AttnCfg<DKA, DVP, BKV, ST, SB, PT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;
@@ -209,9 +213,13 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::N
         const uint32_t v_addr = smem_u32(v_smem + s * Cfg::V_STAGE);
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks) {
-          const uint64_t da = make_desc_k_sw128(p_addr + (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32);
           const uint64_t db = make_desc_k_sw128(v_addr + (ks >> 2) * (DVP * 128) + (ks & 3) * 32);
-          umma_f16_ss(tmem + Cfg::O_COL, da, db, idesc_o, (j | ks) != 0 ? 1u : 0u);
+          if (PT) {
+            umma_f16_ts(tmem + Cfg::O_COL, tmem + Cfg::P_COL + ks * 8, db, idesc_o, (j | ks) != 0 ? 1u : 0u);
+          } else {
+            const uint64_t da = make_desc_k_sw128(p_addr + (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32);
+            umma_f16_ss(tmem + Cfg::O_COL, da, db, idesc_o, (j | ks) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(pv_done);
         umma_commit(&kv_empty[s]);
@@ -481,17 +489,30 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB>::N
           tmem_st_wait();
         }
       }
-      // P_j -> shared memory, K-major SWIZZLE_128B: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
+      if (PT) {
+        // P_j -> tensor memory: row = this thread's lane, column c = keys (2c, 2c+1) as an fp16 pair (the TS-mode A layout)
+        const uint32_t t_p = tmem + lane_base + Cfg::P_COL;
 #pragma unroll
-      for (int c8 = 0; c8 < BKV / 8; ++c8) {
-        uint4 u;
-        u.x = pk[c8 * 4 + 0];
-        u.y = pk[c8 * 4 + 1];
-        u.z = pk[c8 * 4 + 2];
-        u.w = pk[c8 * 4 + 3];
-        *reinterpret_cast<uint4*>(p_row + (c8 >> 3) * (ATT_BQ * 128) + (((c8 & 7) ^ sw) << 4)) = u;
+        for (int c = 0; c < BKV / 32; ++c) {
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w[i] = pk[c * 16 + i];
+          tmem_st_32x16(t_p + c * 16, w);
+        }
+        tmem_st_wait();
+      } else {
+        // P_j -> shared memory, K-major SWIZZLE_128B: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
+#pragma unroll
+        for (int c8 = 0; c8 < BKV / 8; ++c8) {
+          uint4 u;
+          u.x = pk[c8 * 4 + 0];
+          u.y = pk[c8 * 4 + 1];
+          u.z = pk[c8 * 4 + 2];
+          u.w = pk[c8 * 4 + 3];
+          *reinterpret_cast<uint4*>(p_row + (c8 >> 3) * (ATT_BQ * 128) + (((c8 & 7) ^ sw) << 4)) = u;
+        }
+        fence_proxy_async_smem();
       }
-      fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_ready);
     }
@@ -850,10 +871,10 @@ struct AttnLaunchImpl {
   int variant;
 };
 
-template <int DKA, int DVP, int BKV, int ST, int SB, int POLY = 4, int SPLIT = 0>
+template <int DKA, int DVP, int BKV, int ST, int SB, int POLY = 4, int SPLIT = 0, int PT = 0>
 static int attn_set_attr() {
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<DKA, DVP, BKV, ST, SB, POLY, SPLIT>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<DKA, DVP, BKV, ST, SB>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<DKA, DVP, BKV, ST, SB, POLY, SPLIT, PT>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<DKA, DVP, BKV, ST, SB, PT>::SMEM));
   return 0;
 }
 
@@ -874,6 +895,12 @@ static int attn_init() {
   SDW_CUDA_OK(cudaFuncSetAttribute(attn_pair_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<1, 32, 128, 2, 1>::SMEM));
   SDW_CUDA_OK(cudaFuncSetAttribute(attn_pair_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<1, 48, 128, 2, 1>::SMEM));
   SDW_CUDA_OK(cudaFuncSetAttribute(attn_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<1, 64, 128, 2, 1>::SMEM));
+  if (int e = attn_set_attr<1, 48, 64, 2, 2, 0>()) return e;
+  if (int e = attn_set_attr<1, 16, 128, 2, 1, 0, 0, 1>()) return e;
+  if (int e = attn_set_attr<1, 32, 128, 2, 1, 0, 0, 1>()) return e;
+  if (int e = attn_set_attr<1, 48, 128, 2, 1, 0, 0, 1>()) return e;
+  if (int e = attn_set_attr<1, 64, 128, 2, 1, 0, 0, 1>()) return e;
+  if (int e = attn_set_attr<2, 80, 64, 2, 1, 0, 0, 1>()) return e;
   if (int e = attn_set_attr<1, 16, 128, 2, 1, 0, 1>()) return e;
   if (int e = attn_set_attr<1, 32, 128, 2, 1, 0, 1>()) return e;
   if (int e = attn_set_attr<1, 48, 128, 2, 1, 0, 1>()) return e;
@@ -885,6 +912,16 @@ static int attn_init() {
 bool attn_supported(int d) { return d % 8 == 0 && d >= 8 && d <= 160; }
 
 static int variant_for(int d) {
+  // experiments: SDW_ATTN_VARIANT=18 -> head dims 33..48 on the BKV = 64, double-buffered-S tile (2 CTAs per SM)
+  static const int forced = [] { const char* e = std::getenv("SDW_ATTN_VARIANT"); return e ? std::atoi(e) : -1; }();
+  if (forced == 18 && d > 32 && d <= 48) return 18;
+  // P in tensor memory + TS-mode PV (variants 19-22) for head dims <= 64: SDW_ATTN_PT=0 reverts to P in shared memory
+  static const bool pt = [] { const char* e = std::getenv("SDW_ATTN_PT"); return !(e && e[0] == '0'); }();
+  static const bool other = [] {
+    return std::getenv("SDW_ATTN_BKV64") || std::getenv("SDW_ATTN_POLY") || std::getenv("SDW_ATTN_SPLIT") || std::getenv("SDW_ATTN_PAIR");
+  }();
+  if (pt && !other && d <= 64) return d <= 16 ? 19 : (d <= 32 ? 20 : (d <= 48 ? 21 : 22));
+  if (pt && !other && d <= 80 && !std::getenv("SDW_ATTN_D80_BKV64")) return 23;
   // split-S pipeline (variants 10-13): correct, but measured 5 % SLOWER than the whole-tile variants (self-attention
   // 64x64, d = 40, batch 32: 1838 vs 1746 us, profiles/r01_attn_bench_split_s.txt) — the softmax warps' S waits were a
   // symptom, the MUFU + TMEM-read floor is what binds — so it is opt-in: SDW_ATTN_SPLIT=1
@@ -924,8 +961,8 @@ int plan_attention(const AttnDesc& a, AttnLaunch* L) {
   AttnLaunchImpl* I = reinterpret_cast<AttnLaunchImpl*>(L->storage);
   std::memset(I, 0, sizeof(*I));
   I->variant = variant_for(a.d);
-  const int bkv = (I->variant == 5 || I->variant == 6 || I->variant == 9) ? 64 : 128;
-  const int dvp_tab[18] = {16, 32, 48, 64, 80, 160, 48, 48, 48, 80, 16, 32, 48, 64, 16, 32, 48, 64};
+  const int bkv = (I->variant == 5 || I->variant == 6 || I->variant == 9 || I->variant == 18 || I->variant == 23) ? 64 : 128;
+  const int dvp_tab[24] = {16, 32, 48, 64, 80, 160, 48, 48, 48, 80, 16, 32, 48, 64, 16, 32, 48, 64, 48, 16, 32, 48, 64, 80};
   const int dvp = dvp_tab[I->variant];
   AttnKParams& p = I->p;
   p.Nq = a.Nq; p.Nk = a.Nk; p.d = a.d; p.heads = a.heads;
@@ -978,6 +1015,12 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     case 11: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 32, 128, 2, 1, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 32, 128, 2, 1>::SMEM, stream, I->p)); break;
     case 12: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 2, 1, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 2, 1>::SMEM, stream, I->p)); break;
     case 13: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 64, 128, 2, 1, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 64, 128, 2, 1>::SMEM, stream, I->p)); break;
+    case 19: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 16, 128, 2, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 16, 128, 2, 1, 1>::SMEM, stream, I->p)); break;
+    case 20: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 32, 128, 2, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 32, 128, 2, 1, 1>::SMEM, stream, I->p)); break;
+    case 21: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 2, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 2, 1, 1>::SMEM, stream, I->p)); break;
+    case 22: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 64, 128, 2, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 64, 128, 2, 1, 1>::SMEM, stream, I->p)); break;
+    case 23: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<2, 80, 64, 2, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<2, 80, 64, 2, 1, 1>::SMEM, stream, I->p)); break;
+    case 18: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 64, 2, 2, 0>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 64, 2, 2>::SMEM, stream, I->p)); break;
     case 14: SDW_CUDA_OK(launch_pdl(attn_pair_kernel<16>, I->grid, dim3(ATTP_THREADS), AttnCfg<1, 16, 128, 2, 1>::SMEM, stream, I->p)); break;
     case 15: SDW_CUDA_OK(launch_pdl(attn_pair_kernel<32>, I->grid, dim3(ATTP_THREADS), AttnCfg<1, 32, 128, 2, 1>::SMEM, stream, I->p)); break;
     case 16: SDW_CUDA_OK(launch_pdl(attn_pair_kernel<48>, I->grid, dim3(ATTP_THREADS), AttnCfg<1, 48, 128, 2, 1>::SMEM, stream, I->p)); break;
