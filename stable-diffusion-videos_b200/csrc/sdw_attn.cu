@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
       const int kv0 = j * BKV;
       const bool ragged = kv0 + BKV > p.Nk;
       bool need_slow = (j == 0) || ragged;
+      bool p_stored = false;  // PT: the fast path has already put P_j into tensor memory
       float alpha = 1.f;
 
       if (!need_slow) {
@@ -408,6 +409,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
           uint32_t(&cur)[32] = (c & 1) ? vb : va;
           uint32_t(&nxt)[32] = (c & 1) ? va : vb;
           if (c + 1 < BKV / 32) tmem_ld_32x32(t_s + (c + 1) * 32, nxt);  // in flight while this chunk is exponentiated
+          uint32_t pkc[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float x0 = __uint_as_float(cur[i]), x1 = __uint_as_float(cur[i + 1]);
@@ -417,12 +419,23 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
             upk2(fma2(pk2(x0, x1), sl2_2, nmb_2), t0, t1);
             const float e0 = ex2f(t0), e1 = ex2f(t1);
             sm2[(i >> 1) & 1] = add2(sm2[(i >> 1) & 1], pk2(e0, e1));
-            pk[c * 16 + (i >> 1)] = pack_h2(e0, e1);
+            if (PT) pkc[i >> 1] = pack_h2(e0, e1);
+            else pk[c * 16 + (i >> 1)] = pack_h2(e0, e1);
+          }
+          if (PT) {
+            // P chunks go to tensor memory as they are produced (the store overlaps the next chunk's exponentials and
+            // the row never holds all 64 packed registers); the P columns are free once PV_{j-1} has completed
+            if (c == 0 && j > 0) {
+              mbar_wait(pv_done, (j - 1) & 1);
+              tc_fence_after();
+            }
+            tmem_st_32x16(tmem + lane_base + Cfg::P_COL + c * 16, pkc);
           }
           if (c + 1 < BKV / 32) tmem_ld_wait();
         }
         const float m_t = fmaxf(mx[0], mx[1]);
         need_slow = __any_sync(0xffffffffu, (m_t - m_run) * sl2 > LAZY_LOG2);
+        p_stored = PT && !need_slow;
         if (!need_slow) {
           float s0, s1, s2, s3;
           upk2(sm2[0], s0, s1);
@@ -491,13 +504,15 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
       }
       if (PT) {
         // P_j -> tensor memory: row = this thread's lane, column c = keys (2c, 2c+1) as an fp16 pair (the TS-mode A layout)
-        const uint32_t t_p = tmem + lane_base + Cfg::P_COL;
+        if (!p_stored) {
+          const uint32_t t_p = tmem + lane_base + Cfg::P_COL;
 #pragma unroll
-        for (int c = 0; c < BKV / 32; ++c) {
-          uint32_t w[16];
+          for (int c = 0; c < BKV / 32; ++c) {
+            uint32_t w[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) w[i] = pk[c * 16 + i];
-          tmem_st_32x16(t_p + c * 16, w);
+            for (int i = 0; i < 16; ++i) w[i] = pk[c * 16 + i];
+            tmem_st_32x16(t_p + c * 16, w);
+          }
         }
         tmem_st_wait();
       } else {
@@ -901,6 +916,7 @@ static int attn_init() {
   if (int e = attn_set_attr<1, 48, 128, 2, 1, 0, 0, 1>()) return e;
   if (int e = attn_set_attr<1, 64, 128, 2, 1, 0, 0, 1>()) return e;
   if (int e = attn_set_attr<2, 80, 64, 2, 1, 0, 0, 1>()) return e;
+  if (int e = attn_set_attr<1, 48, 128, 3, 1, 0, 0, 1>()) return e;
   if (int e = attn_set_attr<1, 16, 128, 2, 1, 0, 1>()) return e;
   if (int e = attn_set_attr<1, 32, 128, 2, 1, 0, 1>()) return e;
   if (int e = attn_set_attr<1, 48, 128, 2, 1, 0, 1>()) return e;
@@ -915,6 +931,7 @@ static int variant_for(int d) {
   // experiments: SDW_ATTN_VARIANT=18 -> head dims 33..48 on the BKV = 64, double-buffered-S tile (2 CTAs per SM)
   static const int forced = [] { const char* e = std::getenv("SDW_ATTN_VARIANT"); return e ? std::atoi(e) : -1; }();
   if (forced == 18 && d > 32 && d <= 48) return 18;
+  if (forced == 24 && d > 32 && d <= 48) return 24;  // P in TMEM with a three-stage K/V ring
   // P in tensor memory + TS-mode PV (variants 19-22) for head dims <= 64: SDW_ATTN_PT=0 reverts to P in shared memory
   static const bool pt = [] { const char* e = std::getenv("SDW_ATTN_PT"); return !(e && e[0] == '0'); }();
   static const bool other = [] {
@@ -962,7 +979,7 @@ int plan_attention(const AttnDesc& a, AttnLaunch* L) {
   std::memset(I, 0, sizeof(*I));
   I->variant = variant_for(a.d);
   const int bkv = (I->variant == 5 || I->variant == 6 || I->variant == 9 || I->variant == 18 || I->variant == 23) ? 64 : 128;
-  const int dvp_tab[24] = {16, 32, 48, 64, 80, 160, 48, 48, 48, 80, 16, 32, 48, 64, 16, 32, 48, 64, 48, 16, 32, 48, 64, 80};
+  const int dvp_tab[25] = {16, 32, 48, 64, 80, 160, 48, 48, 48, 80, 16, 32, 48, 64, 16, 32, 48, 64, 48, 16, 32, 48, 64, 80, 48};
   const int dvp = dvp_tab[I->variant];
   AttnKParams& p = I->p;
   p.Nq = a.Nq; p.Nk = a.Nk; p.d = a.d; p.heads = a.heads;
@@ -1019,6 +1036,7 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     case 20: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 32, 128, 2, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 32, 128, 2, 1, 1>::SMEM, stream, I->p)); break;
     case 21: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 2, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 2, 1, 1>::SMEM, stream, I->p)); break;
     case 22: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 64, 128, 2, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 64, 128, 2, 1, 1>::SMEM, stream, I->p)); break;
+    case 24: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 3, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 3, 1, 1>::SMEM, stream, I->p)); break;
     case 23: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<2, 80, 64, 2, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<2, 80, 64, 2, 1, 1>::SMEM, stream, I->p)); break;
     case 18: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 64, 2, 2, 0>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 64, 2, 2>::SMEM, stream, I->p)); break;
     case 14: SDW_CUDA_OK(launch_pdl(attn_pair_kernel<16>, I->grid, dim3(ATTP_THREADS), AttnCfg<1, 16, 128, 2, 1>::SMEM, stream, I->p)); break;
