@@ -31,6 +31,8 @@ struct alignas(64) AttnKParams {
   float scale_log2e;     // d^-1/2 * log2(e)
   __half* out;
   int64_t out_ld;
+  int qt_per_cta;        // query tiles per CTA: > 1 only when all keys fit one KV tile (cross attention): K / V^T are
+                         // then loaded once and the TMEM / barrier set-up is amortised over the tiles
 };
 
 // SB = number of S accumulator buffers: 2 (double-buffered, one CTA per SM) or 1 (TMEM 256 columns and <= 113 KB of
@@ -97,12 +99,16 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
   uint64_t* p_ready = s_full + 2;
   uint64_t* pv_done = p_ready + 1;
   uint64_t* s_free = pv_done + 1;  // [2]  (SPLIT)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_free + 2);
+  uint64_t* q_empty = s_free + 2;  // query-tile loop: Q smem free (S of this tile issued and complete)
+  uint64_t* o_free = q_empty + 1;  //                  O accumulator read out by the epilogue
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * ATT_BQ;
   const int head = blockIdx.y, b = blockIdx.z;
   const int ntiles = (p.Nk + BKV - 1) / BKV;
+  // query tiles of this CTA; tile t of the CTA is tile (g0 + j) of every barrier's phase sequence (nqt > 1 => ntiles == 1)
+  const int qt_first = blockIdx.x * p.qt_per_cta;
+  const int nqt = SPLIT ? 1 : min(p.qt_per_cta, (p.Nq + ATT_BQ - 1) / ATT_BQ - qt_first);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.mapQ);
@@ -119,6 +125,8 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
     mbar_init(pv_done, 1);
     mbar_init(&s_free[0], 128);
     mbar_init(&s_free[1], 128);
+    mbar_init(q_empty, 1);
+    mbar_init(o_free, 128);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -135,9 +143,13 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
   if (warp == 0) {
     // ============================ TMA producer ============================================
     if (lane == 0) {
+      for (int t = 0; t < nqt; ++t) {
+      const int q0 = (qt_first + t) * ATT_BQ;
+      if (t > 0) mbar_wait(q_empty, (t - 1) & 1);
       mbar_expect_tx(q_full, Cfg::Q_BYTES);
 #pragma unroll
       for (int a = 0; a < DKA; ++a) tma_load_4d(&p.mapQ, q_full, q_smem + a * (ATT_BQ * 128), a * 64, q0, head, b);
+      if (t > 0) continue;  // single KV tile: K / V^T stay resident
       for (int j = 0; j < ntiles; ++j) {
         const int s = j % ST;
         mbar_wait(&kv_empty[s], ((j / ST) & 1) ^ 1);
@@ -150,6 +162,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
         for (int a = 0; a < BKV / 64; ++a)
           tma_load_4d(&p.mapV, &kv_full[s], v_smem + s * Cfg::V_STAGE + a * (DVP * 128), kv0 + a * 64, 0, head, b);
       }
+      }  // query tiles
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ================================================
@@ -158,18 +171,19 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
       constexpr uint32_t idesc_o = make_idesc_f16(ATT_BQ, DVP);
       const uint32_t q_addr = smem_u32(q_smem);
       const uint32_t p_addr = smem_u32(p_smem);
+      int g0 = 0;  // tiles issued by earlier query tiles of this CTA
       auto issue_s = [&](int j) {
         const int s = j % ST;
         mbar_wait(&kv_full[s], (j / ST) & 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(k_smem + s * Cfg::K_STAGE);
-        const uint32_t ts = tmem + (j % SB) * BKV;
+        const uint32_t ts = tmem + ((g0 + j) % SB) * BKV;
         for (int ks = 0; ks < p.dk_steps; ++ks) {
           const uint64_t da = make_desc_k_sw128(q_addr + (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32);
           const uint64_t db = make_desc_k_sw128(k_addr + (ks >> 2) * (BKV * 128) + (ks & 3) * 32);
           umma_f16_ss(ts, da, db, idesc_s, ks != 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[j % SB]);
+        umma_commit(&s_full[(g0 + j) % SB]);
       };
       constexpr uint32_t idesc_h = make_idesc_f16(ATT_BQ, 64);
       auto issue_half = [&](int j, int h) {  // S_j[:, 64h .. 64h+63] = Q K_j[64h .. 64h+63]^T
@@ -186,7 +200,9 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
         }
         umma_commit(&s_full[h]);
       };
-      mbar_wait(q_full, 0);
+      for (int t = 0; t < nqt; ++t) {
+      g0 = t * ntiles;
+      mbar_wait(q_full, t & 1);
       tc_fence_after();
       if (SPLIT) {
         issue_half(0, 0);
@@ -194,6 +210,11 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
       } else {
         issue_s(0);
         if (SB == 2 && ntiles > 1) issue_s(1);
+        if (nqt > 1) umma_commit(q_empty);  // Q smem may be refilled once S of this (only) KV tile has completed
+      }
+      if (t > 0) {
+        mbar_wait(o_free, (t - 1) & 1);  // the previous query tile's epilogue has read O out
+        tc_fence_after();
       }
       for (int j = 0; j < ntiles; ++j) {
         if (SPLIT && j + 1 < ntiles) {
@@ -205,7 +226,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
           tc_fence_after();
           issue_half(j + 1, 1);
         }
-        mbar_wait(p_ready, j & 1);
+        mbar_wait(p_ready, (g0 + j) & 1);
         tc_fence_after();
         // single S buffer: the softmax has consumed S_j (p_ready), so S_{j+1} goes first and overlaps PV_j
         if (!SPLIT && SB == 1 && j + 1 < ntiles) issue_s(j + 1);
@@ -225,6 +246,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
         umma_commit(&kv_empty[s]);
         if (SB == 2 && j + 2 < ntiles) issue_s(j + 2);
       }
+      }  // query tiles
     }
   } else {
     // ============================ softmax / correction / epilogue ============================
@@ -232,10 +254,13 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t t_o = tmem + lane_base + Cfg::O_COL;
-    float m_run = -INFINITY, l_run = 0.f;
     const float sl2 = p.scale_log2e;
     uint8_t* p_row = p_smem + r * 128;
     const int sw = r & 7;
+    for (int t = 0; t < nqt; ++t) {
+    const int q0 = (qt_first + t) * ATT_BQ;
+    const int g0 = t * ntiles;
+    float m_run = -INFINITY, l_run = 0.f;
 
     // Two softmax paths per KV tile (the FlashAttention-4 "lazy rescale" idea):
     //  fast : exponentials are taken against the row's REFERENCE max m_run (the true running max as of the last slow
@@ -386,9 +411,9 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
     uint32_t pk[BKV / 2];  // P_j of this row, packed fp16 pairs
 
     for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(&s_full[j % SB], (j / SB) & 1);
+      mbar_wait(&s_full[(g0 + j) % SB], ((g0 + j) / SB) & 1);
       tc_fence_after();
-      const uint32_t t_s = tmem + lane_base + (j % SB) * BKV;
+      const uint32_t t_s = tmem + lane_base + ((g0 + j) % SB) * BKV;
       const int kv0 = j * BKV;
       const bool ragged = kv0 + BKV > p.Nk;
       bool need_slow = (j == 0) || ragged;
@@ -417,7 +442,9 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
             mx[1] = fmaxf(mx[1], x1);
             float t0, t1;
             upk2(fma2(pk2(x0, x1), sl2_2, nmb_2), t0, t1);
-            const float e0 = ex2f(t0), e1 = ex2f(t1);
+            // POLY (with PT): one exponential of every POLY-th pair runs on the FMA pipe (1 / (2 POLY) of all scores)
+            const float e0 = ex2f(t0);
+            const float e1 = (PT && POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == 0) ? ex2_poly(t1) : ex2f(t1);
             sm2[(i >> 1) & 1] = add2(sm2[(i >> 1) & 1], pk2(e0, e1));
             if (PT) pkc[i >> 1] = pack_h2(e0, e1);
             else pk[c * 16 + (i >> 1)] = pack_h2(e0, e1);
@@ -426,7 +453,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
             // P chunks go to tensor memory as they are produced (the store overlaps the next chunk's exponentials and
             // the row never holds all 64 packed registers); the P columns are free once PV_{j-1} has completed
             if (c == 0 && j > 0) {
-              mbar_wait(pv_done, (j - 1) & 1);
+              mbar_wait(pv_done, (g0 + j - 1) & 1);
               tc_fence_after();
             }
             tmem_st_32x16(tmem + lane_base + Cfg::P_COL + c * 16, pkc);
@@ -487,7 +514,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
       }
       if (j > 0) {
         // P smem and the O accumulator are free once PV_{j-1} has completed
-        mbar_wait(pv_done, (j - 1) & 1);
+        mbar_wait(pv_done, (g0 + j - 1) & 1);
         tc_fence_after();
         if (need_slow && __any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll
@@ -533,7 +560,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
     }
     }  // !SPLIT
     // ---- epilogue: O / l -> fp16 ------------------------------------------------------------
-    mbar_wait(pv_done, (ntiles - 1) & 1);
+    mbar_wait(pv_done, (g0 + ntiles - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.f / l_run;
     const int row = q0 + r;
@@ -567,6 +594,11 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
         }
       }
     }
+    if (nqt > 1) {  // O has been read out: the MMA warp may start the next query tile's PV
+      tc_fence_before();
+      mbar_arrive(o_free);
+    }
+    }  // query tiles
   }
 
   tc_fence_before();
@@ -917,6 +949,9 @@ static int attn_init() {
   if (int e = attn_set_attr<1, 64, 128, 2, 1, 0, 0, 1>()) return e;
   if (int e = attn_set_attr<2, 80, 64, 2, 1, 0, 0, 1>()) return e;
   if (int e = attn_set_attr<1, 48, 128, 3, 1, 0, 0, 1>()) return e;
+  if (int e = attn_set_attr<1, 48, 128, 2, 1, 1, 0, 1>()) return e;
+  if (int e = attn_set_attr<1, 48, 128, 2, 1, 2, 0, 1>()) return e;
+  if (int e = attn_set_attr<1, 48, 128, 2, 1, 3, 0, 1>()) return e;
   if (int e = attn_set_attr<1, 16, 128, 2, 1, 0, 1>()) return e;
   if (int e = attn_set_attr<1, 32, 128, 2, 1, 0, 1>()) return e;
   if (int e = attn_set_attr<1, 48, 128, 2, 1, 0, 1>()) return e;
@@ -932,6 +967,7 @@ static int variant_for(int d) {
   static const int forced = [] { const char* e = std::getenv("SDW_ATTN_VARIANT"); return e ? std::atoi(e) : -1; }();
   if (forced == 18 && d > 32 && d <= 48) return 18;
   if (forced == 24 && d > 32 && d <= 48) return 24;  // P in TMEM with a three-stage K/V ring
+  if (forced >= 25 && forced <= 27 && d > 32 && d <= 48) return forced;  // P in TMEM + 1/2, 1/4, 1/6 of the exps on the FMA pipe
   // P in tensor memory + TS-mode PV (variants 19-22) for head dims <= 64: SDW_ATTN_PT=0 reverts to P in shared memory
   static const bool pt = [] { const char* e = std::getenv("SDW_ATTN_PT"); return !(e && e[0] == '0'); }();
   static const bool other = [] {
@@ -979,14 +1015,28 @@ int plan_attention(const AttnDesc& a, AttnLaunch* L) {
   std::memset(I, 0, sizeof(*I));
   I->variant = variant_for(a.d);
   const int bkv = (I->variant == 5 || I->variant == 6 || I->variant == 9 || I->variant == 18 || I->variant == 23) ? 64 : 128;
-  const int dvp_tab[25] = {16, 32, 48, 64, 80, 160, 48, 48, 48, 80, 16, 32, 48, 64, 16, 32, 48, 64, 48, 16, 32, 48, 64, 80, 48};
+  const int dvp_tab[28] = {16, 32, 48, 64, 80, 160, 48, 48, 48, 80, 16, 32, 48, 64, 16, 32, 48, 64, 48, 16, 32, 48, 64, 80, 48, 48, 48, 48};
   const int dvp = dvp_tab[I->variant];
   AttnKParams& p = I->p;
   p.Nq = a.Nq; p.Nk = a.Nk; p.d = a.d; p.heads = a.heads;
   p.dk_steps = (a.d + 15) / 16;
   p.scale_log2e = (1.f / std::sqrt(static_cast<float>(a.d))) * 1.4426950408889634f;
   p.out = a.out; p.out_ld = a.out_ld;
-  I->grid = dim3((a.Nq + ATT_BQ - 1) / ATT_BQ, a.heads, a.B);
+  {
+    // cross attention (all keys in one KV tile): several query tiles per CTA, as long as >= ~3 waves of CTAs remain
+    const int bkv_v = (I->variant == 5 || I->variant == 6 || I->variant == 9 || I->variant == 18 || I->variant == 23) ? 64 : 128;
+    const int qtiles = (a.Nq + ATT_BQ - 1) / ATT_BQ;
+    int qt = 1;
+    static const int qt_env = [] { const char* e = std::getenv("SDW_ATTN_QT"); return e ? std::atoi(e) : 0; }();
+    const bool pair_or_split = (I->variant >= 10 && I->variant <= 17);
+    if (a.Nk <= bkv_v && !pair_or_split) {
+      qt = qt_env > 0 ? qt_env : 1;  // opt-in (SDW_ATTN_QT=8) until validated on hardware
+      while (qt > 1 && static_cast<int64_t>((qtiles + qt - 1) / qt) * a.heads * a.B < 148 * 2 * 3) qt >>= 1;
+      qt = std::max(1, std::min(qt, qtiles));
+    }
+    p.qt_per_cta = qt;
+    I->grid = dim3((qtiles + qt - 1) / qt, a.heads, a.B);
+  }
   {
     uint64_t dims[4] = {static_cast<uint64_t>(a.d), static_cast<uint64_t>(a.Nq), static_cast<uint64_t>(a.heads),
                         static_cast<uint64_t>(a.B)};
@@ -1036,6 +1086,9 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     case 20: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 32, 128, 2, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 32, 128, 2, 1, 1>::SMEM, stream, I->p)); break;
     case 21: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 2, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 2, 1, 1>::SMEM, stream, I->p)); break;
     case 22: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 64, 128, 2, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 64, 128, 2, 1, 1>::SMEM, stream, I->p)); break;
+    case 25: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 2, 1, 1, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 2, 1, 1>::SMEM, stream, I->p)); break;
+    case 26: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 2, 1, 2, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 2, 1, 1>::SMEM, stream, I->p)); break;
+    case 27: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 2, 1, 3, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 2, 1, 1>::SMEM, stream, I->p)); break;
     case 24: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 128, 3, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 128, 3, 1, 1>::SMEM, stream, I->p)); break;
     case 23: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<2, 80, 64, 2, 1, 0, 0, 1>, I->grid, dim3(ATT_THREADS), AttnCfg<2, 80, 64, 2, 1, 1>::SMEM, stream, I->p)); break;
     case 18: SDW_CUDA_OK(launch_pdl(attn_fwd_kernel<1, 48, 64, 2, 2, 0>, I->grid, dim3(ATT_THREADS), AttnCfg<1, 48, 64, 2, 2>::SMEM, stream, I->p)); break;
