@@ -177,6 +177,7 @@ typedef struct sdw_gemm_desc {
   int32_t et;                /* 0 auto, 1 never, 2 require: TMA-store epilogue with a TMA-fed residual ring.  With mode 2 the
                               * V^T rows are written through TMA, which clips the token extent at 16-byte granularity: the
                               * vt_ld padding up to the next multiple of 8 tokens may receive finite filler values */
+  int32_t as;                /* 0 auto, 1 never, 2 require: activation rows of an M pair stay in shared memory across its N tiles */
 } sdw_gemm_desc;
 
 int sdw_gemm(const sdw_gemm_desc* desc, void* stream);

@@ -66,6 +66,7 @@ int sdw_gemm(const sdw_gemm_desc* c, void* stream) {
   d.cl = c->cl;
   d.tr = c->tr;
   d.et = c->et;
+  d.as = c->as;
   GemmLaunch L;
   if (int e = plan_gemm(d, &L)) return e;
   return launch_gemm(L, static_cast<cudaStream_t>(stream));

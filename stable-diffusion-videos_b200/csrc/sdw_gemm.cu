@@ -469,6 +469,23 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
     const int epi_bytes = p.epi_tma ? G2_EPI_OUT + G2_EPI_BIAS + (d.resid ? G2_RES_STAGES * G2_RES_STAGE : 0) : G2_EPI_OLD;
     p.nstages = std::min(8, (G2_SMEM_USABLE - G2_BAR_BYTES - epi_bytes) / (a_stage + b_stage));
     SDW_REQUIRE(p.nstages >= 2, "no room for a two-stage operand pipeline");
+    // A-stationary: (kchunks + 1) resident activation slots, the ring carries weights only
+    p.a_stationary = 0;
+    p.a_slots = 0;
+    {
+      static const int as_env = [] { const char* e = std::getenv("SDW_GEMM_AS"); return e ? std::atoi(e) : 0; }();
+      const int slots = kchunks + 1;
+      const int b_st = std::min(8, (G2_SMEM_USABLE - G2_BAR_BYTES - epi_bytes - slots * 16384) / b_stage);
+      const bool can_as = L->cl == 2 && nsub == 1 && d.conv == 0 && !d.b_batched && !reuse && kchunks <= 7 && slots <= 8 &&
+                          p.n_tiles >= 3 && p.m_pairs >= 74 && b_st >= 3;
+      if (d.as == 2) SDW_REQUIRE(can_as, "A-stationary needs a 1x1 / linear GEMM with K <= 448, >= 3 N tiles and >= 74 M pairs");
+      if (can_as && d.as != 1 && (d.as == 2 || as_env == 1)) {
+        p.a_stationary = 1;
+        p.a_slots = slots;
+        p.nstages = b_st;
+        L->grid = dim3(2 * std::min(p.m_pairs, 74), 1, 1);
+      }
+    }
     if (p.epi_tma) {
       // output lattice: column, then the tile lattice (w, h, b) with the parity scatter folded into base + strides
       const int sw_ = std::min(bw, 32), sh_ = std::min(bh, 32 / sw_), sb_ = 32 / (sw_ * sh_);

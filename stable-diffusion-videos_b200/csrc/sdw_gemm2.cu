@@ -68,9 +68,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
   uint64_t* tmem_empty = tmem_full + 2;               // [2]  (leader's copy is the one in use)
   uint64_t* res_full = tmem_empty + 2;                // [G2_RES_STAGES]  residual ring (TMA epilogue)
   uint64_t* res_empty = res_full + G2_RES_STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty + G2_RES_STAGES);
+  uint64_t* a_full = res_empty + G2_RES_STAGES;  // [8]  A-stationary: resident activation slots
+  uint64_t* a_empty = a_full + 8;                // [8]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(a_empty + 8);
+  const bool AS = !TR && NSUB == 1 && CL == 2 && p.a_stationary != 0;
+  const int NA = p.a_slots;
   uint8_t* smem_a = smem + G2_BAR_BYTES;
-  uint8_t* smem_b = smem_a + STAGES * A_STAGE;
+  uint8_t* smem_b = smem_a + (AS ? NA : STAGES) * A_STAGE;
   uint8_t* epi_stage = smem_b + STAGES * Cfg::B_STAGE;  // classic: 8 x 2 KB; TMA: 8 x 4 KB slabs, 8 x 1 KB bias, ring
   uint8_t* epi_bias = epi_stage + G2_EPI_OUT;
   uint8_t* res_ring = epi_bias + G2_EPI_BIAS;
@@ -104,6 +108,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
       mbar_init(&res_full[r], 1);
       mbar_init(&res_empty[r], 4);  // the four warps (one per TMEM lane quarter) that own the chunk's parity
     }
+    for (int r = 0; r < 8; ++r) {
+      mbar_init(&a_full[r], 1);
+      mbar_init(&a_empty[r], 1);
+    }
     if (p.epi_tma) {
       tma_prefetch_desc(&p.mapOut);
       if (p.resid) tma_prefetch_desc(&p.mapRes);
@@ -135,14 +143,50 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
     n0 = n_tile * (NSUB * BN);
   };
 
+  // i-th tile of this cluster.  Default: t = cluster_id + i * nclusters (N fastest across clusters).  A-stationary: the
+  // cluster owns M pairs cluster_id, cluster_id + nclusters, ... and walks all N tiles of each in turn.
+  auto tile_index = [&](int i, int& t) {
+    if (AS) {
+      const int mp = cluster_id + (i / n_groups) * nclusters;
+      t = mp * n_groups + i % n_groups;
+      return mp < p.m_pairs;
+    }
+    t = cluster_id + i * nclusters;
+    return t < total_tiles;
+  };
+
   if (warp == 0) {
     // =========================== TMA producer (both CTAs) ==========================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = cluster_id; t < total_tiles; t += nclusters) {
+      uint32_t ga = 0;  // A-stationary: activation chunks loaded so far
+      int t;
+      for (int i = 0; tile_index(i, t); ++i) {
         int x0, y0, b0, n0;
         tile_coords(t, x0, y0, b0, n0);
+        if (AS) {
+          const bool first_n = (t % n_groups) == 0;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            if (first_n) {
+              const uint32_t slot = ga % NA;
+              mbar_wait(&a_empty[slot], ((ga / NA) & 1) ^ 1);
+              if (leader) mbar_expect_tx(&a_full[slot], 2 * A_STAGE);
+              tma_load_4d_2sm(&p.mapA[0], mapa_rank(smem_u32(&a_full[slot]), lead_rank), smem_a + slot * A_STAGE, kc * 64, x0,
+                              y0, b0);
+              ++ga;
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::B_STAGE);
+            tma_load_4d_2sm(&p.mapB, mapa_rank(smem_u32(&full_bar[stage]), lead_rank), smem_b + stage * Cfg::B_STAGE, kc * 64,
+                            n0 + static_cast<int>(rank) * Cfg::BH, 0, 0);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          continue;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE + Cfg::B_STAGE));
@@ -192,12 +236,35 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
       constexpr uint32_t idesc = make_idesc_f16(256, BN);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int t = cluster_id; t < total_tiles; t += nclusters, ++it) {
+      uint32_t ga_base = 0;  // A-stationary: first activation chunk of the current M pair
+      int t;
+      for (int it = 0; tile_index(it, t); ++it) {
         const int a = it % NBUF;
         mbar_wait(&tmem_empty[a], ((it / NBUF) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + a * Cfg::ACC_COLS;
+        if (AS) {
+          const int nidx = t % n_groups;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            const uint32_t g = ga_base + kc, slot = g % NA;
+            if (nidx == 0) mbar_wait(&a_full[slot], (g / NA) & 1);
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t da = make_desc_k_sw128(smem_u32(smem_a + slot * A_STAGE));
+            const uint64_t db = make_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ss_2cta(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(&empty_bar[stage], 0b11);
+            if (nidx == n_groups - 1) umma_commit_2cta(&a_empty[slot], 0b11);  // last N tile of this M pair
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          if (nidx == n_groups - 1) ga_base += p.kchunks;
+          umma_commit_2cta(&tmem_full[a], 0b11);
+          continue;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -239,7 +306,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
     // of the epilogue by up to G2_RES_STAGES chunks, across tile boundaries
     if (NSUB == 1 && p.epi_tma && p.resid && lane == 0) {
       uint32_t gc = 0;
-      for (int t = cluster_id; t < total_tiles; t += nclusters) {
+      int t;
+      for (int i = 0; tile_index(i, t); ++i) {
         int x0, y0, b0, n0;
         tile_coords(t, x0, y0, b0, n0);
         const int nch = (max(0, min(BN, p.N - n0)) + 31) >> 5;
@@ -253,9 +321,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
     }
   } else if (warp >= 4) {
     // =========================== epilogue (both CTAs, own 128 rows) ==================
-    int it = 0;
     EpiTmaState est;
-    for (int t = cluster_id; t < total_tiles; t += nclusters, ++it) {
+    int t;
+    for (int it = 0; tile_index(it, t); ++it) {
       int x0, y0, b0, n0;
       tile_coords(t, x0, y0, b0, n0);
       const int a = it % NBUF;

@@ -84,6 +84,10 @@ struct alignas(64) GemmKParams {
   CUtensorMap mapVt;        // GEMM_QKV_VT: V^T as (token, head * d + dd, sample), box (32 tokens, 32 rows), no swizzle
   int epi_tma;
   int nstages;              // mainloop pipeline depth (what the epilogue buffers leave of the 227 KB)
+  // A-stationary mainloop (short-K linears with several N tiles): a cluster keeps the activation rows of ONE M pair
+  // resident ((kchunks + 1) slots of 128 x 64) and walks all N tiles of it, so only weights stream through the ring
+  int a_stationary;
+  int a_slots;
   // epilogue
   const float* bias;        // [N] or null
   const float* rowvec;      // [B][rowvec_ld] per-sample vector added per column (time-embedding proj) or null
@@ -147,6 +151,7 @@ struct GemmDesc {
   int cl = 0;   // 0 = auto, 2 / 4: cluster size of the 2-CTA kernel
   int tr = 0;   // 0 = auto, 1 = never, 2 = require the tap-reuse mainloop (3x3 stride-1 conv, W % 16 == 0, H % 8 == 0)
   int et = 0;   // 0 = auto, 1 = never, 2 = require the TMA epilogue
+  int as = 0;   // 0 = auto, 1 = never, 2 = require the A-stationary mainloop
 };
 
 int plan_gemm(const GemmDesc& d, GemmLaunch* out);

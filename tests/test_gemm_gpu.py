@@ -21,7 +21,7 @@ def _tol(ref):
     return float(ref.abs().max()) * 2.0 ** -9 + 1e-3
 
 
-def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None, ver=0, nsub=0, cl=0, tr=0, et=0, out_buf=None, out_c0=0):
+def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None, ver=0, nsub=0, cl=0, tr=0, et=0, out_buf=None, out_c0=0, as_=0):
     """x: [B,H,W,C] fp16 cuda; returns NHWC fp16 output computed by the native kernel."""
     n = _native()
     B, H, W, Cc = x_nhwc.shape
@@ -66,6 +66,7 @@ def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn
         d.cl = cl
         d.tr = tr
         d.et = et
+        d.as_ = as_
         n.gemm(d)
     torch.cuda.synchronize()
     return out
@@ -448,3 +449,34 @@ def test_qkv_vt_tma_epilogue(Bn, Ntok, Cc, heads, et):
     # TMA clips the contiguous (token) extent at 16-byte granularity: the row padding up to the next multiple of 8 tokens
     # may receive finite filler values (sdwalk.h documents this); it must never be NaN / inf
     assert torch.isfinite(vt.float()).all()
+
+
+# ---- A-stationary mainloop: the activation rows of an M pair stay in shared memory across all of its N tiles ---------------
+@pytest.mark.parametrize("T,Cc,N,bn,mode,res", [
+    (20000, 320, 960, 256, 0, False),     # QKV-like, 4 N tiles, ragged last M pair
+    (19200, 320, 2560, 256, 1, False),    # GEGLU
+    (24000, 320, 640, 160, 0, True),      # residual ring + 4 N tiles
+    (19000, 64, 512, 128, 0, True),       # one K chunk
+    (19000, 448, 480, 160, 0, False),     # seven K chunks (eight slots)
+    (40000, 320, 960, 0, 0, True),        # several M pairs per cluster (slot ring wraps), auto BLOCK_N
+])
+def test_gemm_a_stationary(T, Cc, N, bn, mode, res):
+    x = _rand(1, 1, T, Cc, seed=95)
+    w = _rand(N, Cc, scale=Cc ** -0.5, seed=96)
+    bias = _rand(N, seed=97).float()
+    ncols = N // 2 if mode == 1 else N
+    resid = _rand(1, 1, T, ncols, seed=98) if res else None
+    if mode == 1:
+        blk = torch.arange(N, device="cuda")
+        b64, within = blk // 64, blk % 64
+        src = torch.where(within < 32, b64 * 32 + within, ncols + b64 * 32 + within - 32)
+        out = run_conv(x, w, 0, bias=bias[src].contiguous(), mode=1, ver=2, bn=bn, as_=2)
+        h = x.float().reshape(T, Cc) @ w.float().t() + bias
+        a, g = h.chunk(2, dim=-1)
+        ref = (a * Fn.gelu(g)).reshape(1, 1, T, ncols)
+    else:
+        out = run_conv(x, w.reshape(N, Cc, 1, 1), 0, bias=bias, resid=resid, ver=2, bn=bn, as_=2)
+        ref = ref_conv(x, w, 0, bias=bias, resid=resid)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= _tol(ref), (err, _tol(ref))
