@@ -1030,7 +1030,7 @@ int plan_attention(const AttnDesc& a, AttnLaunch* L) {
     static const int qt_env = [] { const char* e = std::getenv("SDW_ATTN_QT"); return e ? std::atoi(e) : 0; }();
     const bool pair_or_split = (I->variant >= 10 && I->variant <= 17);
     if (a.Nk <= bkv_v && !pair_or_split) {
-      qt = qt_env > 0 ? qt_env : 1;  // opt-in (SDW_ATTN_QT=8) until validated on hardware
+      qt = qt_env > 0 ? qt_env : 8;  // cross attention 64x64, d = 40: 153 -> 119 us (profiles/r01_attn_bench_qtile_loop.txt)
       while (qt > 1 && static_cast<int64_t>((qtiles + qt - 1) / qt) * a.heads * a.B < 148 * 2 * 3) qt >>= 1;
       qt = std::max(1, std::min(qt, qtiles));
     }
