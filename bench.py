@@ -110,6 +110,27 @@ def cpu_reference_leg(steps, warmup, threads=None):
             "s_per_frame": spf, "t_unet_s": t_unet, "t_vae_s": t_vae}
 
 
+def _stdout_to_stderr():
+    """Route fd 1 to stderr while the benchmark runs: libraries (NCCL prints its version line from C) must not put
+    anything on stdout next to the ONE JSON line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _restore_stdout(saved):
+    import ctypes
+
+    sys.stdout.flush()
+    try:
+        ctypes.CDLL(None).fflush(None)  # C stdio buffers (NCCL's printf) drain to stderr, not into the JSON stream
+    except Exception:
+        pass
+    os.dup2(saved, 1)
+    os.close(saved)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -121,6 +142,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     a = ap.parse_args()
+    saved_stdout = _stdout_to_stderr()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -131,6 +153,7 @@ def main():
         if rank != 0:
             return
         leg = cpu_reference_leg(max(1, a.steps), a.warmup)
+        _restore_stdout(saved_stdout)
         print(json.dumps({
             "impl": "reference", "metric": "frames/sec at 512x512 50-step SD-1.4", "value": leg["value"],
             "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
@@ -344,7 +367,9 @@ def main():
     if not a.no_cpu_baseline and world == 1:
         res["cpu_baseline"] = {k: v for k, v in cpu_reference_leg(1, 0).items()
                                if k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(res))
+    _restore_stdout(saved_stdout)
+    print(json.dumps(res), flush=True)
+    saved_stdout = _stdout_to_stderr()  # teardown chatter stays off stdout too
     if world > 1:
         dist.destroy_process_group()
 
