@@ -3,15 +3,19 @@
 //
 //   O[b, q, h*d:(h+1)*d] = softmax(Q_h K_h^T * d^-1/2) V_h          per (batch b, head h), fp16 in / fp16 out
 //
-// One CTA = one 128-query tile of one (b, h).  Nothing but Q, K, V^T tiles and the O tile touches HBM:
+// One CTA = one 128-query tile of one (b, h) (several tiles in turn when all keys fit one KV tile: cross attention).
+// Nothing but Q, K, V^T tiles and the O tile touches HBM:
 //   warp 0    : TMA producer.  Q tile once; per KV tile a K box [BKV x dk] and a V^T box [dv x BKV]
 //               (SWIZZLE_128B, head dim zero-filled up to 64*DKA by TMA OOB) into a STAGES-deep ring.
-//   warp 1    : MMA issuer.  S_j = Q K_j^T  (M=128, N=BKV, fp32 in TMEM, double-buffered) and
-//               O += P_j V_j (A = P_j fp16 from shared memory, N = DVP, fp32 in TMEM).
-//   warps 2-5 : online softmax, thread = query row.  tcgen05.ld S_j, running max / sum in fp32
-//               (ex2.approx on pre-scaled scores), rescale O in TMEM only when a row max moved,
-//               write P_j to shared memory in the UMMA K-major 128B-swizzled layout, finally O / l -> fp16.
-// Ordering is carried by mbarriers only (s_full, p_ready, pv_done, kv_full/empty).
+//   warp 1    : MMA issuer.  S_j = Q K_j^T  (M=128, N=BKV, fp32 in TMEM) and O += P_j V_j (N = DVP, fp32 in TMEM).
+//               Shipped variants for head dims <= 80 (PT = 1): A = P_j read from TENSOR MEMORY (TS-mode tcgen05.mma);
+//               legacy / head dim 160: A = P_j from shared memory.
+//   warps 2-5 : online softmax, thread = query row.  tcgen05.ld S_j, reference-max ("lazy") exponentials in fp32 with
+//               packed FFMA2 / FADD2, exact slow path when a row max moves by more than 2^8 (O rescaled in TMEM),
+//               P_j written back to tensor memory as fp16 pairs chunk by chunk (tcgen05.st), finally O / l -> fp16.
+// Ordering is carried by mbarriers only (s_full, p_ready, pv_done, kv_full/empty, q_empty/o_free for the tile loop).
+// Opt-in experiment variants kept for the record (all measured, none faster): split-S pipeline, two threads per query
+// row (attn_pair_kernel), BKV = 64 with double-buffered S, exponentials on the FMA pipe — see variant_for().
 #include "sdw_internal.h"
 #include "sdw_ptx.cuh"
 

@@ -11,8 +11,17 @@
 //                         signalled on the LEADER's full barrier (cta_group::2 TMA, mapa'd barrier address).
 //   warp 1 (leader)     : MMA issuer, 4 x UMMA(M=256, N=BN, K=16) per K block; tcgen05.commit multicast frees the
 //                         smem stage in both CTAs / publishes the accumulator to both epilogues.
-//   warps 4-11 (both)   : epilogue on the CTA's own 128 rows, two warps per TMEM lane quarter (sdw_gemm_epi.cuh), then a remote arrive on the
-//                         leader's tmem_empty barrier.
+//   warp 2 (both CTAs)  : residual producer of the TMA epilogue (one thread; a 4-deep ring of [128 x 32] chunks).
+//   warps 4-11 (both)   : epilogue on the CTA's own 128 rows, two warps per TMEM lane quarter (sdw_gemm_epi.cuh), then a
+//                         remote arrive on the leader's tmem_empty barrier.
+//
+// Mainloop flavours (all in this kernel; chosen per GEMM by plan_gemm, sdw_gemm.cu):
+//   per-tap      one activation box per (tap, channel chunk)              every conv / linear (the original form)
+//   TR = 1       tap reuse: one (8+2)-row box per (channel chunk, kx) feeds the three ky taps      3x3 stride-1 convs
+//   a_stationary the activation rows of an M pair stay resident across its N tiles (opt-in, no gain measured)
+//   CL = 4       activation tile TMA-multicast to two CTA pairs (opt-in, slower)
+// Shared memory is carved at run time: [barriers 1 KB | operand ring | epilogue buffers]; the planner sizes the ring
+// from what the chosen epilogue (classic: 16 KB, TMA: 40-72 KB) leaves of the 227 KB.
 #include "sdw_gemm_epi.cuh"
 #include "sdw_internal.h"
 #include "sdw_ptx.cuh"
