@@ -181,6 +181,9 @@ typedef struct sdw_gemm_desc {
 } sdw_gemm_desc;
 
 int sdw_gemm(const sdw_gemm_desc* desc, void* stream);
+/* planner introspection, host only (also in plan-only mode): out = {kernel version, BLOCK_N, accumulators, cluster size,
+ * tap reuse, TMA epilogue, pipeline stages, A-stationary, grid size, tile w, tile h, tile b} */
+int sdw_debug_plan(const sdw_gemm_desc* desc, int32_t out[12]);
 
 /* fused attention on tcgen05 (tests / tooling): O = softmax(Q K^T d^-1/2) V per (batch, head).
  * q [B][Nq][q_ld], k [B][Nk][k_ld] with head h at columns h*d; vt [B][heads][d][vt_ld] = V transposed;

@@ -43,9 +43,31 @@ int sdw_latents_init(const void* latents, int dtype_is_f16, float init_noise_sig
                       static_cast<cudaStream_t>(stream));
 }
 
+static int to_desc(const sdw_gemm_desc* c, GemmDesc& d);
+
+// planner introspection (host only; works in plan-only mode without a GPU): what plan_gemm chose for this descriptor
+int sdw_debug_plan(const sdw_gemm_desc* c, int32_t out[12]) {
+  SDW_REQUIRE(c != nullptr && out != nullptr, "null");
+  GemmDesc d;
+  if (int e = to_desc(c, d)) return e;
+  GemmLaunch L;
+  if (int e = plan_gemm(d, &L)) return e;
+  out[0] = L.ver; out[1] = L.bn; out[2] = L.nsub; out[3] = L.cl; out[4] = L.tr;
+  out[5] = L.p.epi_tma; out[6] = L.p.nstages; out[7] = L.p.a_stationary;
+  out[8] = static_cast<int32_t>(L.grid.x); out[9] = L.p.bw; out[10] = L.p.bh; out[11] = L.p.bb;
+  return 0;
+}
+
 int sdw_gemm(const sdw_gemm_desc* c, void* stream) {
   SDW_REQUIRE(c != nullptr, "null desc");
   GemmDesc d;
+  if (int e = to_desc(c, d)) return e;
+  GemmLaunch L;
+  if (int e = plan_gemm(d, &L)) return e;
+  return launch_gemm(L, static_cast<cudaStream_t>(stream));
+}
+
+static int to_desc(const sdw_gemm_desc* c, GemmDesc& d) {
   d.A = static_cast<const __half*>(c->A);
   d.C = c->C; d.W = c->W; d.H = c->H; d.B = c->B;
   d.sW = c->sW; d.sH = c->sH; d.sB = c->sB;
@@ -67,9 +89,7 @@ int sdw_gemm(const sdw_gemm_desc* c, void* stream) {
   d.tr = c->tr;
   d.et = c->et;
   d.as = c->as;
-  GemmLaunch L;
-  if (int e = plan_gemm(d, &L)) return e;
-  return launch_gemm(L, static_cast<cudaStream_t>(stream));
+  return 0;
 }
 
 int sdw_attention(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* vt, int64_t vt_ld, int B,
