@@ -199,6 +199,9 @@ int sdw_groupnorm(const void* x, int64_t ldx, int B, int64_t P, int C, int G, co
 int sdw_layernorm(const void* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
                   void* y, int64_t ldy, void* stream);
 
+/* attention planner introspection, host only: out = {kernel variant, query tiles per CTA, grid x, y, z} */
+int sdw_debug_attention_plan(int B, int Nq, int Nk, int heads, int d, int32_t out[5]);
+
 /* pack an OIHW fp16 conv / [N][K] linear weight into the kernel's K-major [N][taps][Cp] layout */
 int sdw_pack_weight(const void* w_oihw, int N, int C, int kh, int kw, int geglu_interleave, void* out, void* stream);
 /* upsampler (nearest x2 + 3x3) weights folded to four 2x2 parity convs: out = 4 blocks of [N][4][ceil64(C)];

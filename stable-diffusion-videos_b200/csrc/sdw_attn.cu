@@ -1068,6 +1068,16 @@ int plan_attention(const AttnDesc& a, AttnLaunch* L) {
   return 0;
 }
 
+// planner introspection (host only): {variant, query tiles per CTA, grid.x, grid.y, grid.z}
+void attention_plan_info(const AttnLaunch& L, int out[5]) {
+  const AttnLaunchImpl* I = reinterpret_cast<const AttnLaunchImpl*>(L.storage);
+  out[0] = I->variant;
+  out[1] = I->p.qt_per_cta;
+  out[2] = static_cast<int>(I->grid.x);
+  out[3] = static_cast<int>(I->grid.y);
+  out[4] = static_cast<int>(I->grid.z);
+}
+
 int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
   if (int e = attn_init()) return e;
   const AttnLaunchImpl* I = reinterpret_cast<const AttnLaunchImpl*>(L.storage);

@@ -122,6 +122,23 @@ int sdw_layernorm(const void* x, int64_t ldx, int64_t rows, int C, const float* 
                    static_cast<cudaStream_t>(stream));
 }
 
+int sdw_debug_attention_plan(int B, int Nq, int Nk, int heads, int d, int32_t out[5]) {
+  SDW_REQUIRE(out != nullptr, "null");
+  AttnDesc a;
+  // fake 16-byte aligned addresses: nothing is dereferenced by the planner (tensor maps are validated in plan-only mode)
+  a.q = reinterpret_cast<const __half*>(uintptr_t(1) << 30); a.q_ld = static_cast<int64_t>(heads) * d;
+  a.k = reinterpret_cast<const __half*>(uintptr_t(2) << 30); a.k_ld = a.q_ld;
+  a.vt = reinterpret_cast<const __half*>(uintptr_t(3) << 30); a.vt_ld = (Nk + 7) / 8 * 8;
+  a.B = B; a.Nq = Nq; a.Nk = Nk; a.heads = heads; a.d = d;
+  a.out = reinterpret_cast<__half*>(uintptr_t(4) << 30); a.out_ld = a.q_ld;
+  AttnLaunch L;
+  if (int e = plan_attention(a, &L)) return e;
+  int v[5];
+  attention_plan_info(L, v);
+  for (int i = 0; i < 5; ++i) out[i] = v[i];
+  return 0;
+}
+
 int sdw_pack_weight_up4(const void* w_oihw, int N, int C, void* out, void* stream) {
   return pack_weight_up4(w_oihw, N, C, out, static_cast<cudaStream_t>(stream));
 }

@@ -192,6 +192,7 @@ struct AttnLaunch {
 bool attn_supported(int d);
 int plan_attention(const AttnDesc& a, AttnLaunch* L);
 int launch_attention(const AttnLaunch& L, cudaStream_t stream);
+void attention_plan_info(const AttnLaunch& L, int out[5]);
 
 // ---------------------------------------------------------------------------
 // fp32 helper kernels (sdw_elem.cu)

@@ -95,3 +95,30 @@ def test_opt_in_variants_are_refused_outside_their_domain(native):
         _plan(native, 1, 1, 4096, 320, 320, 0, **{"as_": 2})   # A-stationary needs >= 3 N tiles and >= 74 M pairs
     p = _plan(native, 1, 1, 131072, 320, 2560, 0, mode=1, resid=False, **{"as_": 2})
     assert p["a_stationary"] == 1 and p["grid"] == 148, p
+
+
+def _attn(n, B, Nq, Nk, heads, d):
+    out = (C.c_int32 * 5)()
+    n.check(n.lib().sdw_debug_attention_plan(B, Nq, Nk, heads, d, out))
+    return dict(zip(("variant", "qt", "gx", "gy", "gz"), list(out)))
+
+
+def test_attention_variants_for_the_sd14_head_dims(native):
+    # head dims <= 64: P in tensor memory + TS-mode PV (variants 19-22); 80: the BKV = 64 P-in-TMEM tile; 160: double-buffered S
+    assert _attn(native, 32, 4096, 4096, 8, 40)["variant"] == 21
+    assert _attn(native, 32, 1024, 1024, 8, 80)["variant"] == 23
+    assert _attn(native, 32, 256, 256, 8, 160)["variant"] == 5
+    assert _attn(native, 16, 9216, 9216, 5, 64)["variant"] == 22   # SD-2.1, 96x96 latent
+    p = _attn(native, 32, 4096, 4096, 8, 40)
+    assert (p["qt"], p["gx"], p["gy"], p["gz"]) == (1, 32, 8, 32)   # self attention: one query tile per CTA
+
+
+def test_cross_attention_loops_over_query_tiles(native):
+    p = _attn(native, 32, 4096, 77, 8, 40)     # all 77 keys in one KV tile: 8 query tiles per CTA, K / V^T loaded once
+    assert p["qt"] == 8 and p["gx"] == 4 and p["gx"] * p["qt"] * 128 == 4096
+    p = _attn(native, 2, 4096, 77, 8, 40)      # small batch: keep >= ~3 waves of CTAs rather than long loops
+    assert p["qt"] < 8 and p["gx"] * p["qt"] * 128 >= 4096
+    p = _attn(native, 32, 300, 77, 8, 40)      # ragged query count
+    assert p["gx"] * p["qt"] * 128 >= 300
+    with pytest.raises(native.SdwError):
+        _attn(native, 1, 64, 64, 1, 512)        # the VAE's d = 512 goes through the unfused path
