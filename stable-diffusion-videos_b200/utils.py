@@ -1,8 +1,8 @@
 """Host-side helpers mirroring stable_diffusion_videos/utils.py for the hot path's neighbours.
 
 `slerp` (utils.py:42-66) routes CUDA tensors through the native batched kernel.  `get_timesteps_arr`
-(utils.py:12-39, librosa) and `make_video_pyav` (utils.py:69-128, torchvision/PyAV) are OUT of the hot-path scope
-(SURVEY.md §8f rows 1-2): they delegate to those libraries when installed and fail loudly otherwise.
+(utils.py:12-39) uses librosa when installed and the numpy / scipy restatement in audio.py otherwise (SURVEY.md §8f
+row 2).  `make_video_pyav` (utils.py:69-128, torchvision/PyAV) is OUT of scope: it delegates or fails loudly.
 """
 import torch
 
@@ -21,11 +21,14 @@ def slerp(t, v0, v1, DOT_THRESHOLD=0.9995):
 
 
 def get_timesteps_arr(audio_filepath, offset, duration, fps=30, margin=1.0, smooth=0.0):
+    """Audio-reactive schedule T in [0, 1] (reference utils.py:12-39).  Uses librosa when it is installed (bit-for-bit
+    the reference's calls); otherwise the numpy / scipy restatement in `audio.py` (WAV input)."""
     try:
-        import librosa  # noqa: F401
-    except ImportError as exc:  # pragma: no cover - librosa is absent in this image
-        raise ImportError("get_timesteps_arr needs librosa (audio-reactive schedule, reference utils.py:12-39); it is "
-                          "a host pre-step outside the native hot path — pass an explicit T instead") from exc
+        import librosa
+    except ImportError:
+        from . import audio
+
+        return audio.get_timesteps_arr(audio_filepath, offset, duration, fps=fps, margin=margin, smooth=smooth)
     import numpy as np
 
     y, sr = librosa.load(audio_filepath, offset=offset, duration=duration)
