@@ -163,6 +163,42 @@ class LMSDiscreteScheduler:
         return sample + sum(c * d for c, d in zip(coeffs, reversed(self.derivatives)))
 
 
+class EulerDiscreteScheduler:
+    """diffusers EulerDiscreteScheduler, deterministic settings (s_churn = 0, timestep_spacing "linspace", linear sigma
+    interpolation): the published Euler sampler of Karras et al. 2022 (Alg. 2).  diffusers is not installed; restated
+    from the paper and the scheduler's documented behaviour, step by step (not via the coefficient form the product uses)."""
+
+    def __init__(self, num_train_timesteps=1000, prediction_type="epsilon"):
+        self.num_train_timesteps = num_train_timesteps
+        self.prediction_type = prediction_type
+        ac = _alphas_cumprod(n=num_train_timesteps).numpy()
+        self._sig_all = np.array(((1 - ac) / ac) ** 0.5)
+        self.init_noise_sigma = float(np.concatenate([self._sig_all[::-1], [0.0]]).astype(np.float32).max())
+
+    def set_timesteps(self, n):
+        ts = np.linspace(0, self.num_train_timesteps - 1, n, dtype=float)[::-1].copy()
+        sig = np.interp(ts, np.arange(0, len(self._sig_all)), self._sig_all)
+        self.sigmas = np.concatenate([sig, [0.0]]).astype(np.float32)
+        self.timesteps = torch.from_numpy(ts)
+
+    def _index(self, t):
+        return int((self.timesteps == float(t)).nonzero()[0].item())
+
+    def scale_model_input(self, sample, t):
+        s = float(self.sigmas[self._index(t)])
+        return sample / ((s ** 2 + 1) ** 0.5)
+
+    def step(self, model_output, timestep, sample):
+        i = self._index(timestep)
+        s = float(self.sigmas[i])
+        if self.prediction_type == "epsilon":
+            x0 = sample - s * model_output
+        else:
+            x0 = model_output * (-s / (s ** 2 + 1) ** 0.5) + (sample / (s ** 2 + 1))
+        derivative = (sample - x0) / s
+        return sample + derivative * (float(self.sigmas[i + 1]) - s)
+
+
 def make_scheduler(kind, prediction_type="epsilon"):
-    return {"pndm": PNDMScheduler, "ddim": DDIMScheduler, "lms": LMSDiscreteScheduler}[kind](
-        prediction_type=prediction_type)
+    return {"pndm": PNDMScheduler, "ddim": DDIMScheduler, "lms": LMSDiscreteScheduler,
+            "euler": EulerDiscreteScheduler}[kind](prediction_type=prediction_type)

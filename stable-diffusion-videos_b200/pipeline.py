@@ -171,7 +171,13 @@ class StableDiffusionWalkPipeline:
             raise FileNotFoundError(f"no safetensors weights under {root / sub}")
 
         sc = json.loads((root / "scheduler" / "scheduler_config.json").read_text())
-        kind = {"PNDMScheduler": "pndm", "DDIMScheduler": "ddim", "LMSDiscreteScheduler": "lms"}[sc["_class_name"]]
+        kinds = {"PNDMScheduler": "pndm", "DDIMScheduler": "ddim", "LMSDiscreteScheduler": "lms",
+                 "EulerDiscreteScheduler": "euler"}
+        if sc["_class_name"] not in kinds:
+            raise NotImplementedError(f"scheduler {sc['_class_name']} has no native plan (deterministic linear multistep "
+                                      f"rules only: {sorted(kinds)}); stochastic samplers (Euler ancestral) and "
+                                      "DPM-Solver are not implemented")
+        kind = kinds[sc["_class_name"]]
         ucfg.prediction_type = sc.get("prediction_type", "epsilon")
         sch = SCHEDULERS[kind](num_train_timesteps=sc.get("num_train_timesteps", 1000),
                                beta_start=sc.get("beta_start", 0.00085), beta_end=sc.get("beta_end", 0.012),

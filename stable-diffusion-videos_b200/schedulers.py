@@ -3,7 +3,7 @@
 The reference drives a diffusers scheduler object through `set_timesteps`, `timesteps`, `init_noise_sigma`,
 `scale_model_input` and `step` (stable_diffusion_pipeline.py:394-426).  Every scheduler it accepts that is
 deterministic (PNDM/PLMS — the SD-1.4 default, DDIM with eta = 0 — the SD-2.1 default, LMS —
-examples/make_music_video.py:15-17) is a LINEAR multistep rule, so here `set_timesteps` pre-computes, in fp64 on
+examples/make_music_video.py:15-17, Euler) is a LINEAR multistep rule, so here `set_timesteps` pre-computes, in fp64 on
 the host, one `sdw_step_coef` per step (include/sdwalk.h); the update itself runs in one fused fp32 CUDA kernel
 together with classifier-free guidance.  `beta_schedule="scaled_linear"`, `steps_offset=1`,
 `set_alpha_to_one=False`, `clip_sample=False` as the reference forces (stable_diffusion_pipeline.py:85-110).
@@ -204,4 +204,47 @@ class LMSDiscreteScheduler(_Base):
         return steps
 
 
-SCHEDULERS = {"pndm": PNDMScheduler, "ddim": DDIMScheduler, "lms": LMSDiscreteScheduler}
+class EulerDiscreteScheduler(_Base):
+    """Euler (Karras et al. 2022, Alg. 2 with s_churn = 0 — the deterministic form the reference's scheduler union
+    accepts, stable_diffusion_pipeline.py:71-78).  derivative = (x - x0) / sigma, x' = x + (sigma_next - sigma) * derivative:
+      epsilon      : derivative = eps                                   -> c_x = 1,                       c_e = dt
+      v_prediction : x0 = -sigma/sqrt(sigma^2+1) * v + x / (sigma^2+1)  -> c_x = 1 + dt*sigma/(sigma^2+1), c_e = dt/sqrt(sigma^2+1)
+    Same sigma table / linspace timesteps / input scaling as K-LMS."""
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        if self.config.prediction_type not in ("epsilon", "v_prediction"):
+            raise ValueError("Euler native plan supports epsilon and v_prediction")
+        ac = self.alphas_cumprod
+        sig = ((1 - ac) / ac) ** 0.5
+        self.init_noise_sigma = float(np.concatenate([sig[::-1], [0.0]]).astype(np.float32).max())
+
+    def set_timesteps(self, n, device=None):
+        self.num_inference_steps = n
+        nt = self.config.num_train_timesteps
+        ts = np.linspace(0, nt - 1, n, dtype=float)[::-1].copy()
+        ac = self.alphas_cumprod
+        sig = ((1 - ac) / ac) ** 0.5
+        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        self.sigmas = np.concatenate([sig, [0.0]]).astype(np.float32)
+        self.timesteps = ts
+
+    def scale_model_input(self, sample, timestep=None):
+        i = int(np.nonzero(self.timesteps == float(timestep))[0][0])
+        return sample / ((float(self.sigmas[i]) ** 2 + 1) ** 0.5)
+
+    def plan(self):
+        steps = []
+        for i in range(self.num_inference_steps):
+            s, s_next = float(self.sigmas[i]), float(self.sigmas[i + 1])
+            dt = s_next - s
+            if self.config.prediction_type == "epsilon":
+                cx, ce = 1.0, dt
+            else:
+                cx, ce = 1.0 + dt * s / (s * s + 1.0), dt / (s * s + 1.0) ** 0.5
+            steps.append(dict(c_x=cx, c_e=[ce, 0, 0, 0, 0], hist_slot=[0, 0, 0, 0], use_x_base=0, save_x_base=0,
+                              push_slot=-1, in_scale=1.0 / (s * s + 1.0) ** 0.5))
+        return steps
+
+
+SCHEDULERS = {"pndm": PNDMScheduler, "ddim": DDIMScheduler, "lms": LMSDiscreteScheduler, "euler": EulerDiscreteScheduler}

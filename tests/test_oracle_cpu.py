@@ -64,7 +64,8 @@ def _replay(plan, x0, eps_list, sigma):
 
 @pytest.mark.parametrize("kind,n,pt", [("pndm", 50, "epsilon"), ("pndm", 4, "epsilon"), ("pndm", 1, "epsilon"),
                                         ("ddim", 50, "epsilon"), ("ddim", 50, "v_prediction"),
-                                        ("lms", 50, "epsilon"), ("lms", 3, "epsilon")])
+                                        ("lms", 50, "epsilon"), ("lms", 3, "epsilon"), ("euler", 50, "epsilon"),
+                                        ("euler", 7, "v_prediction")])
 def test_product_scheduler_plan_equals_oracle_scheduler(kind, n, pt):
     from stable_diffusion_videos_b200.schedulers import SCHEDULERS
 
@@ -82,7 +83,7 @@ def test_product_scheduler_plan_equals_oracle_scheduler(kind, n, pt):
         xo = o.step(e, t, xo)
     xn = _replay(plan, x0, eps, p.init_noise_sigma)
     assert float((xo - xn).abs().max()) <= 1e-6 * float(xo.abs().max()) + 1e-9
-    if kind == "lms":
+    if kind in ("lms", "euler"):
         for i, t in enumerate(o.timesteps):
             assert abs(float(o.scale_model_input(torch.ones(1), t)) - plan[i]["in_scale"]) < 1e-6
 
