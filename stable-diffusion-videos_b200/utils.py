@@ -1,8 +1,7 @@
 """Host-side helpers mirroring stable_diffusion_videos/utils.py for the hot path's neighbours.
 
 `slerp` (utils.py:42-66) routes CUDA tensors through the native batched kernel.  `get_timesteps_arr`
-(utils.py:12-39) uses librosa when installed and the numpy / scipy restatement in audio.py otherwise (SURVEY.md §8f
-row 2).  `make_video_pyav` (utils.py:69-128, torchvision/PyAV) is OUT of scope: it delegates or fails loudly.
+(utils.py:12-39) runs on the numpy / scipy restatement in audio.py.  `make_video_pyav` (utils.py:69-128, torchvision/PyAV) is OUT of scope: it delegates or fails loudly.
 """
 import torch
 
@@ -21,29 +20,18 @@ def slerp(t, v0, v1, DOT_THRESHOLD=0.9995):
 
 
 def get_timesteps_arr(audio_filepath, offset, duration, fps=30, margin=1.0, smooth=0.0):
-    """Audio-reactive schedule T in [0, 1] (reference utils.py:12-39).  Uses librosa when it is installed (bit-for-bit
-    the reference's calls); otherwise the numpy / scipy restatement in `audio.py` (WAV input)."""
+    """Audio-reactive schedule T in [0, 1] (reference utils.py:12-39).  The signal processing is this package's own
+    numpy / scipy restatement (`audio.py`); librosa, when installed, is used only as the decoder
+    for non-WAV inputs."""
+    from . import audio
+
     try:
         import librosa
+
+        y, sr = librosa.load(audio_filepath, offset=offset, duration=duration)
     except ImportError:
-        from . import audio
-
-        return audio.get_timesteps_arr(audio_filepath, offset, duration, fps=fps, margin=margin, smooth=smooth)
-    import numpy as np
-
-    y, sr = librosa.load(audio_filepath, offset=offset, duration=duration)
-    D = librosa.stft(y, n_fft=2048, hop_length=512)
-    D_harmonic, D_percussive = librosa.decompose.hpss(D, margin=margin)
-    y_percussive = librosa.istft(D_percussive, length=len(y))
-    spec_raw = librosa.feature.melspectrogram(y=y_percussive, sr=sr)
-    spec_max = np.amax(spec_raw, axis=0)
-    spec_norm = (spec_max - np.min(spec_max)) / np.ptp(spec_max)
-    x_norm = np.linspace(0, spec_norm.shape[-1], spec_norm.shape[-1])
-    y_norm = np.cumsum(spec_norm)
-    y_norm /= y_norm[-1]
-    x_resize = np.linspace(0, y_norm.shape[-1], int(duration * fps))
-    T = np.interp(x_resize, x_norm, y_norm)
-    return T * (1 - smooth) + np.linspace(0.0, 1.0, T.shape[0]) * smooth
+        y, sr = audio.load(audio_filepath, offset=offset, duration=duration)
+    return audio.timesteps_from_signal(y, sr, duration, fps=fps, margin=margin, smooth=smooth)
 
 
 def make_video_pyav(frames_or_frame_dir="./frames", audio_filepath=None, fps=30, audio_offset=0, audio_duration=2,
