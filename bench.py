@@ -74,17 +74,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_leg(steps, warmup, threads=None):
-    """time the oracle (restated diffusers CPU path, fp32) on a bounded sample: `steps` batch-2 UNet forwards at the
-    64x64 latent + ONE VAE decode; frame time = 51 * t_unet + t_vae (frames are cost-identical)."""
+def cpu_reference_leg(steps, warmup, budget_s=150.0):
+    """time the oracle (restated diffusers CPU path, fp32) on a bounded sample: up to `steps` batch-2 UNet forwards at
+    the 64x64 latent (after up to `warmup` untimed ones) + ONE VAE decode, all host cores; frame time = 51 * t_unet +
+    t_vae (frames are cost-identical).  The sample stops early once `budget_s` of CPU time is spent; the number of
+    forwards that really ran is reported."""
     import torch
 
     from oracle.unet import UNet2DConditionModel, UNetConfig
     from oracle.vae import AutoencoderKLDecoder, VAEConfig
 
-    if threads:
-        torch.set_num_threads(threads)
-    threads = torch.get_num_threads()  # torch's default: one thread per physical core of the box
+    # BASELINE.md §3: all host cores, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    threads = torch.get_num_threads()
     torch.manual_seed(0)
     unet = UNet2DConditionModel(UNetConfig.sd14()).eval()
     vae = AutoencoderKLDecoder(VAEConfig()).eval()
@@ -92,22 +95,29 @@ def cpu_reference_leg(steps, warmup, threads=None):
     ctx = torch.randn(2, 77, 768)
     z = torch.randn(1, 4, 64, 64)
     with torch.no_grad():
-        # bounded sample: a batch-2 fp32 UNet forward costs ~1 min on a shared host, so at most 1 warm-up + 2 timed
-        steps = max(1, min(steps, 2))
-        for _ in range(min(1, warmup) if steps > 1 else 0):
+        t_begin = time.perf_counter()
+        warm_run = 0
+        for _ in range(max(0, warmup)):
             unet(x, torch.tensor(981), ctx)
+            warm_run += 1
+            if time.perf_counter() - t_begin > budget_s / 4:
+                break
         t0 = time.perf_counter()
-        for _ in range(steps):
+        steps_run = 0
+        for _ in range(max(1, steps)):
             unet(x, torch.tensor(981), ctx)
-        t_unet = (time.perf_counter() - t0) / steps
+            steps_run += 1
+            if time.perf_counter() - t_begin > budget_s:
+                break
+        t_unet = (time.perf_counter() - t0) / steps_run
         t0 = time.perf_counter()
         vae.decode(z)
         t_vae = time.perf_counter() - t0
     spf = 51 * t_unet + t_vae
     return {"value": 1.0 / spf, "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": f"{steps} timed batch-2 UNet forwards (64x64 latent, fp32) + 1 VAE decode on {threads} threads; "
-                      f"s/frame = 51*{t_unet:.3f} + {t_vae:.3f} = {spf:.1f}",
-            "s_per_frame": spf, "t_unet_s": t_unet, "t_vae_s": t_vae}
+            "sample": f"{steps_run} timed (+{warm_run} warm-up) batch-2 UNet forwards (64x64 latent, fp32) + 1 VAE decode "
+                      f"on {threads} threads; s/frame = 51*{t_unet:.3f} + {t_vae:.3f} = {spf:.1f}",
+            "s_per_frame": spf, "t_unet_s": t_unet, "t_vae_s": t_vae, "steps_run": steps_run, "warmup_run": warm_run}
 
 
 def _stdout_to_stderr():
@@ -156,9 +166,11 @@ def main():
         _restore_stdout(saved_stdout)
         print(json.dumps({
             "impl": "reference", "metric": "frames/sec at 512x512 50-step SD-1.4", "value": leg["value"],
-            "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "unit": "frames/s", "n_gpus": a.gpus, "steps": leg["steps_run"], "warmup": leg["warmup_run"],
             "ms_per_step": leg["t_unet_s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": workload, "reference_arm": leg["sample"]},
+            "dtype": "f32", "data": "synthetic", "config": {"workload": workload, "reference_arm": leg["sample"],
+                                            "step": "one batch-2 UNet forward of the restated diffusers CPU path; "
+                                                    "frames/s = 1 / (51 x step + VAE decode)"},
             "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": leg["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -198,7 +210,7 @@ def main():
     del usd, vsd
     pipe.unet.state, pipe.vae.state = None, None
     eng.set_scheduler(pipe.scheduler, a.inference_steps, 7.5)
-    eng._plan_key = (type(pipe.scheduler).__name__, a.inference_steps, 7.5)
+    eng._plan_key = pipe._plan_key(a.inference_steps, 7.5)
     n_unet_calls = eng.n_steps
 
     # ---- inputs: one clip's worth of interpolated (embedding, latent) pairs, resident on the device ------------
@@ -365,7 +377,7 @@ def main():
         "clocks": clk,
     }
     if not a.no_cpu_baseline and world == 1:
-        res["cpu_baseline"] = {k: v for k, v in cpu_reference_leg(1, 0).items()
+        res["cpu_baseline"] = {k: v for k, v in cpu_reference_leg(2, 1).items()
                                if k in ("value", "unit", "cores", "kind", "sample")}
     _restore_stdout(saved_stdout)
     print(json.dumps(res), flush=True)

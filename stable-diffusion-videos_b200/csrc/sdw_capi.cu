@@ -122,6 +122,8 @@ int sdw_layernorm(const void* x, int64_t ldx, int64_t rows, int C, const float* 
                    static_cast<cudaStream_t>(stream));
 }
 
+void sdw_debug_attention_trace(void* buf) { sdw::attention_set_trace(static_cast<long long*>(buf)); }
+
 int sdw_debug_attention_plan(int B, int Nq, int Nk, int heads, int d, int32_t out[5]) {
   SDW_REQUIRE(out != nullptr, "null");
   AttnDesc a;

@@ -112,8 +112,11 @@ class Engine:
                     if strict:
                         raise N.SdwError(f"unexpected parameter {name}")
                     continue
-                if tuple(t.shape) != tuple(shapes[name]) and t.numel() != expected[name]:
-                    raise N.SdwError(f"shape mismatch for {name}: {tuple(t.shape)} vs {shapes[name]}")
+                want, got = tuple(shapes[name]), tuple(t.shape)
+                # the only accepted alias: a 1x1 conv stored as a Linear weight or the reverse, (c_out, c_in) <->
+                # (c_out, c_in, 1, 1) (old VAE attention checkpoints, use_linear_projection models)
+                if got != want and got + (1, 1) != want and got != want + (1, 1):
+                    raise N.SdwError(f"shape mismatch for {name}: {got} vs {want}")
                 th = t.detach().to(device=self.device, dtype=torch.float16).contiguous()
                 keep.append(th)
                 N.check(lib.sdw_engine_load_param(self._h, name.encode(), N.ptr(th), C.c_int64(th.numel()),
@@ -162,6 +165,13 @@ class Engine:
         if tuple(latents.shape) != (F, self.unet_cfg.in_channels, h, w):
             raise ValueError(f"Unexpected latents shape, got {tuple(latents.shape)}, expected "
                              f"{(F, self.unet_cfg.in_channels, h, w)}")
+        D = self.unet_cfg.cross_attention_dim
+        if tuple(cond.shape) != (F, self.ctx_tokens, D):
+            raise ValueError(f"Unexpected text_embeddings shape, got {tuple(cond.shape)}, expected "
+                             f"{(F, self.ctx_tokens, D)}")
+        if self.guidance and (uncond is None or tuple(uncond.shape) != (1, self.ctx_tokens, D)):
+            raise ValueError(f"Unexpected unconditional embedding shape, got "
+                             f"{None if uncond is None else tuple(uncond.shape)}, expected {(1, self.ctx_tokens, D)}")
         lat = latents.to(torch.float32).contiguous()
         cnd = cond.to(torch.float16).contiguous()
         unc = uncond.to(torch.float16).contiguous() if uncond is not None else None

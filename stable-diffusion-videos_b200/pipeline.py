@@ -199,6 +199,7 @@ class StableDiffusionWalkPipeline:
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = device
+        self._uncond_cache = {}  # embeddings live on the previous device / came from the previous encoder
         if hasattr(self.text_encoder, "to"):
             self.text_encoder = self.text_encoder.to(device)
         return self
@@ -226,6 +227,12 @@ class StableDiffusionWalkPipeline:
             eng.load_state_dict(self.unet.state, self.vae.state)
             self._engines = {key: eng}  # one resident engine (each carries its own packed weights)
         return eng
+
+    def _plan_key(self, num_inference_steps, guidance_scale):
+        """identity of the native coefficient plan + captured graph: scheduler instance AND its configuration"""
+        sc = self.scheduler.config
+        return (type(self.scheduler).__name__, id(self.scheduler), sc.num_train_timesteps, sc.beta_start, sc.beta_end,
+                sc.prediction_type, sc.steps_offset, int(num_inference_steps), float(guidance_scale))
 
     def _uncond(self, uncond_tokens):
         key = tuple(uncond_tokens)
@@ -313,7 +320,7 @@ class StableDiffusionWalkPipeline:
 
         # ---- native hot path: set-up (P:394-401), loop (P:412-430), decode + post-process (P:432-438, 450)
         eng = self._engine(height // 8, width // 8, B, do_cfg)
-        plan_key = (type(self.scheduler).__name__, num_inference_steps, float(guidance_scale))
+        plan_key = self._plan_key(num_inference_steps, guidance_scale)
         if eng._plan_key != plan_key:
             eng.set_scheduler(self.scheduler, num_inference_steps, guidance_scale)
             eng._plan_key = plan_key

@@ -1,7 +1,8 @@
 """Host-side helpers mirroring stable_diffusion_videos/utils.py for the hot path's neighbours.
 
 `slerp` (utils.py:42-66) routes CUDA tensors through the native batched kernel.  `get_timesteps_arr`
-(utils.py:12-39) runs on the numpy / scipy restatement in audio.py.  `make_video_pyav` (utils.py:69-128, torchvision/PyAV) is OUT of scope: it delegates or fails loudly.
+(utils.py:12-39) runs on the numpy / scipy restatement in audio.py.  `make_video_pyav` (utils.py:69-128) keeps the reference semantics (audio excerpt muxed as AAC) on top of
+torchvision/PyAV when those exist and fails loudly otherwise — it never writes a mute file for an audio walk.
 """
 import torch
 
@@ -34,14 +35,24 @@ def get_timesteps_arr(audio_filepath, offset, duration, fps=30, margin=1.0, smoo
     return audio.timesteps_from_signal(y, sr, duration, fps=fps, margin=margin, smooth=smooth)
 
 
-def make_video_pyav(frames_or_frame_dir="./frames", audio_filepath=None, fps=30, audio_offset=0, audio_duration=2,
-                    sr=22050, output_filepath="output.mp4", glob_pattern="*.png"):
+def _video_writer():
+    """torchvision.io.write_video (PyAV / ffmpeg underneath) when the installed torchvision still ships it."""
     try:
         from torchvision.io import write_video
     except ImportError as exc:
         raise RuntimeError("make_video_pyav needs torchvision.io.write_video + PyAV/ffmpeg (reference "
-                           "utils.py:69-128); codec I/O is outside the native hot path — call walk(make_video=False) "
-                           "and mux the frame%06d.png files with ffmpeg") from exc
+                           "utils.py:69-128); no H.264 / AAC encoder exists in this image and codec I/O is outside the "
+                           "native hot path — call walk(make_video=False) and mux the frame%06d.png files (and the "
+                           "audio excerpt) with ffmpeg") from exc
+    return write_video
+
+
+def make_video_pyav(frames_or_frame_dir="./frames", audio_filepath=None, fps=30, audio_offset=0, audio_duration=2,
+                    sr=22050, output_filepath="output.mp4", glob_pattern="*.png"):
+    """Reference utils.py:69-128: frames (a directory of images, or a (T, C, H, W) uint8 tensor) -> H.264 mp4
+    (crf 10, yuv420p); with `audio_filepath`, the excerpt [audio_offset, audio_offset + audio_duration) is resampled to
+    `sr`, mixed to mono and muxed as AAC.  Never drops the audio silently: without an encoder this raises."""
+    write_video = _video_writer()
     from pathlib import Path
 
     import numpy as np
@@ -49,11 +60,23 @@ def make_video_pyav(frames_or_frame_dir="./frames", audio_filepath=None, fps=30,
 
     output_filepath = str(output_filepath)
     if isinstance(frames_or_frame_dir, (str, Path)):
-        frames = None
-        for img in sorted(Path(frames_or_frame_dir).glob(glob_pattern)):
-            frame = torch.from_numpy(np.asarray(Image.open(img).convert("RGB"))).unsqueeze(0)
-            frames = frame if frames is None else torch.cat([frames, frame])
+        frames = [torch.from_numpy(np.asarray(Image.open(img).convert("RGB")).copy())
+                  for img in sorted(Path(frames_or_frame_dir).glob(glob_pattern))]
+        frames = torch.stack(frames)  # THWC already
     else:
-        frames = frames_or_frame_dir
-    write_video(output_filepath, frames, fps=fps, options={"crf": "10", "pix_fmt": "yuv420p"})
+        frames = frames_or_frame_dir.permute(0, 2, 3, 1)  # TCHW -> THWC (utils.py:102)
+    opts = {"crf": "10", "pix_fmt": "yuv420p"}
+    if audio_filepath:
+        try:
+            import librosa
+
+            y, sr = librosa.load(audio_filepath, sr=sr, mono=True, offset=audio_offset, duration=audio_duration)
+        except ImportError:
+            from . import audio
+
+            y, sr = audio.load(audio_filepath, offset=audio_offset, duration=audio_duration, sr=sr)
+        write_video(output_filepath, frames, fps=fps, audio_array=torch.tensor(y).unsqueeze(0), audio_fps=sr,
+                    audio_codec="aac", options=opts)
+    else:
+        write_video(output_filepath, frames, fps=fps, options=opts)
     return output_filepath

@@ -9,6 +9,11 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    import torch
+
+    # every "fp32 reference" computed with torch on the GPU must be real fp32, not cuDNN / cuBLAS TF32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     config.addinivalue_line("markers", "gpu: needs a CUDA GPU (run on the B200 box via gpurun)")
 
 

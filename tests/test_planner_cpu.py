@@ -104,13 +104,17 @@ def _attn(n, B, Nq, Nk, heads, d):
 
 
 def test_attention_variants_for_the_sd14_head_dims(native):
-    # head dims <= 64: P in tensor memory + TS-mode PV (variants 19-22); 80: the BKV = 64 P-in-TMEM tile; 160: double-buffered S
-    assert _attn(native, 32, 4096, 4096, 8, 40)["variant"] == 21
-    assert _attn(native, 32, 1024, 1024, 8, 80)["variant"] == 23
+    # head dims <= 64 with more than one KV tile: the two-query-tile persistent kernel (variants 8-11, one CTA per SM);
+    # 80: the BKV = 64 P-in-TMEM tile; 160: double-buffered S
+    assert _attn(native, 32, 4096, 4096, 8, 40)["variant"] == 10
+    assert _attn(native, 32, 1024, 1024, 8, 80)["variant"] == 4
     assert _attn(native, 32, 256, 256, 8, 160)["variant"] == 5
-    assert _attn(native, 16, 9216, 9216, 5, 64)["variant"] == 22   # SD-2.1, 96x96 latent
+    assert _attn(native, 16, 9216, 9216, 5, 64)["variant"] == 11   # SD-2.1, 96x96 latent
+    assert _attn(native, 32, 4096, 77, 8, 40)["variant"] == 2       # single KV tile: the one-tile kernel with a query loop
     p = _attn(native, 32, 4096, 4096, 8, 40)
-    assert (p["qt"], p["gx"], p["gy"], p["gz"]) == (1, 32, 8, 32)   # self attention: one query tile per CTA
+    assert (p["qt"], p["gx"], p["gy"], p["gz"]) == (2, 148, 1, 1)   # persistent: 148 CTAs over 32 * 8 * 16 work items
+    p = _attn(native, 1, 576, 576, 5, 64)                           # fewer work items than SMs
+    assert (p["gx"], p["gy"], p["gz"]) == (15, 1, 1)
 
 
 def test_cross_attention_loops_over_query_tiles(native):
