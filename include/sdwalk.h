@@ -201,8 +201,8 @@ int sdw_layernorm(const void* x, int64_t ldx, int64_t rows, int C, const float* 
 
 /* attention planner introspection, host only: out = {kernel variant, query tiles per CTA, grid x, y, z} */
 int sdw_debug_attention_plan(int B, int Nq, int Nk, int heads, int d, int32_t out[5]);
-/* tooling: device buffer of 2 x 4096 x 5 int64 that CTA 0 of the two-tile attention kernel fills with clock64 stamps per
- * KV tile (wait start, S ready, row in registers, max done, P stored) for query tiles A and B; NULL switches it off */
+/* tooling: device buffer of 2 x 4096 x 8 int64 that CTA 0 of the two-tile attention kernel fills with clock64 stamps per
+ * KV tile (wait start, S ready, row in registers, max done, MUFU token held, burst issued, P stored) for query tiles A and B; NULL switches it off */
 void sdw_debug_attention_trace(void* buf);
 
 /* pack an OIHW fp16 conv / [N][K] linear weight into the kernel's K-major [N][taps][Cp] layout */

@@ -56,21 +56,30 @@ __device__ __forceinline__ float ex2f(float x) {
 // =============================================================================================
 // attn_pp_kernel
 // =============================================================================================
-static constexpr int PP_THREADS = 384;  // warpgroup 0: warp 0 TMA, warp 1 MMA(A), warp 2 MMA(B), warp 3 idle;
-                                        // warpgroup 1: softmax of query tile A; warpgroup 2: softmax of query tile B
-template <int DVP>
+// NS = softmax warpgroups per query tile.  NS = 1: thread = query row (128 score columns per thread and KV tile).
+// NS = 2: two threads per query row, 64 columns each (half maxima exchanged through shared memory, row sums merged in the
+// epilogue).  A single warp issues MUFU.EX2 only every ~11.4 cycles (8 is the pipe rate, tools/softmax_loop_bench.cu):
+// with one softmax warp per scheduler bursting at a time the XU pipe idles 30 % of the time; with NS = 2 every scheduler
+// holds four softmax warps, two of which burst together.
+template <int DVP, int NS>
 struct PPCfg {
   static constexpr int ST = 4;                       // K / V^T ring depth
+  static constexpr int THREADS = 128 + 256 * NS;     // warpgroup 0: warp 0 TMA, warp 1 MMA(A), warp 2 MMA(B), warp 3 idle;
+                                                     // then NS softmax warpgroups of query tile A, NS of query tile B
   static constexpr int Q_BYTES = ATT_BQ * 128;       // one 128 x 64 fp16 tile, SWIZZLE_128B
   static constexpr int K_STAGE = 128 * 128;          // BKV = 128 keys x 64 (zero-filled head dim) fp16
   static constexpr int V_STAGE = 2 * DVP * 128;      // V^T: two 64-key boxes of DVP rows
-  static constexpr int SMEM = 2 * Q_BYTES + ST * (K_STAGE + V_STAGE) + 1024 + 512;
+  static constexpr int XCH_BYTES = NS == 2 ? (2 * 2 * 2 * 128 + 2 * 2 * 128) * 4 : 0;  // half maxima [X][parity][half][row], sums [X][half][row]
+  static constexpr int SMEM = 2 * Q_BYTES + ST * (K_STAGE + V_STAGE) + XCH_BYTES + 1024 + 512;
   // tensor memory (512 columns, one CTA per SM): S_A S_B | P_A P_B | O_A O_B
   static constexpr int S_COL = 0, P_COL = 256, O_COL = 384;
+  static constexpr int REGS_SOFTMAX = NS == 2 ? 112 : 224, REGS_OTHER = NS == 2 ? 32 : 48;
   static_assert(DVP <= 64 && DVP % 16 == 0, "head dim <= 64");
+  static_assert(128 * REGS_OTHER + 256 * NS * REGS_SOFTMAX <= 65536 - 1024, "register file (an exact fit hung setmaxnreg.inc on hardware: keep slack)");
 };
 
-// named barriers 1 / 2 carry the MUFU token between the two softmax warpgroups (barrier 0 is __syncthreads)
+// named barriers 1 / 2 carry the MUFU token between the softmax warpgroups of query tile A and those of B, 3 / 4 pair the
+// two column halves of a query tile (NS = 2); barrier 0 is __syncthreads
 template <int ID>
 __device__ __forceinline__ void named_bar_sync(uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(threads) : "memory");
@@ -79,7 +88,7 @@ template <int ID>
 __device__ __forceinline__ void named_bar_arrive(uint32_t threads) {
   asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(threads) : "memory");
 }
-// volatile: stays between the token barriers (a plain asm could be scheduled across them)
+// volatile: stays behind the token barrier (a plain asm could be scheduled across it)
 __device__ __forceinline__ uint32_t ex2_ordered(uint32_t x) {
   uint32_t y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=r"(y) : "r"(x));
@@ -91,23 +100,27 @@ __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.syn
 template <int REGS>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
-template <int DVP>
-__global__ void __launch_bounds__(PP_THREADS, 1) attn_pp_kernel(const __grid_constant__ AttnKParams p) {
-  using Cfg = PPCfg<DVP>;
+template <int DVP, int NS, int TOKEN>
+__global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(const __grid_constant__ AttnKParams p) {
+  using Cfg = PPCfg<DVP, NS>;
   constexpr int ST = Cfg::ST, BKV = 128;
+  constexpr int COLS = BKV / NS, NCH = COLS / 32;   // score columns / 32-column chunks per softmax thread
+  constexpr uint32_t GROUP = 128 * NS;              // softmax threads per query tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;                          // [2][Q_BYTES]
   uint8_t* k_smem = q_smem + 2 * Cfg::Q_BYTES;     // [ST][K_STAGE]
   uint8_t* v_smem = k_smem + ST * Cfg::K_STAGE;    // [ST][V_STAGE]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + ST * Cfg::V_STAGE);
+  float* xch_max = reinterpret_cast<float*>(v_smem + ST * Cfg::V_STAGE);  // NS = 2: [X][parity][half][128]
+  float* xch_sum = xch_max + (NS == 2 ? 2 * 2 * 2 * 128 : 0);             //         [X][half][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xch_max) + Cfg::XCH_BYTES);
   uint64_t* q_full = bars;            // [2] TMA -> MMA(X)
   uint64_t* q_empty = q_full + 2;     // [2] MMA(X) commit -> TMA: every S of this work item has completed
   uint64_t* kv_full = q_empty + 2;    // [ST] TMA -> both MMA warps
   uint64_t* kv_empty = kv_full + ST;  // [ST] PV_A(j) and PV_B(j) commits (count 2) -> TMA
   uint64_t* s_full = kv_empty + ST;   // [2] MMA(X) commit -> softmax(X)
-  uint64_t* s_free = s_full + 2;      // [2] softmax(X) (128) -> MMA(X): the score row sits in registers
-  uint64_t* p_ready = s_free + 2;     // [2] softmax(X) (128) -> MMA(X): P_j is in tensor memory
+  uint64_t* s_free = s_full + 2;      // [2] softmax(X) (GROUP) -> MMA(X): the score rows sit in registers
+  uint64_t* p_ready = s_free + 2;     // [2] softmax(X) (GROUP) -> MMA(X): P_j is in tensor memory
   uint64_t* pv_done = p_ready + 2;    // [2] MMA(X) commit -> softmax(X): P columns / O accumulator free
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2);
 
@@ -122,8 +135,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_pp_kernel(const __grid_con
       mbar_init(&q_full[x], 1);
       mbar_init(&q_empty[x], 1);
       mbar_init(&s_full[x], 1);
-      mbar_init(&s_free[x], 128);
-      mbar_init(&p_ready[x], 128);
+      mbar_init(&s_free[x], GROUP);
+      mbar_init(&p_ready[x], GROUP);
       mbar_init(&pv_done[x], 1);
     }
     for (int s = 0; s < ST; ++s) {
@@ -144,7 +157,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_pp_kernel(const __grid_con
   pdl_launch_dependents();
 
   if (warp < 4) {
-    reg_dealloc<48>();
+    reg_dealloc<Cfg::REGS_OTHER>();
     if (warp == 0) {
       // ============================ TMA producer ============================================
       if (lane == 0) {
@@ -222,54 +235,68 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_pp_kernel(const __grid_con
     }
   } else {
     // ============================ softmax / correction / epilogue of query tile X ==============
-    reg_alloc<224>();
-    const int X = (warp >> 2) - 1;
+    reg_alloc<Cfg::REGS_SOFTMAX>();
+    const int g = (warp >> 2) - 1;
+    const int X = g / NS;            // query tile
+    const int hlf = g % NS;          // column half of the score tile (NS = 2)
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t t_s = tmem + lane_base + Cfg::S_COL + X * 128;
-    const uint32_t t_p = tmem + lane_base + Cfg::P_COL + X * 64;
+    const uint32_t t_s = tmem + lane_base + Cfg::S_COL + X * 128 + hlf * COLS;
+    const uint32_t t_p = tmem + lane_base + Cfg::P_COL + X * 64 + hlf * (COLS / 2);
     const uint32_t t_o = tmem + lane_base + Cfg::O_COL + X * 64;
     const float sl2 = p.scale_log2e;
-    const bool trace = p.dbg != nullptr && blockIdx.x == 0 && r == 0;
+    const bool trace = p.dbg != nullptr && blockIdx.x == 0 && r == 0 && hlf == 0;
     constexpr float LAZY_LOG2 = 8.f;
     int gt = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const int qp = w % p.qpairs, head = (w / p.qpairs) % p.heads, b = w / (p.qpairs * p.heads);
       float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < ntiles; ++j, ++gt) {
-        long long ts0 = 0, ts1 = 0, ts2 = 0, ts3 = 0;
+        long long ts0 = 0, ts1 = 0, ts2 = 0, ts3 = 0, ts4 = 0, ts5 = 0;
         if (trace) ts0 = clock64();
         mbar_wait(&s_full[X], gt & 1);
         tc_fence_after();
         if (trace) ts1 = clock64();
-        // ---- the whole score row into registers, then give the S columns back -------------------
-        uint32_t v[4][32];
+        // ---- this thread's score columns into registers, then give the S columns back -----------
+        uint32_t v[NCH][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, v[c]);
+        for (int c = 0; c < NCH; ++c) tmem_ld_32x32(t_s + c * 32, v[c]);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&s_free[X]);
         if (trace) ts2 = clock64();
-        const int kv0 = j * BKV;
-        if (kv0 + BKV > p.Nk) {  // ragged last tile: keys >= Nk do not exist
+        const int kv0 = j * BKV + hlf * COLS;
+        if (kv0 + COLS > p.Nk) {  // ragged last tile: keys >= Nk do not exist
 #pragma unroll
-          for (int i = 0; i < BKV; ++i)
+          for (int i = 0; i < COLS; ++i)
             if (kv0 + i >= p.Nk) v[i >> 5][i & 31] = 0xff800000u;  // -inf
         }
         // ---- row max, lazy reference update ------------------------------------------------------
-        float mx[4];
+        float m_t;
+        {
+          float mx[NCH];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float a0 = __uint_as_float(v[c][0]), a1 = __uint_as_float(v[c][1]);
+          for (int c = 0; c < NCH; ++c) {
+            float a0 = __uint_as_float(v[c][0]), a1 = __uint_as_float(v[c][1]);
 #pragma unroll
-          for (int i = 2; i < 32; i += 2) {
-            a0 = fmaxf(a0, __uint_as_float(v[c][i]));
-            a1 = fmaxf(a1, __uint_as_float(v[c][i + 1]));
+            for (int i = 2; i < 32; i += 2) {
+              a0 = fmaxf(a0, __uint_as_float(v[c][i]));
+              a1 = fmaxf(a1, __uint_as_float(v[c][i + 1]));
+            }
+            mx[c] = fmaxf(a0, a1);
           }
-          mx[c] = fmaxf(a0, a1);
+          m_t = mx[0];
+#pragma unroll
+          for (int c = 1; c < NCH; ++c) m_t = fmaxf(m_t, mx[c]);
         }
-        const float m_t = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        if (NS == 2) {  // the other half of the row lives in the partner warpgroup
+          float* slot = xch_max + ((X * 2 + (gt & 1)) * 2) * 128;
+          slot[hlf * 128 + r] = m_t;
+          if (X == 0) named_bar_sync<3>(GROUP);
+          else named_bar_sync<4>(GROUP);
+          m_t = fmaxf(m_t, slot[(hlf ^ 1) * 128 + r]);  // both threads of a row now hold the same maximum
+        }
         bool pv_waited = (j == 0);  // tile 0: the epilogue of the previous work item has waited for its last PV
         if (j == 0) {
           m_ref = m_t;
@@ -284,6 +311,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_pp_kernel(const __grid_con
           pv_waited = true;
 #pragma unroll
           for (int c = 0; c < DVP / 16; ++c) {
+            if (NS == 2 && (c & 1) != hlf) continue;  // the two threads of a row split the accumulator columns
             uint32_t o[16];
             tmem_ld_32x16(t_o + c * 16, o);
             tmem_ld_wait();
@@ -295,15 +323,17 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_pp_kernel(const __grid_con
         }
         if (trace) ts3 = clock64();
         // ---- exponentials against the reference max, P -> tensor memory chunk by chunk -------------
-        // The two softmax warpgroups share each scheduler's MUFU pipe.  Left alone they fall into lock step (both
+        // The softmax warps share each scheduler's MUFU pipe.  Left alone the two query tiles fall into lock step (both
         // exponentiate at half rate, then both do their FMA / pack / TMEM / barrier work with the pipe idle: measured
-        // 3086 cycles per A+B tile pair against 2048 of MUFU work, gpurun trace r02).  A token passed through two named
-        // barriers makes the 128-instruction MUFU bursts of A and B alternate instead, so one warpgroup's burst covers
-        // the other's non-MUFU phase.
+        // 3086 cycles per A+B tile pair against 2048 of MUFU work, profiles/r02_attn_pp_trace.txt).  A token passed
+        // through two named barriers makes the MUFU bursts of tile A and tile B alternate instead, so one tile's burst
+        // covers the other's non-MUFU phase.
         const float mb = m_ref * sl2;
         const uint64_t sl2_2 = pk2(sl2, sl2), nmb_2 = pk2(-mb, -mb);
+        uint64_t sm2[4] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
+        if (TOKEN) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NCH; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float t0, t1;
@@ -313,25 +343,28 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_pp_kernel(const __grid_con
           }
         }
         if (X == 0) {
-          if (gt > 0) named_bar_sync<2>(256);
+          if (gt > 0) named_bar_sync<2>(2 * GROUP);
         } else {
-          named_bar_sync<1>(256);
+          named_bar_sync<1>(2 * GROUP);
         }
+        if (trace) ts4 = clock64();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NCH; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[c][i] = ex2_ordered(v[c][i]);
         }
         {
           // ptxas is free to hoist a bar.arrive above independent MUFU instructions (it did): tie the token release to the
           // tail of the burst through a data dependency — the sign bits of a few late results, zero at run time
-          const uint32_t dep = (v[3][31] | v[3][30] | v[3][15] | v[2][31] | v[1][31] | v[0][31]) >> 31;
-          if (X == 0) named_bar_arrive<1>(256 + dep);
-          else named_bar_arrive<2>(256 + dep);
+          uint32_t dep = v[NCH - 1][31] | v[NCH - 1][30] | v[NCH - 1][15] | v[0][31];
+          if (NCH > 2) dep |= v[NCH - 2][31] | v[1][31];
+          dep >>= 31;
+          if (X == 0) named_bar_arrive<1>(2 * GROUP + dep);
+          else named_bar_arrive<2>(2 * GROUP + dep);
+          if (trace) ts5 = clock64() + dep;
         }
-        uint64_t sm2[4] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NCH; ++c) {
           uint32_t pkc[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -345,6 +378,27 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_pp_kernel(const __grid_con
           }
           tmem_st_32x16(t_p + c * 16, pkc);  // row = lane, column k = keys (2k, 2k+1) as an fp16 pair (TS-mode A layout)
         }
+        } else {
+          // free-running variant: no token, the scale / exponential / sum / pack work of a chunk is left to the instruction
+          // scheduler to interleave, P chunks leave as they are produced
+          if (!pv_waited) {
+            mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has read P_{j-1}: the P columns may be overwritten
+            tc_fence_after();
+          }
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            uint32_t pkc[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float t0, t1;
+              upk2(fma2(pk2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sl2_2, nmb_2), t0, t1);
+              const float e0 = ex2f(t0), e1 = ex2f(t1);
+              sm2[(i >> 1) & 3] = add2(sm2[(i >> 1) & 3], pk2(e0, e1));
+              pkc[i >> 1] = pack_h2(e0, e1);
+            }
+            tmem_st_32x16(t_p + c * 16, pkc);
+          }
+        }
         {
           float s0, s1, s2, s3, s4, s5, s6, s7;
           upk2(sm2[0], s0, s1);
@@ -357,11 +411,17 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_pp_kernel(const __grid_con
         tc_fence_before();
         mbar_arrive(&p_ready[X]);
         if (trace) {
-          long long* o = p.dbg + (static_cast<long long>(X) * 4096 + (gt & 4095)) * 5;
-          o[0] = ts0; o[1] = ts1; o[2] = ts2; o[3] = ts3; o[4] = clock64();
+          long long* o = p.dbg + (static_cast<long long>(X) * 4096 + (gt & 4095)) * 8;
+          o[0] = ts0; o[1] = ts1; o[2] = ts2; o[3] = ts3; o[4] = ts4; o[5] = ts5; o[6] = clock64();
         }
       }
       // ---- epilogue: O / l -> fp16 ------------------------------------------------------------
+      if (NS == 2) {  // the row sum is the sum of the two halves
+        xch_sum[(X * 2 + hlf) * 128 + r] = l_run;
+        if (X == 0) named_bar_sync<3>(GROUP);
+        else named_bar_sync<4>(GROUP);
+        l_run += xch_sum[(X * 2 + (hlf ^ 1)) * 128 + r];
+      }
       mbar_wait(&pv_done[X], (gt - 1) & 1);
       tc_fence_after();
       const float inv_l = 1.f / l_run;
@@ -370,6 +430,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_pp_kernel(const __grid_con
       const bool vec_ok = ((p.out_ld & 7) == 0) && ((p.d & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
 #pragma unroll
       for (int c = 0; c < DVP / 16; ++c) {
+        if (NS == 2 && (c & 1) != hlf) continue;  // the two threads of a row split the output columns
         uint32_t o[16];
         tmem_ld_32x16(t_o + c * 16, o);
         tmem_ld_wait();
@@ -396,10 +457,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1) attn_pp_kernel(const __grid_con
           }
         }
       }
-      // the next work item's first PV overwrites O (accumulate = 0) only after this warpgroup's next p_ready, which
-      // every thread signals after this read-out: no separate "O free" barrier is needed
+      // the next work item's first PV overwrites O (accumulate = 0) only after this tile's next p_ready, which every
+      // softmax thread of the tile signals after this read-out: no separate "O free" barrier is needed
     }
-    if (X == 0 && gt > 0) named_bar_sync<2>(256);  // consume B's last token so no named barrier is left half-arrived
+    if (TOKEN && X == 0 && gt > 0) named_bar_sync<2>(2 * GROUP);  // consume B's last token so no named barrier is left half-arrived
   }
 
   tc_fence_before();
@@ -806,7 +867,10 @@ static int attn_set_attr() {
 }
 template <int DVP>
 static int attn_pp_set_attr() {
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 1>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 2>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 1>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 2>::SMEM));
   return 0;
 }
 
@@ -923,7 +987,13 @@ template <int DVP>
 static cudaError_t launch_pp(const AttnLaunchImpl* I, cudaStream_t stream) {
   AttnKParams p = I->p;
   p.dbg = g_attn_dbg;
-  return launch_pdl(attn_pp_kernel<DVP>, I->grid, dim3(PP_THREADS), PPCfg<DVP>::SMEM, stream, p);
+  // SDW_ATTN_NS=1: one softmax thread per query row (A/B measurements); default two
+  static const bool ns1 = [] { const char* e = std::getenv("SDW_ATTN_NS"); return e && e[0] == '1'; }();
+  static const bool tok = [] { const char* e = std::getenv("SDW_ATTN_TOKEN"); return !(e && e[0] == '0'); }();
+  if (ns1 && tok) return launch_pdl(attn_pp_kernel<DVP, 1, 1>, I->grid, dim3(PPCfg<DVP, 1>::THREADS), PPCfg<DVP, 1>::SMEM, stream, p);
+  if (ns1) return launch_pdl(attn_pp_kernel<DVP, 1, 0>, I->grid, dim3(PPCfg<DVP, 1>::THREADS), PPCfg<DVP, 1>::SMEM, stream, p);
+  if (tok) return launch_pdl(attn_pp_kernel<DVP, 2, 1>, I->grid, dim3(PPCfg<DVP, 2>::THREADS), PPCfg<DVP, 2>::SMEM, stream, p);
+  return launch_pdl(attn_pp_kernel<DVP, 2, 0>, I->grid, dim3(PPCfg<DVP, 2>::THREADS), PPCfg<DVP, 2>::SMEM, stream, p);
 }
 
 int launch_attention(const AttnLaunch& L, cudaStream_t stream) {

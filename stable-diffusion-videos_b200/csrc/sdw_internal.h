@@ -193,7 +193,7 @@ bool attn_supported(int d);
 int plan_attention(const AttnDesc& a, AttnLaunch* L);
 int launch_attention(const AttnLaunch& L, cudaStream_t stream);
 void attention_plan_info(const AttnLaunch& L, int out[5]);
-void attention_set_trace(long long* buf);  // device buffer [2][4096][5] of clock64 stamps written by CTA 0 of attn_pp_kernel (nullptr = off)
+void attention_set_trace(long long* buf);  // device buffer [2][4096][8] of clock64 stamps written by CTA 0 of attn_pp_kernel (nullptr = off)
 
 // ---------------------------------------------------------------------------
 // fp32 helper kernels (sdw_elem.cu)

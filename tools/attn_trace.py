@@ -15,7 +15,7 @@ q = torch.randn(B, Nq, Cc, device="cuda").half()
 k = torch.randn(B, Nk, Cc, device="cuda").half()
 vt = torch.randn(B, heads, d, Nk, device="cuda").half()
 out = torch.empty(B, Nq, Cc, device="cuda", dtype=torch.float16)
-buf = torch.zeros(2, 4096, 5, dtype=torch.int64, device="cuda")
+buf = torch.zeros(2, 4096, 8, dtype=torch.int64, device="cuda")
 
 
 def run():
@@ -35,14 +35,16 @@ t = buf.cpu()
 nt = (Nk + 127) // 128
 for X in range(2):
     rows = t[X]
-    rows = rows[rows[:, 4] > 0]
+    rows = rows[rows[:, 6] > 0]
     rows = rows[rows[:, 0].argsort()]
     if rows.shape[0] < 8:
         print("tile", "AB"[X], "no samples")
         continue
     body = rows[4:-4].double()
-    wait, ld, mx, ex = (body[:, 1] - body[:, 0]).mean(), (body[:, 2] - body[:, 1]).mean(), \
-        (body[:, 3] - body[:, 2]).mean(), (body[:, 4] - body[:, 3]).mean()
-    period = (body[1:, 0] - body[:-1, 0]).mean()
-    print(f"query tile {'AB'[X]}: {rows.shape[0]} tiles; per KV tile: wait S {wait:.0f}, TMEM->regs {ld:.0f}, row max "
-          f"{mx:.0f}, exp+P store {ex:.0f}; period {period:.0f} cycles (XU floor 1024 per tile, 2048 per A+B pair)")
+    d = lambda a, b: float((body[:, b] - body[:, a]).mean())  # noqa: E731
+    period = float((body[1:, 0] - body[:-1, 0]).mean())
+    tok = body[:, 4].min() > 0
+    print(f"query tile {'AB'[X]}: {rows.shape[0]} tiles; per KV tile: wait S {d(0, 1):.0f}, TMEM->regs {d(1, 2):.0f}, row max "
+          f"{d(2, 3):.0f}, " + (f"scale + token wait {d(3, 4):.0f}, MUFU burst {d(4, 5):.0f}, sum/pack/P store {d(5, 6):.0f}" if tok
+                               else f"exp + P store {d(3, 6):.0f}") +
+          f"; period {period:.0f} cycles (XU floor 1024 per tile, 2048 per A+B pair)")
