@@ -22,9 +22,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed ncu --set full capture
-# profiles/r01_ncu_gemm2_conv_tapreuse_raw.csv (same shape, batch 60)
-DOMINANT_KERNEL_DRAM_BYTES = 452.1e6
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels the roofline block names, taken from committed
+# `ncu --set full` captures (profiles/roofline_traffic.json: bytes, the batch of the capture, the raw page they come from)
+def _traffic(kernel, batch):
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[kernel]
+        return {"bytes": t["bytes"] * batch / t["batch"], "source": f"ncu capture {t['source']} at batch {t['batch']}, "
+                                                                   f"scaled to batch {batch}"}
+    except Exception:
+        return {"bytes": None, "source": "no capture committed"}
+
+
 FLOP_PER_FRAME = {"sd14": 2 * 51 * 0.8033e12 + 2.5145e12}  # SURVEY.md §8d algorithmic FLOPs (84.45 T)
 UNET_FLOP_B1 = 0.8033e12
 VAE_FLOP = 2.5145e12
@@ -279,13 +287,65 @@ def main():
     h2d = F * (4 * h * w + 77 * 768) * 2
     d2h = F * 512 * 512 * 3
 
-    # ---- roofline of the dominant kernel, measured live: the 64x64-level ResBlock conv3x3 (320 -> 320, bias + residual)
-    #      through the tcgen05 implicit-GEMM kernel at this run's UNet batch (2F), CUDA events on the launch stream
+    # ---- walk()-level throughput: the call users make (P:556), PNG files included (frame sink: pinned async D2H + workers)
+    walk_leg = None
+    if world == 1:
+        import shutil
+        import tempfile
+
+        tmp = tempfile.mkdtemp(prefix="sdw_bench_walk_")
+        n_walk = F * min(K, 3)
+        kw = dict(output_dir=tmp, num_inference_steps=a.inference_steps, guidance_scale=7.5, batch_size=F, make_video=False)
+        pipe.walk(["0", "1"], seeds=[42, 1337], num_interpolation_steps=F, name="warm", **kw)  # same engine shape, warm
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pipe.walk(["0", "1"], seeds=[42, 1337], num_interpolation_steps=n_walk, name="timed", **kw)
+        torch.cuda.synchronize()
+        t_walk = time.perf_counter() - t0
+        n_png = len([f for f in os.listdir(os.path.join(tmp, "timed", "timed_000000")) if f.endswith(".png")])
+        assert n_png == n_walk, (n_png, n_walk)
+        walk_leg = {"value": n_walk / t_walk, "unit": "frames/s", "frames": n_walk,
+                    "note": "StableDiffusionWalkPipeline.walk(make_video=False): embed_text + init_noise + slerp/lerp + "
+                            "sampler + D2H + PNG files on disk (tmpfs-independent: written under the system temp dir)"}
+        shutil.rmtree(tmp, ignore_errors=True)
+
+    # ---- rooflines, measured live at this run's UNet batch (2F), each kernel alone with L2 flushed between launches,
+    #      CUDA events on the launch stream
     kern = None
     if rank == 0:
         import ctypes as C
 
         Bn = 2 * F
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+        def timed(fn, warm=2, reps=6):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            tot = 0.0
+            for _ in range(reps):
+                flush.zero_()
+                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                k0.record()
+                fn()
+                k1.record()
+                torch.cuda.synchronize()
+                tot += k0.elapsed_time(k1)
+            return tot / reps * 1e3  # us
+
+        # (1) dominant kernel by share of the step: self-attention at the 64x64 level (8 heads x 40)
+        Cc, Nt = 320, 4096
+        qa = torch.randn(Bn, Nt, Cc, device=dev).half()
+        ka = torch.randn(Bn, Nt, Cc, device=dev).half()
+        vta = torch.randn(Bn, 8, 40, Nt, device=dev).half()
+        oa = torch.empty(Bn, Nt, Cc, device=dev, dtype=torch.float16)
+        attn_us = timed(lambda: _native.check(_native.lib().sdw_attention(
+            _native.ptr(qa), C.c_int64(Cc), _native.ptr(ka), C.c_int64(Cc), _native.ptr(vta), C.c_int64(Nt), Bn, Nt, Nt, 8,
+            40, _native.ptr(oa), C.c_int64(Cc), _native.stream_ptr())))
+        attn_flop = 4.0 * Bn * 8 * Nt * Nt * 40
+        attn_exps = float(Bn) * 8 * Nt * Nt
+        del qa, ka, vta, oa
+        # (2) the 64x64-level ResBlock conv3x3 (320 -> 320, bias + residual): the tensor-bound GEMM family
         xk = torch.randn(Bn, 64, 64, 320, device=dev).half()
         wk = _native.pack_weight((torch.randn(320, 320, 3, 3, device=dev) * (2880 ** -0.5)).half())
         bk = torch.randn(320, device=dev)
@@ -297,50 +357,22 @@ def main():
         d.conv = 1; d.Wt = wk.data_ptr(); d.N = 320
         d.bias = bk.data_ptr(); d.resid = rk.data_ptr(); d.ldr = 320
         d.out = ok.data_ptr(); d.ldc = 320; d.alpha = 1.0
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-        for _ in range(3):
-            _native.gemm(d)
-        torch.cuda.synchronize()
-        tot = 0.0
-        reps = 10
-        for _ in range(reps):
-            flush.zero_()
-            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            k0.record()
-            _native.gemm(d)
-            k1.record()
-            torch.cuda.synchronize()
-            tot += k0.elapsed_time(k1)
+        conv_us = timed(lambda: _native.gemm(d))
         kern = {"name": "gemm2_tc_kernel<160, tap-reuse> conv3x3 64x64 320->320 bias+residual", "batch": Bn,
-                "flop_per_launch": 2.0 * Bn * 64 * 64 * 320 * 2880, "us_per_launch": tot / reps * 1e3}
-        del xk, wk, rk, ok
-        # the heaviest single launch of the step: self-attention at the 64x64 level (8 heads x 40), same timing method
-        Cc, Nt = 320, 4096
-        qa = torch.randn(Bn, Nt, Cc, device=dev).half()
-        ka = torch.randn(Bn, Nt, Cc, device=dev).half()
-        vta = torch.randn(Bn, 8, 40, Nt, device=dev).half()
-        oa = torch.empty(Bn, Nt, Cc, device=dev, dtype=torch.float16)
-
-        def attn():
-            _native.check(_native.lib().sdw_attention(_native.ptr(qa), C.c_int64(Cc), _native.ptr(ka), C.c_int64(Cc),
-                                                      _native.ptr(vta), C.c_int64(Nt), Bn, Nt, Nt, 8, 40, _native.ptr(oa),
-                                                      C.c_int64(Cc), _native.stream_ptr()))
-        for _ in range(2):
-            attn()
-        torch.cuda.synchronize()
-        tot_a = 0.0
-        for _ in range(5):
-            flush.zero_()
-            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            k0.record()
-            attn()
-            k1.record()
-            torch.cuda.synchronize()
-            tot_a += k0.elapsed_time(k1)
-        attn_us = tot_a / 5 * 1e3
-        attn_flop = 4.0 * Bn * 8 * Nt * Nt * 40
-        attn_exps = float(Bn) * 8 * Nt * Nt
-        del qa, ka, vta, oa, flush
+                "flop_per_launch": 2.0 * Bn * 64 * 64 * 320 * 2880, "us_per_launch": conv_us}
+        # (3) the short-K transformer linears (HBM / epilogue bound): attention out-projection 320 -> 320 + residual
+        T = Bn * 4096
+        wl = _native.pack_weight((torch.randn(320, 320, 1, 1, device=dev) * (320 ** -0.5)).half())
+        dl = _native.GemmDesc()
+        xl = xk.view(T, 320)
+        dl.A = xl.data_ptr(); dl.C, dl.W, dl.H, dl.B = 320, T, 1, 1
+        dl.sW = 320
+        dl.Wt = wl.data_ptr(); dl.N = 320
+        dl.bias = bk.data_ptr(); dl.resid = rk.data_ptr(); dl.ldr = 320
+        dl.out = ok.data_ptr(); dl.ldc = 320; dl.alpha = 1.0
+        lin_us = timed(lambda: _native.gemm(dl))
+        lin_bytes = 2.0 * T * 320 * 3 + 2.0 * 320 * 320  # activations in, residual in, out; weights once
+        del xk, wk, rk, ok, wl, flush
 
     if rank != 0:
         return
@@ -348,6 +380,10 @@ def main():
     burst_tf = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1736.7) \
         if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
     k_ach = kern["flop_per_launch"] / (kern["us_per_launch"] * 1e-6) / 1e12
+    attn_tf = attn_flop / (attn_us * 1e-6) / 1e12
+    sm_hz = (clk["sm_mhz"] if clk and clk.get("sm_mhz") else 1850) * 1e6
+    xu_floor_us = attn_exps / (16.0 * 148 * sm_hz) * 1e6
+    tr_attn, tr_conv = _traffic("attention_self_64x64_d40", 2 * F), _traffic("conv3x3_64x64_320", 2 * F)
     achieved_tf = value * FLOP_PER_FRAME["sd14"] / 1e12 / world
     pro, per_step, vae_l = eng.launches()
     launches_per_call = pro + 1 + n_unet_calls * (per_step + 1) + vae_l
@@ -358,24 +394,30 @@ def main():
         "config": {"workload": workload, "frames_per_step": F, "unet_calls_per_frame": n_unet_calls,
                    "unet_batch": 2 * F, "parallelism": f"frame-dp{world}", "cuda_graph": not a.no_graph,
                    "l2": "working set per step (1.8 GB weights + activations) exceeds the 126 MB L2"},
-        "roofline": {"bound": "tensor", "achieved": k_ach, "peak": burst_tf, "unit": "TFLOP/s",
-                     "frac": k_ach / burst_tf, "traffic": DOMINANT_KERNEL_DRAM_BYTES,
-                     "kernel": kern["name"], "kernel_batch": kern["batch"], "us_per_launch": kern["us_per_launch"],
-                     "note": f"dominant kernel timed alone (L2 flushed between launches) vs {peak_src} burst fp16/bf16 "
-                             "peak; traffic = dram read+write bytes per launch from the committed ncu --set full "
-                             "capture (profiles/), at that capture's batch",
-                     "whole_sampler": {"achieved": achieved_tf, "peak": peak_tf, "frac": achieved_tf / peak_tf,
-                                       "note": "frames x 84.45 TFLOP / time / gpus vs sustained peak"},
-                     "attention": {"kernel": "attn_fwd_kernel self-attention 64x64, 8 heads x 40", "kernel_batch": Bn,
-                                   "us_per_launch": attn_us, "achieved": attn_flop / (attn_us * 1e-6) / 1e12,
-                                   "peak": burst_tf, "unit": "TFLOP/s", "frac": attn_flop / (attn_us * 1e-6) / 1e12 / burst_tf,
-                                   "mufu_floor_us": attn_exps / (16.0 * 148 * 1.85e9) * 1e6,
-                                   "note": "heaviest single launch (~24 % of the step); bound by one MUFU.EX2 per score "
-                                           "(16/clk/SM) and the fp32 TMEM read of S, not by the tensor pipe"}},
+        "roofline": {
+            "bound": "tensor", "achieved": attn_tf, "peak": burst_tf, "unit": "TFLOP/s", "frac": attn_tf / burst_tf,
+            "traffic": tr_attn["bytes"], "traffic_source": tr_attn["source"],
+            "kernel": "attn_pp_kernel self-attention 64x64, 8 heads x 40 (dominant kernel by share of the step)",
+            "kernel_batch": 2 * F, "us_per_launch": attn_us,
+            "xu_floor_us": xu_floor_us, "xu_frac": xu_floor_us / attn_us,
+            "note": f"timed alone, L2 flushed between launches, vs {peak_src} burst fp16/bf16 peak; this kernel is bound by "
+                    "one MUFU.EX2 per score (16/clk/SM): xu_frac = exponential floor at the sampled SM clock / time",
+            "conv3x3": {"kernel": kern["name"], "kernel_batch": kern["batch"], "us_per_launch": kern["us_per_launch"],
+                        "bound": "tensor", "achieved": k_ach, "peak": burst_tf, "unit": "TFLOP/s", "frac": k_ach / burst_tf,
+                        "traffic": tr_conv["bytes"], "traffic_source": tr_conv["source"]},
+            "short_k_linear": {"kernel": "gemm2_tc_kernel attention out-projection 64x64 320->320 bias+residual",
+                               "kernel_batch": 2 * F, "us_per_launch": lin_us, "bound": "hbm",
+                               "achieved": lin_bytes / (lin_us * 1e-6) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                               "frac": lin_bytes / (lin_us * 1e-6) / 1e9 / peak_gbs,
+                               "note": "algorithmic bytes (activations in + residual in + out + weights) / time"},
+            "whole_sampler": {"achieved": achieved_tf, "peak": peak_tf, "frac": achieved_tf / peak_tf, "unit": "TFLOP/s",
+                              "note": "frames x 84.45 TFLOP / time / gpus vs sustained peak"}},
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches_per_call * K,
         "clocks": clk,
     }
+    if walk_leg:
+        res["walk"] = walk_leg
     if not a.no_cpu_baseline and world == 1:
         res["cpu_baseline"] = {k: v for k, v in cpu_reference_leg(2, 1).items()
                                if k in ("value", "unit", "cores", "kind", "sample")}

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SDW_ABI_VERSION 1
+#define SDW_ABI_VERSION 2
 
 const char* sdw_last_error(void);
 int sdw_abi_version(void);
@@ -65,12 +65,14 @@ typedef struct sdw_step_coef {
   int32_t hist_slot[4];
   int32_t use_x_base;  /* 1: sample := x_base (PLMS second step) */
   int32_t save_x_base; /* 1: x_base := sample before the update (PLMS first step) */
-  int32_t push_slot;   /* >=0: store the combined eps into hist[push_slot] */
+  int32_t push_slot;   /* >=0: store push_e * e + push_x * s into hist[push_slot] */
   float next_in_scale; /* scale_model_input factor for the next UNet call */
+  float push_e, push_x; /* what the history keeps: (1, 0) = the combined eps (PLMS / LMS); DPM-Solver++ keeps the data
+                         * prediction x0 = s / alpha_t - (sigma_t / alpha_t) e */
 } sdw_step_coef;
 /* update: e = u + g (c - u);  s = use_x_base ? x_base : x;  x' = c_x s + c_e[0] e + sum_j c_e[1+j] hist[hist_slot[j]];
- * covers PNDM/PLMS (warm-up, cur_sample step, 4-term Adams-Bashforth), DDIM eps / v-prediction (eta = 0) and
- * LMS (epsilon) exactly; coefficients are computed on the host in fp64 (see schedulers.py). */
+ * covers PNDM/PLMS (warm-up, cur_sample step, 4-term Adams-Bashforth), DDIM eps / v-prediction (eta = 0), LMS, Euler
+ * and DPM-Solver++(2M) (history of x0) exactly; coefficients are computed on the host in fp64 (see schedulers.py). */
 
 int sdw_cfg_sched_step(const void* eps_nhwc, int has_uncond, float* x, float* x_base, float* hist,
                        const sdw_step_coef* coef, int F, int C, int H, int W, void* next_in, int next_in_cpad,
@@ -132,6 +134,20 @@ int sdw_engine_sample(sdw_engine* e, const float* latents_f32, const void* cond_
 /* use_graph = 1 captures the whole call into a CUDA graph on first use: `stream` must then be a real stream, not
  * the legacy default stream 0.  out_raw_f32 (optional): fp32 [F][8h][8w][3] decoder output BEFORE (x/2+0.5).clamp(0,1) — the float image of P:435 */
 int sdw_engine_launches(const sdw_engine* e, int* prologue, int* unet_per_step, int* vae);
+/* The same sampler in three segments, for per-step callbacks (stable_diffusion_pipeline.py:429-430): `begin` stages the
+ * inputs and runs the prologue (context assembly, cross-attention K/V, first model input); `steps` runs denoise steps
+ * [s0, s1) eagerly and copies the current latents (fp32 [F][4][h][w]) to out_latents when non-null; `end` decodes.
+ * sdw_engine_sample == begin + steps(0, n_steps) + end under one CUDA graph. */
+int sdw_engine_sample_begin(sdw_engine* e, const float* latents_f32, const void* cond_f16, const void* uncond_f16,
+                            void* stream);
+int sdw_engine_sample_steps(sdw_engine* e, int s0, int s1, float* out_latents, void* stream);
+int sdw_engine_sample_end(sdw_engine* e, uint8_t* out_u8, float* out_latents, float* out_raw_f32, void* stream);
+/* the two model calls of the hot loop as stand-alone entry points: one UNet forward on an explicit [Bn] batch (Bn = 2F with
+ * guidance: x fp32 [Bn][4][h][w], ctx fp16 [Bn][tokens][D] -> eps fp32 NHWC [Bn][h][w][4]; reference P:418) and one VAE
+ * decode + post-process of fp32 [F][4][h][w] latents (division by the scaling factor inside) -> uint8 NHWC frames and,
+ * optionally, the pre-clamp fp32 decoder output (reference P:432-438) */
+int sdw_unet_forward(sdw_engine* e, const float* x_nchw, int step, const void* ctx_f16, float* eps_nhwc_out, void* stream);
+int sdw_vae_decode_u8(sdw_engine* e, const float* latents_nchw, uint8_t* out_u8, float* out_f32_nhwc, void* stream);
 /* parity hooks: one UNet forward on an explicit [Bn] batch / one VAE decode */
 int sdw_engine_debug_unet(sdw_engine* e, const float* x_nchw, int step, const void* ctx_f16, float* eps_nhwc_out,
                           void* stream);
@@ -210,6 +226,32 @@ int sdw_pack_weight(const void* w_oihw, int N, int C, int kh, int kw, int geglu_
 /* upsampler (nearest x2 + 3x3) weights folded to four 2x2 parity convs: out = 4 blocks of [N][4][ceil64(C)];
  * block (py*2+px) is the weight operand of a conv = 3 GEMM with up_py/up_px = (py, px) */
 int sdw_pack_weight_up4(const void* w_oihw, int N, int C, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * CLIP text tower: replaces `self.text_encoder(input_ids)[0]` of embed_text (stable_diffusion_pipeline.py:809-820) and of
+ * the unconditional "" encode (P:341-348).  Parameter names are transformers' CLIPTextModel state-dict keys
+ * ("text_model.embeddings.token_embedding.weight", "text_model.encoder.layers.{i}.self_attn.q_proj.weight", ...,
+ * "text_model.final_layer_norm.bias"); all tensors are handed over as fp16.  Life cycle as the sampler engine:
+ * create -> arena_bytes -> bind(arena: caller-owned device memory, 256-byte aligned) -> load_param x N -> forward x M.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sdw_clip sdw_clip;
+typedef struct sdw_clip_config {
+  int32_t vocab, max_positions, hidden, layers, heads, intermediate;
+  int32_t act_gelu_erf; /* 0: quick-GELU x sigmoid(1.702 x) (SD-1.x ViT-L/14); 1: erf GELU (SD-2.x OpenCLIP-H) */
+  float eps;            /* LayerNorm epsilon (1e-5) */
+  int32_t max_batch;    /* prompts per forward call the activation buffers are sized for */
+} sdw_clip_config;
+int sdw_clip_create(const sdw_clip_config* cfg, sdw_clip** out);
+void sdw_clip_destroy(sdw_clip* e);
+int sdw_clip_arena_bytes(const sdw_clip* e, uint64_t* bytes);
+int sdw_clip_bind(sdw_clip* e, void* arena, uint64_t bytes);
+int sdw_clip_num_params(const sdw_clip* e);
+int sdw_clip_param_info(const sdw_clip* e, int index, const char** name, int64_t* numel);
+int sdw_clip_load_param(sdw_clip* e, const char* name, const void* data_f16, int64_t numel, void* stream);
+int sdw_clip_missing_params(const sdw_clip* e, const char** first_missing);
+/* ids: device int32 [B][max_positions] (token ids, already padded / truncated by the tokenizer);
+ * out: device fp16 [B][max_positions][hidden] = last_hidden_state after the final LayerNorm */
+int sdw_clip_forward(sdw_clip* e, const int32_t* ids, int B, void* out_f16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -199,6 +199,56 @@ class EulerDiscreteScheduler:
         return sample + derivative * (float(self.sigmas[i + 1]) - s)
 
 
+class DPMSolverMultistepScheduler:
+    """diffusers v0.11 `DPMSolverMultistepScheduler` defaults (dpmsolver++, solver_order 2, midpoint, lower_order_final,
+    epsilon prediction, no thresholding) — a member of the reference's scheduler union (stable_diffusion_pipeline.py:71-78).
+    Stateful restatement of its `step`: convert_model_output, first-order update, multistep second-order update."""
+
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps=1000, prediction_type="epsilon", solver_order=2, lower_order_final=True):
+        assert prediction_type == "epsilon"
+        self.n_train = num_train_timesteps
+        ac = _alphas_cumprod(n=num_train_timesteps).double()
+        self.alpha_t, self.sigma_t = ac.sqrt(), (1 - ac).sqrt()
+        self.lambda_t = self.alpha_t.log() - self.sigma_t.log()
+        self.solver_order, self.lower_order_final = solver_order, lower_order_final
+        self.timesteps = None
+
+    def set_timesteps(self, n):
+        self.num_inference_steps = n
+        self.timesteps = torch.from_numpy(np.linspace(0, self.n_train - 1, n + 1).round()[::-1][:-1].copy().astype(np.int64))
+        self.model_outputs = [None] * self.solver_order
+        self.lower_order_nums = 0
+        self.prev_t = None
+
+    def scale_model_input(self, sample, t):
+        return sample
+
+    def step(self, model_output, timestep, sample):
+        t = int(timestep)
+        idx = int((self.timesteps == t).nonzero()[0])
+        prev = 0 if idx == len(self.timesteps) - 1 else int(self.timesteps[idx + 1])
+        final = idx == len(self.timesteps) - 1 and self.lower_order_final and len(self.timesteps) < 15
+        x0 = (sample - float(self.sigma_t[t]) * model_output) / float(self.alpha_t[t])  # convert_model_output
+        self.model_outputs = self.model_outputs[1:] + [x0]
+        lam_t, lam_s = float(self.lambda_t[prev]), float(self.lambda_t[t])
+        h = lam_t - lam_s
+        a_p, s_p, s_t = float(self.alpha_t[prev]), float(self.sigma_t[prev]), float(self.sigma_t[t])
+        if self.solver_order == 1 or self.lower_order_nums < 1 or final:
+            out = (s_p / s_t) * sample - a_p * np.expm1(-h) * x0
+        else:
+            m0, m1 = self.model_outputs[-1], self.model_outputs[-2]
+            h0 = lam_s - float(self.lambda_t[self.prev_t])
+            r0 = h0 / h
+            d1 = (1.0 / r0) * (m0 - m1)
+            out = (s_p / s_t) * sample - a_p * np.expm1(-h) * m0 - 0.5 * a_p * np.expm1(-h) * d1
+        if self.lower_order_nums < self.solver_order:
+            self.lower_order_nums += 1
+        self.prev_t = t
+        return out.to(sample.dtype)
+
+
 def make_scheduler(kind, prediction_type="epsilon"):
-    return {"pndm": PNDMScheduler, "ddim": DDIMScheduler, "lms": LMSDiscreteScheduler,
+    return {"dpm": DPMSolverMultistepScheduler, "pndm": PNDMScheduler, "ddim": DDIMScheduler, "lms": LMSDiscreteScheduler,
             "euler": EulerDiscreteScheduler}[kind](prediction_type=prediction_type)

@@ -22,7 +22,7 @@ class StepCoef(C.Structure):
     _fields_ = [
         ("guidance", C.c_float), ("c_x", C.c_float), ("c_e", C.c_float * 5),
         ("hist_slot", C.c_int32 * 4), ("use_x_base", C.c_int32), ("save_x_base", C.c_int32),
-        ("push_slot", C.c_int32), ("next_in_scale", C.c_float),
+        ("push_slot", C.c_int32), ("next_in_scale", C.c_float), ("push_e", C.c_float), ("push_x", C.c_float),
     ]
 
 

@@ -124,6 +124,7 @@ struct StepCoef {
   int hist_slot[4];
   int use_x_base, save_x_base, push_slot;
   float next_in_scale;
+  float push_e, push_x;  // hist[push_slot] := push_e * e + push_x * sample   (eps history: 1, 0; DPM-Solver++ keeps x0)
 };
 
 __global__ void cfg_sched_step_kernel(const float* __restrict__ eps, int has_uncond, float* __restrict__ x,
@@ -153,7 +154,7 @@ __global__ void cfg_sched_step_kernel(const float* __restrict__ eps, int has_unc
   for (int j = 0; j < 4; ++j)
     if (k.c_e[j + 1] != 0.f) acc = fmaf(k.c_e[j + 1], hist[static_cast<int64_t>(k.hist_slot[j]) * n + i], acc);
   const float xn = fmaf(k.c_x, xs, acc);
-  if (k.push_slot >= 0) hist[static_cast<int64_t>(k.push_slot) * n + i] = e;
+  if (k.push_slot >= 0) hist[static_cast<int64_t>(k.push_slot) * n + i] = fmaf(k.push_x, xs, k.push_e * e);
   x[i] = xn;
   if (next_in) {
     const __half v = __float2half_rn(xn * k.next_in_scale);

@@ -914,6 +914,29 @@ static int run_all(Engine* E, cudaStream_t st) {
   return run_ops(E->vae_ops, st, 0);
 }
 
+static int stage_inputs(Engine* E, const float* latents_f32, const void* cond_f16, const void* uncond_f16,
+                        cudaStream_t st) {
+  const sdw_engine_config& c = E->cfg;
+  const int64_t nlat = static_cast<int64_t>(c.frames) * c.in_channels * c.latent_h * c.latent_w;
+  const int64_t per = static_cast<int64_t>(c.ctx_tokens) * c.cross_attention_dim;
+  SDW_CUDA_OK(cudaMemcpyAsync(E->lat_stage, latents_f32, nlat * 4, cudaMemcpyDeviceToDevice, st));
+  SDW_CUDA_OK(cudaMemcpyAsync(E->cond_stage, cond_f16, static_cast<size_t>(c.frames) * per * 2, cudaMemcpyDeviceToDevice, st));
+  if (c.guidance)
+    SDW_CUDA_OK(cudaMemcpyAsync(E->uncond_stage, uncond_f16, static_cast<size_t>(per) * 2, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+static int copy_outputs(Engine* E, uint8_t* out_u8, float* out_latents, float* out_raw_f32, cudaStream_t st) {
+  const sdw_engine_config& c = E->cfg;
+  const int64_t nlat = static_cast<int64_t>(c.frames) * c.in_channels * c.latent_h * c.latent_w;
+  const size_t out_bytes = static_cast<size_t>(c.frames) * c.latent_h * c.vae_scale * c.latent_w * c.vae_scale * c.vae_out_channels;
+  if (out_u8) SDW_CUDA_OK(cudaMemcpyAsync(out_u8, E->out_u8, out_bytes, cudaMemcpyDeviceToDevice, st));
+  if (out_latents) SDW_CUDA_OK(cudaMemcpyAsync(out_latents, E->x, nlat * 4, cudaMemcpyDeviceToDevice, st));
+  if (out_raw_f32)
+    SDW_CUDA_OK(cudaMemcpyAsync(out_raw_f32, E->out_img_f32, out_bytes * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
 int sdw_engine_sample(sdw_engine* e, const float* latents_f32, const void* cond_f16, const void* uncond_f16,
                       uint8_t* out_u8, float* out_latents, float* out_raw_f32, int use_graph, void* stream) {
   Engine* E = reinterpret_cast<Engine*>(e);
@@ -921,14 +944,7 @@ int sdw_engine_sample(sdw_engine* e, const float* latents_f32, const void* cond_
   SDW_REQUIRE(!E->dry && E->n_steps > 0, "engine not bound or schedule not set");
   SDW_REQUIRE(!E->cfg.guidance || uncond_f16, "guidance needs the unconditional embedding");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const sdw_engine_config& c = E->cfg;
-  const int F = c.frames, H = c.latent_h, W = c.latent_w, lc = c.in_channels;
-  const int64_t nlat = static_cast<int64_t>(F) * lc * H * W;
-  const int64_t per = static_cast<int64_t>(c.ctx_tokens) * c.cross_attention_dim;
-  SDW_CUDA_OK(cudaMemcpyAsync(E->lat_stage, latents_f32, nlat * 4, cudaMemcpyDeviceToDevice, st));
-  SDW_CUDA_OK(cudaMemcpyAsync(E->cond_stage, cond_f16, static_cast<size_t>(F) * per * 2, cudaMemcpyDeviceToDevice, st));
-  if (c.guidance)
-    SDW_CUDA_OK(cudaMemcpyAsync(E->uncond_stage, uncond_f16, static_cast<size_t>(per) * 2, cudaMemcpyDeviceToDevice, st));
+  if (int rc = stage_inputs(E, latents_f32, cond_f16, uncond_f16, st)) return rc;
   if (use_graph) {
     if (!E->graph_exec || E->graph_steps != E->n_steps) {
       if (E->graph_exec) {
@@ -952,12 +968,49 @@ int sdw_engine_sample(sdw_engine* e, const float* latents_f32, const void* cond_
   } else {
     if (int rc = run_all(E, st)) return rc;
   }
-  const size_t out_bytes = static_cast<size_t>(F) * H * c.vae_scale * W * c.vae_scale * c.vae_out_channels;
-  SDW_CUDA_OK(cudaMemcpyAsync(out_u8, E->out_u8, out_bytes, cudaMemcpyDeviceToDevice, st));
-  if (out_latents) SDW_CUDA_OK(cudaMemcpyAsync(out_latents, E->x, nlat * 4, cudaMemcpyDeviceToDevice, st));
-  if (out_raw_f32)
-    SDW_CUDA_OK(cudaMemcpyAsync(out_raw_f32, E->out_img_f32, out_bytes * 4, cudaMemcpyDeviceToDevice, st));
-  return 0;
+  return copy_outputs(E, out_u8, out_latents, out_raw_f32, st);
+}
+
+// ---- the same sampler in three segments, for per-step callbacks (stable_diffusion_pipeline.py:429-430): begin stages
+// the inputs and runs the prologue, steps runs denoise steps [s0, s1) eagerly and hands the current latents out, end
+// decodes.  sdw_engine_sample is begin + steps(0, n) + end under one CUDA graph.
+int sdw_engine_sample_begin(sdw_engine* e, const float* latents_f32, const void* cond_f16, const void* uncond_f16,
+                            void* stream) {
+  Engine* E = reinterpret_cast<Engine*>(e);
+  SDW_REQUIRE(E && latents_f32 && cond_f16, "null");
+  SDW_REQUIRE(!E->dry && E->n_steps > 0, "engine not bound or schedule not set");
+  SDW_REQUIRE(!E->cfg.guidance || uncond_f16, "guidance needs the unconditional embedding");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const sdw_engine_config& c = E->cfg;
+  if (int rc = stage_inputs(E, latents_f32, cond_f16, uncond_f16, st)) return rc;
+  const int64_t per = static_cast<int64_t>(c.ctx_tokens) * c.cross_attention_dim;
+  if (int rc = unet_ctx_assemble(E->cond_stage, E->uncond_stage, c.frames, c.guidance, per, E->ctx, st)) return rc;
+  if (int rc = run_ops(E->prologue, st, 0)) return rc;
+  return latents_init(E->lat_stage, 0, E->init_sigma, E->first_in_scale, E->x, E->model_in, c.in_channels, c.guidance,
+                      c.frames, c.in_channels, c.latent_h, c.latent_w, st);
+}
+
+int sdw_engine_sample_steps(sdw_engine* e, int s0, int s1, float* out_latents, void* stream) {
+  Engine* E = reinterpret_cast<Engine*>(e);
+  SDW_REQUIRE(E && !E->dry && E->n_steps > 0, "engine not bound or schedule not set");
+  SDW_REQUIRE(0 <= s0 && s0 <= s1 && s1 <= E->n_steps, "step range out of the schedule");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const sdw_engine_config& c = E->cfg;
+  for (int s = s0; s < s1; ++s) {
+    if (int rc = run_ops(E->unet_ops, st, s)) return rc;
+    if (int rc = cfg_sched_step(E->eps, c.guidance, E->x, E->x_base, E->hist, &E->coefs[s], c.frames, c.in_channels,
+                                c.latent_h, c.latent_w, s + 1 < E->n_steps ? E->model_in : nullptr, c.in_channels, st))
+      return rc;
+  }
+  return copy_outputs(E, nullptr, out_latents, nullptr, st);
+}
+
+int sdw_engine_sample_end(sdw_engine* e, uint8_t* out_u8, float* out_latents, float* out_raw_f32, void* stream) {
+  Engine* E = reinterpret_cast<Engine*>(e);
+  SDW_REQUIRE(E && out_u8 && !E->dry, "null / engine not bound");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = run_ops(E->vae_ops, st, 0)) return rc;
+  return copy_outputs(E, out_u8, out_latents, out_raw_f32, st);
 }
 
 int sdw_engine_launches(const sdw_engine* e, int* prologue, int* unet, int* vae) {
@@ -1026,6 +1079,17 @@ int sdw_engine_debug_unet(sdw_engine* e, const float* x_nchw, int step, const vo
                               static_cast<size_t>(E->Bn) * c.latent_h * c.latent_w * c.out_channels * 4,
                               cudaMemcpyDeviceToDevice, st));
   return 0;
+}
+
+// the two model calls of the hot loop as stand-alone entry points (SURVEY.md §8b export list): one UNet forward
+// (stable_diffusion_pipeline.py:418) and one VAE decode + post-process (P:432-438)
+int sdw_unet_forward(sdw_engine* e, const float* x_nchw, int step, const void* ctx_f16, float* eps_nhwc_out,
+                     void* stream) {
+  return sdw_engine_debug_unet(e, x_nchw, step, ctx_f16, eps_nhwc_out, stream);
+}
+int sdw_engine_debug_vae(sdw_engine* e, const float* latents_nchw, uint8_t* out_u8, float* out_f32_nhwc, void* stream);
+int sdw_vae_decode_u8(sdw_engine* e, const float* latents_nchw, uint8_t* out_u8, float* out_f32_nhwc, void* stream) {
+  return sdw_engine_debug_vae(e, latents_nchw, out_u8, out_f32_nhwc, stream);
 }
 
 int sdw_engine_debug_vae(sdw_engine* e, const float* latents_nchw, uint8_t* out_u8, float* out_f32_nhwc, void* stream) {

@@ -144,12 +144,14 @@ class Engine:
                 k.hist_slot[j] = int(st["hist_slot"][j])
             k.use_x_base, k.save_x_base, k.push_slot = st["use_x_base"], st["save_x_base"], st["push_slot"]
             k.next_in_scale = float(plan[i + 1]["in_scale"]) if i + 1 < n else 1.0
+            k.push_e, k.push_x = float(st.get("push_e", 1.0)), float(st.get("push_x", 0.0))
         with torch.cuda.device(self.device):
             N.check(N.lib().sdw_engine_set_schedule(
                 self._h, n, ts.ctypes.data_as(C.POINTER(C.c_float)), coefs, C.c_float(scheduler.init_noise_sigma),
                 C.c_float(plan[0]["in_scale"]), N.stream_ptr()))
             torch.cuda.current_stream().synchronize()
         self.n_steps = n
+        self._timesteps = [torch.tensor(t) for t in np.asarray(scheduler.timesteps).tolist()]
 
     def launches(self):
         a, b, c = C.c_int(), C.c_int(), C.c_int()
@@ -157,8 +159,12 @@ class Engine:
         return a.value, b.value, c.value
 
     # ------------------------------------------------------------------------------------------
-    def sample(self, latents, cond, uncond=None, use_graph=True, return_latents=False, return_raw=False):
-        """latents [F,4,h,w] (any float dtype), cond [F,tokens,D], uncond [1,tokens,D] -> uint8 [F,8h,8w,3] (CUDA)."""
+    def sample(self, latents, cond, uncond=None, use_graph=True, return_latents=False, return_raw=False, callback=None,
+               callback_steps=1):
+        """latents [F,4,h,w] (any float dtype), cond [F,tokens,D], uncond [1,tokens,D] -> uint8 [F,8h,8w,3] (CUDA).
+
+        `callback(i, t, latents)` (reference P:429-430) is called every `callback_steps` denoise steps with the current
+        fp32 latents; the sampler then runs as eager per-step segments instead of one CUDA graph."""
         F = self.frames
         h, w = self.latent_hw
         N.require_cuda(latents, cond, uncond)
@@ -183,8 +189,21 @@ class Engine:
             cur = torch.cuda.current_stream()
             self._stream.wait_stream(cur)
             with torch.cuda.stream(self._stream):
-                N.check(N.lib().sdw_engine_sample(self._h, N.ptr(lat), N.ptr(cnd), N.ptr(unc), N.ptr(out), N.ptr(fin),
-                                                  N.ptr(raw), int(use_graph), N.stream_ptr()))
+                if callback is None:
+                    N.check(N.lib().sdw_engine_sample(self._h, N.ptr(lat), N.ptr(cnd), N.ptr(unc), N.ptr(out), N.ptr(fin),
+                                                      N.ptr(raw), int(use_graph), N.stream_ptr()))
+                else:
+                    lib = N.lib()
+                    N.check(lib.sdw_engine_sample_begin(self._h, N.ptr(lat), N.ptr(cnd), N.ptr(unc), N.stream_ptr()))
+                    step_lat = torch.empty_like(lat)
+                    for i in range(self.n_steps):
+                        report = i % callback_steps == 0
+                        N.check(lib.sdw_engine_sample_steps(self._h, i, i + 1, N.ptr(step_lat) if report else None,
+                                                            N.stream_ptr()))
+                        if report:
+                            self._stream.synchronize()
+                            callback(i, self._timesteps[i], step_lat.clone())
+                    N.check(lib.sdw_engine_sample_end(self._h, N.ptr(out), N.ptr(fin), N.ptr(raw), N.stream_ptr()))
             cur.wait_stream(self._stream)
         if return_raw:
             return out, raw

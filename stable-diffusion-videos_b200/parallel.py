@@ -19,6 +19,27 @@ def frame_block(n, world, rank):
     return lo, min(n, lo + per)
 
 
+def world_size():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def barrier():
+    if world_size() > 1:
+        dist.barrier()
+
+
+def broadcast_object(obj, src=0):
+    if world_size() == 1:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
 def init_distributed():
     """(rank, world, local_rank) from the torchrun environment; initialises the process group when WORLD_SIZE > 1."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -55,26 +76,22 @@ def broadcast_state_dict(sd, src=0):
 def gather_frames(local_frames, n_total, dst=0):
     """gather per-rank uint8 frame blocks [k_r, H, W, 3] (contiguous frame_block split of n_total) to rank `dst`.
 
-    Returns the [n_total, H, W, 3] tensor on `dst`, None elsewhere.  Uniform collective: every rank pads its block
-    to ceil(n_total / world) frames, one all_gather_into_tensor (NCCL) / all_gather (gloo), trim on dst."""
+    Returns the [n_total, H, W, 3] tensor on `dst`, None elsewhere.  Every rank pads its block to ceil(n_total / world)
+    frames and sends it ONCE: `dist.gather` to `dst` (NCCL: grouped send/recv over NVLink; gloo on CPU tensors) — only
+    rank `dst` receives, so the bytes on the wire are the frames themselves (an all-gather would move world x that)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local_frames
-    world, rank = dist.get_world_size(), dist.get_rank()
+    world, rk = dist.get_world_size(), dist.get_rank()
     per = math.ceil(n_total / world)
     shape = tuple(local_frames.shape[1:])
     buf = torch.zeros((per,) + shape, dtype=local_frames.dtype, device=local_frames.device)
     buf[: local_frames.shape[0]] = local_frames
-    if local_frames.is_cuda:
-        out = torch.empty((world * per,) + shape, dtype=buf.dtype, device=buf.device)
-        dist.all_gather_into_tensor(out, buf)
-    else:
-        parts = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(parts, buf)
-        out = torch.cat(parts)
-    if rank != dst:
+    parts = [torch.empty_like(buf) for _ in range(world)] if rk == dst else None
+    dist.gather(buf, gather_list=parts, dst=dst)
+    if rk != dst:
         return None
     keep = []
     for r in range(world):
         lo, hi = frame_block(n_total, world, r)
-        keep.append(out[r * per: r * per + (hi - lo)])
+        keep.append(parts[r][: hi - lo])
     return torch.cat(keep)

@@ -100,6 +100,64 @@ class SyntheticTextEncoder:
         return (torch.cat(outs).to(self.dtype).to(self.device),)
 
 
+class _FrameSink:
+    """Frame sink of a clip: device uint8 frames -> `frame%06d.png` files (P:550-554) without
+    stalling the sampler.  Two pinned host buffers alternate: the D2H copy of batch k runs on a side stream while the
+    GPU renders batch k+1, and PNG encoding runs on a worker pool (the reference encodes serially on the main thread)."""
+
+    def __init__(self, save_path, ext, batch_shape, device, workers=8):
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.save_path, self.ext = save_path, ext
+        self.host = [torch.empty(batch_shape, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.events = [None, None]
+        self.pending_writes = [[], []]
+        self.stream = torch.cuda.Stream(device=device)
+        self.pool = ThreadPoolExecutor(max_workers=workers)
+        self.k = 0
+        self.inflight = None  # (slot, n, first_index) whose copy has been issued but not handed to the workers
+        self.bytes_d2h = 0
+
+    def _save(self, arr, path):
+        from PIL import Image
+
+        Image.fromarray(arr).save(path)
+
+    def _flush(self):
+        if self.inflight is None:
+            return
+        slot, n, first = self.inflight
+        self.events[slot].synchronize()
+        for i in range(n):
+            path = self.save_path / (f"frame%06d{self.ext}" % (first + i))
+            self.pending_writes[slot].append(self.pool.submit(self._save, self.host[slot][i].numpy(), path))
+        self.inflight = None
+
+    def push(self, frames_u8, n, first_index):
+        slot = self.k & 1
+        for fut in self.pending_writes[slot]:  # the workers are done reading this host buffer
+            fut.result()
+        self.pending_writes[slot] = []
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.host[slot][:n].copy_(frames_u8[:n], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        frames_u8.record_stream(self.stream)
+        self.events[slot] = ev
+        self.bytes_d2h += n * frames_u8[0].numel()
+        self._flush()  # the PREVIOUS batch: its copy overlapped this batch's rendering
+        self.inflight = (slot, n, first_index)
+        self.k += 1
+
+    def close(self):
+        self._flush()
+        for slot in (0, 1):
+            for fut in self.pending_writes[slot]:
+                fut.result()
+        self.pool.shutdown()
+
+
 class StableDiffusionWalkPipeline:
     _optional_components = ["safety_checker", "feature_extractor"]
 
@@ -172,11 +230,11 @@ class StableDiffusionWalkPipeline:
 
         sc = json.loads((root / "scheduler" / "scheduler_config.json").read_text())
         kinds = {"PNDMScheduler": "pndm", "DDIMScheduler": "ddim", "LMSDiscreteScheduler": "lms",
-                 "EulerDiscreteScheduler": "euler"}
+                 "EulerDiscreteScheduler": "euler", "DPMSolverMultistepScheduler": "dpm"}
         if sc["_class_name"] not in kinds:
             raise NotImplementedError(f"scheduler {sc['_class_name']} has no native plan (deterministic linear multistep "
-                                      f"rules only: {sorted(kinds)}); stochastic samplers (Euler ancestral) and "
-                                      "DPM-Solver are not implemented")
+                                      f"rules only: {sorted(kinds)}); stochastic samplers (Euler ancestral, "
+                                      "DPM-Solver SDE variants) are not implemented")
         kind = kinds[sc["_class_name"]]
         ucfg.prediction_type = sc.get("prediction_type", "epsilon")
         sch = SCHEDULERS[kind](num_train_timesteps=sc.get("num_train_timesteps", 1000),
@@ -185,7 +243,12 @@ class StableDiffusionWalkPipeline:
                                prediction_type=ucfg.prediction_type)
         from transformers import CLIPTextModel, CLIPTokenizer
 
-        text_encoder = CLIPTextModel.from_pretrained(str(root / "text_encoder"), torch_dtype=torch_dtype)
+        # transformers is the checkpoint READER only: the tower that runs is the native one (clip.py, sdw_clip_*)
+        from .clip import NativeCLIPTextEncoder
+
+        hf_text = CLIPTextModel.from_pretrained(str(root / "text_encoder"), torch_dtype=torch_dtype)
+        text_encoder = NativeCLIPTextEncoder.from_hf_model(hf_text)
+        del hf_text
         tokenizer = CLIPTokenizer.from_pretrained(str(root / "tokenizer"))
         pipe = cls(NativeVAE(vcfg, _sd("vae")), text_encoder, tokenizer, NativeUNet(ucfg, _sd("unet")), sch)
         pipe.tiled = tiled
@@ -262,9 +325,6 @@ class StableDiffusionWalkPipeline:
         if (callback_steps is None) or (not isinstance(callback_steps, int) or callback_steps <= 0):
             raise ValueError(f"`callback_steps` has to be a positive integer but is {callback_steps} of type"
                              f" {type(callback_steps)}.")
-        if callback is not None:
-            raise NotImplementedError("per-step callbacks cannot run inside the fused native sampler "
-                                      "(SURVEY.md §8f row 4)")
         if eta != 0.0 and not isinstance(self.scheduler, PNDMScheduler) and type(self.scheduler).__name__.startswith("DDIM"):
             raise NotImplementedError("stochastic DDIM (eta > 0) is not implemented; eta = 0 is the reference default")
 
@@ -318,15 +378,10 @@ class StableDiffusionWalkPipeline:
                 raise ValueError(f"Unexpected latents shape, got {latents.shape}, expected {latents_shape}")
             latents = latents.to(self.device)
 
-        # ---- native hot path: set-up (P:394-401), loop (P:412-430), decode + post-process (P:432-438, 450)
-        eng = self._engine(height // 8, width // 8, B, do_cfg)
-        plan_key = self._plan_key(num_inference_steps, guidance_scale)
-        if eng._plan_key != plan_key:
-            eng.set_scheduler(self.scheduler, num_inference_steps, guidance_scale)
-            eng._plan_key = plan_key
         want_float = output_type != "pil"
-        res = eng.sample(latents, text_embeddings.to(self.device), uncond, use_graph=True, return_raw=want_float)
-        frames_u8, raw = res if want_float else (res, None)
+        frames_u8, raw = self._sample_device(latents, text_embeddings, uncond, height, width, num_inference_steps,
+                                             guidance_scale, want_raw=want_float, callback=callback,
+                                             callback_steps=callback_steps)
         if output_type == "pil":
             from PIL import Image
 
@@ -337,6 +392,20 @@ class StableDiffusionWalkPipeline:
         if not return_dict:
             return (image, None)
         return StableDiffusionPipelineOutput(images=image, nsfw_content_detected=None)
+
+    def _sample_device(self, latents, text_embeddings, uncond, height, width, num_inference_steps, guidance_scale,
+                       want_raw=False, callback=None, callback_steps=1):
+        """native hot path: set-up (P:394-401), loop (P:412-430), decode + post-process (P:432-438, 450).
+        Returns (uint8 NHWC frames on the device, pre-clamp fp32 decoder output or None)."""
+        B = latents.shape[0]
+        eng = self._engine(height // 8, width // 8, B, guidance_scale > 1.0)
+        plan_key = self._plan_key(num_inference_steps, guidance_scale)
+        if eng._plan_key != plan_key:
+            eng.set_scheduler(self.scheduler, num_inference_steps, guidance_scale)
+            eng._plan_key = plan_key
+        res = eng.sample(latents, text_embeddings.to(self.device), uncond, use_graph=True, return_raw=want_raw,
+                         callback=callback, callback_steps=callback_steps)
+        return res if want_raw else (res, None)
 
     # ------------------------------------------------------------------------------------------
     # interpolation inputs (reference P:457-479)
@@ -374,36 +443,51 @@ class StableDiffusionWalkPipeline:
             raise ValueError(f"Unexpected T shape, got {T.shape}, expected dim 0 to be {num_interpolation_steps}")
         if upsample:
             raise NotImplementedError("Real-ESRGAN upsampling is outside the hot path (SURVEY.md §2 #5)")
-        from .parallel import frame_block
+        if height % 8 != 0 or width % 8 != 0:  # raised by __call__ in the reference (P:271-272)
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if eta != 0.0 and type(self.scheduler).__name__.startswith("DDIM"):
+            raise NotImplementedError("stochastic DDIM (eta > 0) is not implemented; eta = 0 is the reference default")
+        from . import parallel
 
+        rank, world = self._dist if self._dist is not None else (0, 1)
         Tk = T[skip:]
-        lo, hi = 0, Tk.shape[0]
-        if self._dist is not None:
-            lo, hi = frame_block(Tk.shape[0], self._dist[1], self._dist[0])
+        lo, hi = parallel.frame_block(Tk.shape[0], world, rank)  # contiguous per-rank block of the frames still to render
+        h8, w8 = height // 8, width // 8
+        do_cfg = guidance_scale > 1.0
+        uncond = self._uncond([negative_prompt if negative_prompt is not None else ""]) if do_cfg else None
+        sink = _FrameSink(save_path, image_file_ext, (batch_size, height, width, self.vae.cfg.out_channels),
+                          self.device) if rank == 0 else None
+        mine = []  # this rank's frames, on the device, when they have to travel to rank 0
         frame_index = skip + lo
-        # frame sink: PNG encoding runs on worker threads while the GPU renders the next batch
-        # (the reference saves serially, P:550-554); all writes are joined before the clip returns
-        from concurrent.futures import ThreadPoolExecutor
-
-        pending = []
-        pool = ThreadPoolExecutor(max_workers=8)
-        gen = self.generate_inputs(prompt_a, prompt_b, seed_a, seed_b,
-                                   (1, self.unet.in_channels, height // 8, width // 8), Tk[lo:hi], batch_size)
+        gen = self.generate_inputs(prompt_a, prompt_b, seed_a, seed_b, (1, self.unet.in_channels, h8, w8), Tk[lo:hi],
+                                   batch_size)
         for batch_idx, embeds_batch, noise_batch in gen:
             nb = embeds_batch.shape[0]
             if nb < batch_size:  # keep ONE engine shape per walk: pad the tail batch, drop the padding
                 pad = batch_size - nb
                 embeds_batch = torch.cat([embeds_batch, embeds_batch[-1:].expand(pad, -1, -1)])
                 noise_batch = torch.cat([noise_batch, noise_batch[-1:].expand(pad, -1, -1, -1)])
-            outputs = self(latents=noise_batch, text_embeddings=embeds_batch, height=height, width=width,
-                           guidance_scale=guidance_scale, eta=eta, num_inference_steps=num_inference_steps,
-                           output_type="pil", negative_prompt=negative_prompt)["images"][:nb]
-            for image in outputs:
-                pending.append(pool.submit(image.save, save_path / (f"frame%06d{image_file_ext}" % frame_index)))
-                frame_index += 1
-        for fut in pending:
-            fut.result()  # re-raise any I/O error
-        pool.shutdown()
+            frames_u8, _ = self._sample_device(noise_batch, embeds_batch, uncond, height, width, num_inference_steps,
+                                               guidance_scale)
+            if world > 1:
+                mine.append(frames_u8[:nb].clone())
+            else:
+                sink.push(frames_u8, nb, frame_index)  # async D2H + PNG workers; the GPU goes on with the next batch
+            frame_index += nb
+        if world > 1:
+            # decoded frames travel to rank 0 over NCCL (NVLink); rank 0 alone writes files (reference layout P:550-554)
+            shape = (0, height, width, self.vae.cfg.out_channels)
+            local = torch.cat(mine) if mine else torch.empty(shape, dtype=torch.uint8, device=self.device)
+            allf = parallel.gather_frames(local, Tk.shape[0], dst=0)
+            if rank == 0:
+                for i0 in range(0, allf.shape[0], batch_size):
+                    chunk = allf[i0:i0 + batch_size]
+                    sink.push(chunk, chunk.shape[0], skip + i0)
+        if sink is not None:
+            sink.close()  # joins every write, re-raises I/O errors
+        if world > 1:
+            parallel.barrier()  # nobody starts the next clip (or muxes) before this clip's files exist
+
 
     # ------------------------------------------------------------------------------------------
     # walk (reference P:556-807)
@@ -419,8 +503,19 @@ class StableDiffusionWalkPipeline:
              make_video: Optional[bool] = True):
         height = height or self.unet.config.sample_size * self.vae_scale_factor
         width = width or self.unet.config.sample_size * self.vae_scale_factor
+        # one process per GPU under torchrun: frames of every clip are sharded over the ranks (the
+        # reference's only multi-device precedent pads / shards / unshards inside the pipeline the same way,
+        # flax_stable_diffusion_pipeline.py:546,568-578,594-597,935); rank 0 gathers the frames and is the only writer
+        from . import parallel
+
+        if self._dist is None and parallel.world_size() > 1:
+            self.set_frame_sharding(parallel.rank(), parallel.world_size())
+        rank, world = self._dist if self._dist is not None else (0, 1)
         output_path = Path(output_dir)
-        name = name or time.strftime("%Y%m%d-%H%M%S")
+        if name is None:
+            name = time.strftime("%Y%m%d-%H%M%S")
+            if world > 1:
+                name = parallel.broadcast_object(name)  # every rank must agree on the run directory
         save_path_root = output_path / name
         save_path_root.mkdir(parents=True, exist_ok=True)
         output_filepath = save_path_root / f"{name}.mp4"
@@ -429,7 +524,9 @@ class StableDiffusionWalkPipeline:
         if not resume:
             audio_start_sec = audio_start_sec or 0
         prompt_config_path = save_path_root / "prompt_config.json"
-        if not resume:
+        if not resume and rank != 0:
+            pass  # rank 0 writes the config
+        elif not resume:
             prompt_config_path.write_text(json.dumps(dict(
                 prompts=prompts, seeds=seeds, num_interpolation_steps=num_interpolation_steps, fps=fps,
                 num_inference_steps=num_inference_steps, guidance_scale=guidance_scale, eta=eta, upsample=upsample,
@@ -449,6 +546,8 @@ class StableDiffusionWalkPipeline:
             save_path = save_path_root / f"{name}_{i:06d}"
             step_output_filepath = save_path / f"{name}_{i:06d}.mp4"
             skip = 0
+            if world > 1:
+                parallel.barrier()  # rank 0's file operations of the previous clip are visible before anyone globs
             if resume:
                 if step_output_filepath.exists():
                     print(f"Skipping {save_path} because frames already exist")
@@ -473,13 +572,15 @@ class StableDiffusionWalkPipeline:
                                   guidance_scale=guidance_scale, eta=eta, height=height, width=width,
                                   upsample=upsample, batch_size=batch_size, T=T, skip=skip,
                                   negative_prompt=negative_prompt, step=(i, len(prompts) - 1))
-            if make_video:
+            if make_video and rank == 0:
                 from .utils import make_video_pyav
 
                 make_video_pyav(save_path, audio_filepath=audio_filepath, fps=fps,
                                 output_filepath=step_output_filepath, glob_pattern=f"*{image_file_ext}",
                                 audio_offset=audio_offset, audio_duration=audio_duration, sr=44100)
-        if make_video:
+        if world > 1:
+            parallel.barrier()
+        if make_video and rank == 0:
             from .utils import make_video_pyav
 
             return make_video_pyav(save_path_root, audio_filepath=audio_filepath, fps=fps,

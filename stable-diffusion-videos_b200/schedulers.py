@@ -10,6 +10,8 @@ together with classifier-free guidance.  `beta_schedule="scaled_linear"`, `steps
 """
 from types import SimpleNamespace
 
+import math
+
 import numpy as np
 
 
@@ -247,4 +249,53 @@ class EulerDiscreteScheduler(_Base):
         return steps
 
 
-SCHEDULERS = {"pndm": PNDMScheduler, "ddim": DDIMScheduler, "lms": LMSDiscreteScheduler, "euler": EulerDiscreteScheduler}
+class DPMSolverMultistepScheduler(_Base):
+    """DPM-Solver++ (2M), the diffusers default configuration (algorithm_type "dpmsolver++", solver_order 2,
+    solver_type "midpoint", lower_order_final=True, no thresholding): a two-step linear multistep rule on the DATA
+    prediction x0 = (x - sigma_t eps) / alpha_t.  The native step keeps x0 in the history ring (push_e, push_x) and the
+    update is again  x' = c_x x + c_e0 eps + c_e1 hist:
+        first order :  x' = (s_p/s_t) x - a_p (e^-h - 1) x0_t
+        second order:  x' = (s_p/s_t) x - a_p (e^-h - 1) [ (1 + 1/(2r)) x0_t - 1/(2r) x0_prev ],   r = h_prev / h
+    with a = sqrt(abar), s = sqrt(1 - abar), lambda = ln(a/s), h = lambda_p - lambda_t (scheduler union P:71-78)."""
+    order = 2
+
+    def __init__(self, solver_order=2, lower_order_final=True, **kw):
+        super().__init__(**kw)
+        if solver_order not in (1, 2):
+            raise ValueError("DPM-Solver++ native plan: solver_order 1 or 2")
+        self.config.solver_order, self.config.lower_order_final = solver_order, lower_order_final
+
+    def set_timesteps(self, n, device=None):
+        self.num_inference_steps = n
+        T = self.config.num_train_timesteps
+        self.timesteps = np.linspace(0, T - 1, n + 1).round()[::-1][:-1].copy().astype(np.int64)
+
+    def plan(self):
+        ac = self.alphas_cumprod
+        ts = [int(t) for t in self.timesteps]
+        n = len(ts)
+        lam = lambda a: 0.5 * (math.log(a) - math.log(1.0 - a))  # noqa: E731
+        steps = []
+        for i, t in enumerate(ts):
+            prev = ts[i + 1] if i + 1 < n else 0
+            a_t, a_p = float(ac[t]), float(ac[prev])
+            al_t, si_t, al_p, si_p = a_t ** 0.5, (1 - a_t) ** 0.5, a_p ** 0.5, (1 - a_p) ** 0.5
+            h = lam(a_p) - lam(a_t)
+            g = -al_p * math.expm1(-h)  # coefficient on the (combined) data prediction
+            first = (self.config.solver_order == 1 or i == 0
+                     or (i == n - 1 and self.config.lower_order_final and n < 15))
+            if first:
+                w_cur, w_old = 1.0, 0.0
+            else:
+                h_prev = lam(a_t) - lam(float(ac[ts[i - 1]]))
+                r = h_prev / h
+                w_cur, w_old = 1.0 + 0.5 / r, -0.5 / r
+            # x0_t = x / al_t - (si_t / al_t) eps
+            st = dict(c_x=si_p / si_t + g * w_cur / al_t, c_e=[-g * w_cur * si_t / al_t, g * w_old, 0.0, 0.0, 0.0],
+                      hist_slot=[(i - 1) & 1, 0, 0, 0], use_x_base=0, save_x_base=0, push_slot=i & 1,
+                      push_e=-si_t / al_t, push_x=1.0 / al_t, in_scale=1.0)
+            steps.append(st)
+        return steps
+
+
+SCHEDULERS = {"dpm": DPMSolverMultistepScheduler, "pndm": PNDMScheduler, "ddim": DDIMScheduler, "lms": LMSDiscreteScheduler, "euler": EulerDiscreteScheduler}

@@ -18,7 +18,7 @@ def test_every_declared_symbol_is_exported():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.sdw_abi_version() == 1
+    assert lib.sdw_abi_version() == 2
 
 
 def test_engine_dry_run_sizes_sd14_arena():

@@ -65,7 +65,7 @@ def test_vae_decode(cfgs, hw, frames):
     assert d.float().mean() <= 1.0 and (d <= 2).float().mean() >= 0.99 and int(d.max()) <= 8
 
 
-@pytest.mark.parametrize("kind,steps", [("pndm", 4), ("ddim", 5), ("lms", 6), ("euler", 5)])
+@pytest.mark.parametrize("kind,steps", [("pndm", 4), ("ddim", 5), ("lms", 6), ("euler", 5), ("dpm", 6)])
 def test_full_sampler_tiny(kind, steps):
     from oracle.pipeline import sample_frames, synthetic_embedding, to_uint8
     from oracle.schedulers import make_scheduler

@@ -56,8 +56,8 @@ def _replay(plan, x0, eps_list, sigma):
         for j in range(4):
             if st["c_e"][j + 1] != 0:
                 acc = acc + st["c_e"][j + 1] * hist[st["hist_slot"][j]]
-        if st["push_slot"] >= 0:
-            hist[st["push_slot"]] = e
+        if st["push_slot"] >= 0:  # what sdw_cfg_sched_step keeps: push_e * e + push_x * s (eps history by default)
+            hist[st["push_slot"]] = st.get("push_e", 1.0) * e + st.get("push_x", 0.0) * s
         x = st["c_x"] * s + acc
     return x
 
@@ -65,7 +65,8 @@ def _replay(plan, x0, eps_list, sigma):
 @pytest.mark.parametrize("kind,n,pt", [("pndm", 50, "epsilon"), ("pndm", 4, "epsilon"), ("pndm", 1, "epsilon"),
                                         ("ddim", 50, "epsilon"), ("ddim", 50, "v_prediction"),
                                         ("lms", 50, "epsilon"), ("lms", 3, "epsilon"), ("euler", 50, "epsilon"),
-                                        ("euler", 7, "v_prediction")])
+                                        ("euler", 7, "v_prediction"), ("dpm", 50, "epsilon"), ("dpm", 25, "epsilon"),
+                                        ("dpm", 10, "epsilon"), ("dpm", 1, "epsilon")])
 def test_product_scheduler_plan_equals_oracle_scheduler(kind, n, pt):
     from stable_diffusion_videos_b200.schedulers import SCHEDULERS
 

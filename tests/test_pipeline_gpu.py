@@ -106,3 +106,27 @@ def test_generate_inputs_batches_like_the_reference(pipe_and_oracle):
     la = pipe.init_noise(42, (1, 4, 8, 8), ea.dtype)
     assert torch.equal(batches[0][2][0], la[0]) and torch.equal(batches[0][1][0], ea[0])  # t = 0 endpoints exact
     assert torch.equal(batches[2][1][0], eb[0])
+
+
+def test_callback_sees_every_step_and_does_not_change_the_frames(pipe_and_oracle):
+    """per-step callback(i, t, latents) (stable_diffusion_pipeline.py:429-430): the segmented eager sampler must report the
+    scheduler's timesteps in order, hand out the evolving latents, and end on the same frames as the fused graph."""
+    from oracle.pipeline import sample_frames
+    from oracle.schedulers import make_scheduler
+
+    pipe, unet, vae = pipe_and_oracle
+    g = torch.Generator(device="cuda").manual_seed(3)
+    lat = torch.randn(2, 4, 8, 8, generator=g, device="cuda", dtype=torch.float16)
+    emb = torch.cat([pipe.embed_text("0"), pipe.embed_text("1")])
+    seen = []
+    a = pipe(text_embeddings=emb, latents=lat, height=64, width=64, num_inference_steps=4, output_type="numpy",
+             callback=lambda i, t, x: seen.append((i, int(t), x.float().cpu())), callback_steps=2)
+    b = pipe(text_embeddings=emb, latents=lat, height=64, width=64, num_inference_steps=4, output_type="numpy")
+    assert [s[0] for s in seen] == [0, 2, 4] and [s[1] for s in seen] == [751, 501, 1]  # PNDM-4: 751 501 501 251 1
+    assert np.abs(a.images - b.images).max() <= 1e-6
+    # the latents the callback sees are the oracle's after the same number of steps
+    ref = []
+    sample_frames(unet, vae, make_scheduler("pndm"), lat.float().cpu(), emb.float().cpu(), pipe._uncond([""]).float().cpu(),
+                  4, 7.5, callback=lambda i, t, x: ref.append(x.clone()))
+    for (i, _, x) in seen:
+        assert float((x - ref[i]).norm() / ref[i].norm()) <= 1e-2
