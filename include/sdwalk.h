@@ -113,6 +113,7 @@ typedef struct sdw_engine_config {
   int32_t frames;                  /* frames per sample call (the reference's batch_size) */
   int32_t guidance;                /* 1: classifier-free guidance -> UNet batch 2*frames (P:414) */
   int32_t max_steps;
+  int32_t tiled;                   /* 1: every 3x3 conv pads circularly (from_pretrained(tiled=True), P:841-858) */
 } sdw_engine_config;
 
 int sdw_engine_create(const sdw_engine_config* cfg, sdw_engine** out);

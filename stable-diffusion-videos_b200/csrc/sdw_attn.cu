@@ -471,6 +471,369 @@ __global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(con
   }
 }
 
+// 2^t for two values on the FMA / ALU pipes (what FlashAttention-4 does for part of its exponentials): floor by a
+// round-down magic add, degree-3 minimax polynomial on the fraction (max rel. error 7.5e-5, below the fp16 rounding of P),
+// exponent spliced in with one integer multiply-add per value
+__device__ __forceinline__ void ex2_poly2(float t0, float t1, float& e0, float& e1) {
+  t0 = fmaxf(t0, -126.f);
+  t1 = fmaxf(t1, -126.f);
+  const uint64_t magic = pk2(12582912.f, 12582912.f);
+  const uint64_t t = pk2(t0, t1);
+  uint64_t xr, f;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(xr) : "l"(t), "l"(magic));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(xr), "l"(magic));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(t), "l"(f));
+  uint64_t q = fma2(f, pk2(0.0780244991f, 0.0780244991f), pk2(0.2260671854f, 0.2260671854f));
+  q = fma2(q, f, pk2(0.6958335042f, 0.6958335042f));
+  q = fma2(q, f, pk2(0.9999251962f, 0.9999251962f));
+  float q0, q1, r0, r1;
+  upk2(q, q0, q1);
+  upk2(xr, r0, r1);
+  e0 = __int_as_float(__float_as_int(r0) * 8388608 + __float_as_int(q0));
+  e1 = __int_as_float(__float_as_int(r1) * 8388608 + __float_as_int(q1));
+}
+
+// =============================================================================================
+// attn_db_kernel — the two-query-tile persistent kernel with DOUBLE-BUFFERED scores (BKV = 96, P written in place)
+// =============================================================================================
+// What bounds attn_pp_kernel (profiles/r02_attn_pp_matrix.txt): a warp that issues nothing but MUFU.EX2 gets one every
+// ~11.4 cycles, two warps of a scheduler together one every 9 (8 is the pipe rate, tools/softmax_loop_bench.cu) — and the
+// TMEM-load / row-max / pack / P-store phases of a softmax warp issue no MUFU at all.  With one score buffer per query tile
+// those phases are serial per KV tile (the exponentials need the row max, the row max needs the whole score row), so the
+// XU pipe sees ~1.4 warps' worth of MUFU demand: 3040 cycles per A+B tile pair against 2048 of MUFU work.
+// Here every query tile owns TWO score buffers of 96 columns (2 x 2 x 96 + 2 x 64 = 512 TMEM columns): while a warp
+// exponentiates S_j chunk by chunk it also takes the row max of S_{j+1}, so the max is known before tile j+1 starts and
+// the whole KV loop is ONE homogeneous stream (load, max, scale, ex2, sum, pack, store) the scheduler can interleave — the
+// structure the microbenchmark reaches 8.8 cycles per MUFU with.  P_j (fp16 pairs) overwrites the first 48 columns of
+// S_j's own buffer; O += P_j V_j reads it as a TS-mode MMA, and S_{j+2} is issued into the buffer right behind that MMA,
+// so buffer reuse is ordered by the MMA warp's own program order (no "S free" barrier at all).
+template <int DVP>
+struct DBCfg {
+  static constexpr int BKV = 96;
+  static constexpr int ST = 5;                       // K / V^T ring depth (S runs two tiles ahead of PV)
+  static constexpr int THREADS = 384;                // as attn_pp_kernel<.., 1, ..>
+  static constexpr int Q_BYTES = ATT_BQ * 128;
+  static constexpr int K_STAGE = BKV * 128;          // 96 keys x 64 (zero-filled head dim) fp16
+  static constexpr int V_STAGE = 2 * DVP * 128;      // V^T: two 64-key boxes (the MMA uses the first 96 keys)
+  static constexpr int SMEM = 2 * Q_BYTES + ST * (K_STAGE + V_STAGE) + 1024 + 512;
+  static constexpr int S_COL = 0, O_COL = 384;       // S buffers: X * 192 + buf * 96;  O: 384 + X * 64
+  static_assert(DVP <= 64 && DVP % 16 == 0, "head dim <= 64");
+};
+
+// POLY: every POLY-th pair of exponentials runs on the FMA pipe (ex2_poly2) instead of the MUFU pipe (0 = none)
+template <int DVP, int POLY>
+__global__ void __launch_bounds__(DBCfg<DVP>::THREADS, 1) attn_db_kernel(const __grid_constant__ AttnKParams p) {
+  using Cfg = DBCfg<DVP>;
+  constexpr int ST = Cfg::ST, BKV = Cfg::BKV, NCH = BKV / 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;                          // [2][Q_BYTES]
+  uint8_t* k_smem = q_smem + 2 * Cfg::Q_BYTES;     // [ST][K_STAGE]
+  uint8_t* v_smem = k_smem + ST * Cfg::K_STAGE;    // [ST][V_STAGE]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + ST * Cfg::V_STAGE);
+  uint64_t* q_full = bars;            // [2] TMA -> MMA(X)
+  uint64_t* q_empty = q_full + 2;     // [2] MMA(X) commit -> TMA: every S of this work item has completed
+  uint64_t* kv_full = q_empty + 2;    // [ST] TMA -> both MMA warps
+  uint64_t* kv_empty = kv_full + ST;  // [ST] PV_A(j) and PV_B(j) commits (count 2) -> TMA
+  uint64_t* s_full = kv_empty + ST;   // [2][2] MMA(X) commit -> softmax(X), one per score buffer
+  uint64_t* p_ready = s_full + 4;     // [2] softmax(X) (128) -> MMA(X): P_j is in tensor memory
+  uint64_t* pv_done = p_ready + 2;    // [2] MMA(X) commit -> softmax(X): O is stable (rescale / epilogue only)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = (p.Nk + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.mapQ);
+    tma_prefetch_desc(&p.mapK);
+    tma_prefetch_desc(&p.mapV);
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&q_full[x], 1);
+      mbar_init(&q_empty[x], 1);
+      mbar_init(&s_full[2 * x], 1);
+      mbar_init(&s_full[2 * x + 1], 1);
+      mbar_init(&p_ready[x], 128);
+      mbar_init(&pv_done[x], 1);
+    }
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 2);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp < 4) {
+    reg_dealloc<48>();
+    if (warp == 0) {
+      // ============================ TMA producer ============================================
+      if (lane == 0) {
+        int kvc = 0, wi = 0;
+        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++wi) {
+          const int qp = w % p.qpairs, head = (w / p.qpairs) % p.heads, b = w / (p.qpairs * p.heads);
+          for (int x = 0; x < 2; ++x) {
+            if (wi > 0) mbar_wait(&q_empty[x], (wi - 1) & 1);
+            mbar_expect_tx(&q_full[x], Cfg::Q_BYTES);
+            tma_load_4d(&p.mapQ, &q_full[x], q_smem + x * Cfg::Q_BYTES, 0, qp * 2 * ATT_BQ + x * ATT_BQ, head, b);
+          }
+          for (int j = 0; j < ntiles; ++j, ++kvc) {
+            const int s = kvc % ST;
+            mbar_wait(&kv_empty[s], ((kvc / ST) & 1) ^ 1);
+            mbar_expect_tx(&kv_full[s], Cfg::K_STAGE + Cfg::V_STAGE);
+            tma_load_4d(&p.mapK, &kv_full[s], k_smem + s * Cfg::K_STAGE, 0, j * BKV, head, b);
+            tma_load_4d(&p.mapV, &kv_full[s], v_smem + s * Cfg::V_STAGE, j * BKV, 0, head, b);
+            tma_load_4d(&p.mapV, &kv_full[s], v_smem + s * Cfg::V_STAGE + DVP * 128, j * BKV + 64, 0, head, b);
+          }
+        }
+      }
+    } else if (warp <= 2) {
+      // ============================ MMA issuer of query tile X ===============================
+      if (lane == 0) {
+        const int X = warp - 1;
+        constexpr uint32_t idesc_s = make_idesc_f16(ATT_BQ, BKV);
+        constexpr uint32_t idesc_o = make_idesc_f16(ATT_BQ, DVP);
+        const uint32_t q_addr = smem_u32(q_smem + X * Cfg::Q_BYTES);
+        const uint32_t t_sx = tmem + Cfg::S_COL + X * 192;
+        const uint32_t t_o = tmem + Cfg::O_COL + X * 64;
+        int kvc = 0, gt = 0, wi = 0;  // KV ring position, score tiles of THIS pipeline so far, work items
+        // S of local tile j (global tile g): buffer g & 1.  Its previous content (P of tile g - 2) was consumed by PV(g - 2),
+        // issued earlier by this same thread: tcgen05 operations of one thread execute in order, so no barrier is needed.
+        auto issue_s = [&](int j) {
+          const int g = gt + j, s = (kvc + j) % ST;
+          mbar_wait(&kv_full[s], ((kvc + j) / ST) & 1);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(k_smem + s * Cfg::K_STAGE);
+          const uint32_t ts = t_sx + (g & 1) * BKV;
+          for (int ks = 0; ks < p.dk_steps; ++ks)
+            umma_f16_ss(ts, make_desc_k_sw128(q_addr + ks * 32), make_desc_k_sw128(k_addr + ks * 32), idesc_s,
+                        ks != 0 ? 1u : 0u);
+          umma_commit(&s_full[2 * X + (g & 1)]);
+          if (j == ntiles - 1) umma_commit(&q_empty[X]);  // every S of this work item is issued: Q may be refilled when done
+        };
+        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++wi) {
+          mbar_wait(&q_full[X], wi & 1);
+          tc_fence_after();
+          issue_s(0);
+          if (ntiles > 1) issue_s(1);
+          for (int j = 0; j < ntiles; ++j) {
+            const int g = gt + j;
+            mbar_wait(&p_ready[X], g & 1);
+            tc_fence_after();
+            const int s = (kvc + j) % ST;
+            const uint32_t v_addr = smem_u32(v_smem + s * Cfg::V_STAGE);
+            const uint32_t t_p = t_sx + (g & 1) * BKV;  // P_j sits in the first 48 columns of S_j's buffer
+#pragma unroll
+            for (int ks = 0; ks < BKV / 16; ++ks) {
+              const uint64_t db = make_desc_k_sw128(v_addr + (ks >> 2) * (DVP * 128) + (ks & 3) * 32);
+              umma_f16_ts(t_o, t_p + ks * 8, db, idesc_o, (j | ks) != 0 ? 1u : 0u);
+            }
+            umma_commit(&pv_done[X]);
+            umma_commit(&kv_empty[s]);
+            if (j + 2 < ntiles) issue_s(j + 2);
+          }
+          kvc += ntiles;
+          gt += ntiles;
+        }
+      }
+    }
+  } else {
+    // ============================ softmax / correction / epilogue of query tile X ==============
+    reg_alloc<224>();
+    const int X = (warp >> 2) - 1;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_sx = tmem + lane_base + Cfg::S_COL + X * 192;
+    const uint32_t t_o = tmem + lane_base + Cfg::O_COL + X * 64;
+    const float sl2 = p.scale_log2e;
+    const uint64_t sl2_2 = pk2(sl2, sl2);
+    const bool trace = p.dbg != nullptr && blockIdx.x == 0 && r == 0;
+    constexpr float LAZY_LOG2 = 8.f;
+    int gt = 0;
+    // row max of 32 score columns (keys kv0 .. kv0 + 31; keys >= Nk do not exist)
+    auto chunk_max = [&](const uint32_t (&y)[32], int kv0) {
+      float a0 = -INFINITY, a1 = -INFINITY;
+      if (kv0 + 32 <= p.Nk) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          a0 = fmaxf(a0, __uint_as_float(y[i]));
+          a1 = fmaxf(a1, __uint_as_float(y[i + 1]));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (kv0 + i < p.Nk) a0 = fmaxf(a0, __uint_as_float(y[i]));
+      }
+      return fmaxf(a0, a1);
+    };
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      const int qp = w % p.qpairs, head = (w / p.qpairs) % p.heads, b = w / (p.qpairs * p.heads);
+      float m_ref = -INFINITY, l_run = 0.f, m_next = -INFINITY;
+      {
+        // first tile of the work item: its row max has no previous tile to hide behind
+        mbar_wait(&s_full[2 * X + (gt & 1)], (gt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t ts = t_sx + (gt & 1) * BKV;
+        uint32_t y[NCH][32];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tmem_ld_32x32(ts + c * 32, y[c]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) m_next = fmaxf(m_next, chunk_max(y[c], c * 32));
+      }
+      for (int j = 0; j < ntiles; ++j, ++gt) {
+        long long ts0 = 0, ts1 = 0;
+        if (trace) ts0 = clock64();
+        const uint32_t ts = t_sx + (gt & 1) * BKV;         // S_j (already waited for: its max is m_next)
+        const uint32_t tn = t_sx + ((gt + 1) & 1) * BKV;   // S_{j+1}
+        const bool has_next = j + 1 < ntiles;
+        const int kv0 = j * BKV;
+        const bool ragged = kv0 + BKV > p.Nk;
+        // ---- lazy reference update with the max taken during the previous tile ---------------------
+        const float m_t = m_next;
+        if (j == 0) {
+          m_ref = m_t;
+        } else if (__any_sync(0xffffffffu, (m_t - m_ref) * sl2 > LAZY_LOG2)) {
+          const float m_new = fmaxf(m_ref, m_t);
+          const float alpha = ex2f((m_ref - m_new) * sl2);
+          m_ref = m_new;
+          l_run *= alpha;
+          mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has completed: O is stable
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < DVP / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_32x16(t_o + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x16(t_o + c * 16, o);
+          }
+          tmem_st_wait();
+        }
+        const float mb = m_ref * sl2;
+        const uint64_t nmb_2 = pk2(-mb, -mb);
+        uint64_t sm2[4] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
+        m_next = -INFINITY;
+        // ---- one stream: exponentials of S_j chunk c, row max of S_{j+1} chunk c - 1 -----------------
+        uint32_t xa[32], xb[32], y[32];
+        tmem_ld_32x32(ts, xa);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t(&cur)[32] = (c & 1) ? xb : xa;
+          uint32_t(&nxt)[32] = (c & 1) ? xa : xb;
+          if (c + 1 < NCH) tmem_ld_32x32(ts + (c + 1) * 32, nxt);
+          if (has_next && c >= 1) {
+            if (c == 1) {  // S_{j+1} was issued right behind PV_{j-1}: ready by now
+              mbar_wait(&s_full[2 * X + ((gt + 1) & 1)], ((gt + 1) >> 1) & 1);
+              tc_fence_after();
+              if (trace) ts1 = clock64();
+            }
+            tmem_ld_32x32(tn + (c - 1) * 32, y);
+          }
+          uint32_t pkc[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float t0, t1;
+            upk2(fma2(pk2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sl2_2, nmb_2), t0, t1);
+            float e0, e1;
+            if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
+              ex2_poly2(t0, t1, e0, e1);
+            } else {
+              e0 = ex2f(t0);
+              e1 = ex2f(t1);
+            }
+            if (ragged) {
+              if (kv0 + c * 32 + i >= p.Nk) e0 = 0.f;
+              if (kv0 + c * 32 + i + 1 >= p.Nk) e1 = 0.f;
+            }
+            sm2[(i >> 1) & 3] = add2(sm2[(i >> 1) & 3], pk2(e0, e1));
+            pkc[i >> 1] = pack_h2(e0, e1);
+          }
+          tmem_ld_wait();  // chunk c + 1 of S_j and chunk c - 1 of S_{j+1} have landed
+          // P chunk c -> columns [16 c, 16 c + 16) of S_j's own buffer: those score columns were consumed in chunk c / 2
+          tmem_st_32x16(ts + c * 16, pkc);
+          if (has_next && c >= 1) m_next = fmaxf(m_next, chunk_max(y, (j + 1) * BKV + (c - 1) * 32));
+        }
+        if (has_next) {  // last chunk of S_{j+1}
+          tmem_ld_32x32(tn + (NCH - 1) * 32, y);
+          tmem_ld_wait();
+          m_next = fmaxf(m_next, chunk_max(y, (j + 1) * BKV + (NCH - 1) * 32));
+        }
+        {
+          float s0, s1, s2, s3, s4, s5, s6, s7;
+          upk2(sm2[0], s0, s1);
+          upk2(sm2[1], s2, s3);
+          upk2(sm2[2], s4, s5);
+          upk2(sm2[3], s6, s7);
+          l_run += ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_ready[X]);
+        if (trace) {
+          long long* o = p.dbg + (static_cast<long long>(X) * 4096 + (gt & 4095)) * 8;
+          o[0] = ts0; o[1] = ts0; o[2] = ts0; o[3] = ts0; o[4] = ts1 ? ts1 : ts0; o[5] = ts1 ? ts1 : ts0; o[6] = clock64();
+        }
+      }
+      // ---- epilogue: O / l -> fp16 ------------------------------------------------------------
+      mbar_wait(&pv_done[X], (gt - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.f / l_run;
+      const int row = qp * 2 * ATT_BQ + X * ATT_BQ + r;
+      __half* orow = p.out + (static_cast<int64_t>(b) * p.Nq + row) * p.out_ld + head * p.d;
+      const bool vec_ok = ((p.out_ld & 7) == 0) && ((p.d & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+#pragma unroll
+      for (int c = 0; c < DVP / 16; ++c) {
+        uint32_t o[16];
+        tmem_ld_32x16(t_o + c * 16, o);
+        tmem_ld_wait();
+        if (row < p.Nq) {
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const int dd = c * 16 + h8 * 8;
+            if (dd >= p.d) break;
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[h8 * 8 + i]) * inv_l;
+            if (vec_ok && dd + 8 <= p.d) {
+              uint4 u;
+              u.x = pack_h2(f[0], f[1]);
+              u.y = pack_h2(f[2], f[3]);
+              u.z = pack_h2(f[4], f[5]);
+              u.w = pack_h2(f[6], f[7]);
+              *reinterpret_cast<uint4*>(orow + dd) = u;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (dd + i < p.d) orow[dd + i] = __float2half_rn(f[i]);
+            }
+          }
+        }
+      }
+      // the next work item's first PV (accumulate = 0) is issued only after this tile's next p_ready, which every softmax
+      // thread signals after this read-out; its first S may already sit in the other score buffer
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // =============================================================================================
 // attn_fwd_kernel
 // =============================================================================================
@@ -852,7 +1215,8 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
 // variants: 0..3 attn_fwd_kernel, head dim <= 16 / 32 / 48 / 64 (BKV 128, P in TMEM, two CTAs per SM)
 //           4    attn_fwd_kernel, head dim <= 80  (BKV 64, P in TMEM)
 //           5    attn_fwd_kernel, head dim <= 160 (BKV 64, double-buffered S, P in shared memory)
-//           8..11 attn_pp_kernel, head dim <= 16 / 32 / 48 / 64, more than one KV tile
+//           8..11 attn_pp_kernel, head dim <= 16 / 32 / 48 / 64, more than one KV tile (single score buffer per query tile)
+//           12..15 attn_db_kernel, same head dims, double-buffered scores (BKV = 96): the default for long key sequences
 struct AttnLaunchImpl {
   AttnKParams p;
   dim3 grid;
@@ -871,6 +1235,9 @@ static int attn_pp_set_attr() {
   SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 2>::SMEM));
   SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 1>::SMEM));
   SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 2>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_db_kernel<DVP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBCfg<DVP>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_db_kernel<DVP, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBCfg<DVP>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_db_kernel<DVP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBCfg<DVP>::SMEM));
   return 0;
 }
 
@@ -899,8 +1266,10 @@ void attention_set_trace(long long* buf) { g_attn_dbg = buf; }
 static int variant_for(int d, int Nk) {
   // SDW_ATTN_PP=0: the one-query-tile kernel everywhere (A/B measurements)
   static const bool pp = [] { const char* e = std::getenv("SDW_ATTN_PP"); return !(e && e[0] == '0'); }();
+  // SDW_ATTN_DB=0: single score buffer per query tile (attn_pp_kernel) instead of the double-buffered kernel
+  static const bool db = [] { const char* e = std::getenv("SDW_ATTN_DB"); return !(e && e[0] == '0'); }();
   const int cls = d <= 16 ? 0 : (d <= 32 ? 1 : (d <= 48 ? 2 : 3));
-  if (d <= 64) return (pp && Nk > 128) ? 8 + cls : cls;
+  if (d <= 64) return (pp && Nk > 128) ? (db && Nk > 192 ? 12 : 8) + cls : cls;
   return d <= 80 ? 4 : 5;
 }
 
@@ -913,8 +1282,8 @@ int plan_attention(const AttnDesc& a, AttnLaunch* L) {
   std::memset(I, 0, sizeof(*I));
   I->variant = variant_for(a.d, a.Nk);
   const bool pp = I->variant >= 8;
-  const int bkv = (I->variant == 4 || I->variant == 5) ? 64 : 128;
-  const int dvp_tab[12] = {16, 32, 48, 64, 80, 160, 0, 0, 16, 32, 48, 64};
+  const int bkv = (I->variant == 4 || I->variant == 5) ? 64 : (I->variant >= 12 ? 96 : 128);
+  const int dvp_tab[16] = {16, 32, 48, 64, 80, 160, 0, 0, 16, 32, 48, 64, 16, 32, 48, 64};
   const int dvp = dvp_tab[I->variant];
   AttnKParams& p = I->p;
   p.Nq = a.Nq; p.Nk = a.Nk; p.d = a.d; p.heads = a.heads;
@@ -987,6 +1356,13 @@ template <int DVP>
 static cudaError_t launch_pp(const AttnLaunchImpl* I, cudaStream_t stream) {
   AttnKParams p = I->p;
   p.dbg = g_attn_dbg;
+  if (I->variant >= 12) {
+    // SDW_ATTN_POLY=4|2: every 4th / 2nd pair of exponentials on the FMA pipe (measurement switch)
+    static const int poly = [] { const char* e = std::getenv("SDW_ATTN_POLY"); return e ? std::atoi(e) : 0; }();
+    if (poly == 4) return launch_pdl(attn_db_kernel<DVP, 4>, I->grid, dim3(DBCfg<DVP>::THREADS), DBCfg<DVP>::SMEM, stream, p);
+    if (poly == 2) return launch_pdl(attn_db_kernel<DVP, 2>, I->grid, dim3(DBCfg<DVP>::THREADS), DBCfg<DVP>::SMEM, stream, p);
+    return launch_pdl(attn_db_kernel<DVP, 0>, I->grid, dim3(DBCfg<DVP>::THREADS), DBCfg<DVP>::SMEM, stream, p);
+  }
   // SDW_ATTN_NS=1: one softmax thread per query row (A/B measurements); default two
   static const bool ns1 = [] { const char* e = std::getenv("SDW_ATTN_NS"); return e && e[0] == '1'; }();
   static const bool tok = [] { const char* e = std::getenv("SDW_ATTN_TOKEN"); return !(e && e[0] == '0'); }();
@@ -1010,6 +1386,10 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     case 9: SDW_CUDA_OK(launch_pp<32>(I, stream)); break;
     case 10: SDW_CUDA_OK(launch_pp<48>(I, stream)); break;
     case 11: SDW_CUDA_OK(launch_pp<64>(I, stream)); break;
+    case 12: SDW_CUDA_OK(launch_pp<16>(I, stream)); break;
+    case 13: SDW_CUDA_OK(launch_pp<32>(I, stream)); break;
+    case 14: SDW_CUDA_OK(launch_pp<48>(I, stream)); break;
+    case 15: SDW_CUDA_OK(launch_pp<64>(I, stream)); break;
     default: set_error("bad attention variant"); return 1;
   }
   SDW_CUDA_OK(cudaGetLastError());

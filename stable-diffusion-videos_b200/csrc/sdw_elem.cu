@@ -288,4 +288,94 @@ int pack_weight(const void* w, int N, int C, int kh, int kw, int geglu, void* ou
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// tiled = True (stable_diffusion_pipeline.py:841-858: every Conv2d gets padding_mode="circular"): a padded convolution on
+// the torus is a zero-padded convolution of the wrap-padded image, cropped.  wrap_pad copies an NHWC image into a dense
+// (H + 2 pad) x (W + 2 pad) one whose border repeats the opposite edge; crop takes the interior of the padded result back
+// out (adding a residual for the fp16 case).  Element size is generic (fp16 activations, fp32 eps, uint8 frames).
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void wrap_pad_kernel(const uint8_t* __restrict__ x, int64_t ld_bytes, int B, int H, int W, int pix_bytes, int pad,
+                                uint8_t* __restrict__ y) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad, chunks = pix_bytes / VEC;
+  const int64_t n = static_cast<int64_t>(B) * Hp * Wp * chunks;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % chunks);
+  const int64_t pp = i / chunks;
+  const int xp = static_cast<int>(pp % Wp), yp = static_cast<int>((pp / Wp) % Hp);
+  const int64_t b = pp / (static_cast<int64_t>(Wp) * Hp);
+  const int xs = ((xp - pad) % W + W) % W, ys = ((yp - pad) % H + H) % H;
+  const uint8_t* src = x + ((b * H + ys) * W + xs) * ld_bytes + static_cast<int64_t>(c) * VEC;
+  uint8_t* dst = y + pp * pix_bytes + static_cast<int64_t>(c) * VEC;
+  if (VEC == 16) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+  else if (VEC == 8) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
+  else *dst = *src;
+}
+
+template <int VEC>
+__global__ void crop_kernel(const uint8_t* __restrict__ yp, int B, int H, int W, int pix_bytes, int crop,
+                            const __half* __restrict__ resid, int64_t ldr, uint8_t* __restrict__ out, int64_t ldo_bytes) {
+  const int Wp = W + 2 * crop, Hp = H + 2 * crop, chunks = pix_bytes / VEC;
+  const int64_t n = static_cast<int64_t>(B) * H * W * chunks;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = static_cast<int>(i % chunks);
+  const int64_t p = i / chunks;
+  const int xw = static_cast<int>(p % W), yh = static_cast<int>((p / W) % H);
+  const int64_t b = p / (static_cast<int64_t>(W) * H);
+  const uint8_t* src = yp + ((b * Hp + yh + crop) * Wp + xw + crop) * pix_bytes + static_cast<int64_t>(c) * VEC;
+  uint8_t* dst = out + p * ldo_bytes + static_cast<int64_t>(c) * VEC;
+  if (VEC == 16) {
+    uint4 v = *reinterpret_cast<const uint4*>(src);
+    if (resid) {
+      const uint4 r = *reinterpret_cast<const uint4*>(resid + p * ldr + c * 8);
+      __half2* a = reinterpret_cast<__half2*>(&v);
+      const __half2* q = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fa = __half22float2(a[k]), fb = __half22float2(q[k]);
+        a[k] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
+      }
+    }
+    *reinterpret_cast<uint4*>(dst) = v;
+  } else if (VEC == 8) {
+    *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
+  } else {
+    *dst = *src;
+  }
+}
+
+int wrap_pad(const void* x, int64_t ld_bytes, int B, int H, int W, int pix_bytes, int pad, void* y, cudaStream_t stream) {
+  SDW_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && pix_bytes > 0 && pad >= 1 && pad <= H && pad <= W, "wrap_pad: bad arguments");
+  const int vec = (pix_bytes % 16 == 0 && ld_bytes % 16 == 0) ? 16 : ((pix_bytes % 8 == 0 && ld_bytes % 8 == 0) ? 8 : 1);
+  const int64_t n = static_cast<int64_t>(B) * (H + 2 * pad) * (W + 2 * pad) * (pix_bytes / vec);
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  const uint8_t* xs = static_cast<const uint8_t*>(x);
+  uint8_t* ys = static_cast<uint8_t*>(y);
+  if (vec == 16) wrap_pad_kernel<16><<<blocks, 256, 0, stream>>>(xs, ld_bytes, B, H, W, pix_bytes, pad, ys);
+  else if (vec == 8) wrap_pad_kernel<8><<<blocks, 256, 0, stream>>>(xs, ld_bytes, B, H, W, pix_bytes, pad, ys);
+  else wrap_pad_kernel<1><<<blocks, 256, 0, stream>>>(xs, ld_bytes, B, H, W, pix_bytes, pad, ys);
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int crop_interior(const void* yp, int B, int H, int W, int pix_bytes, int crop, const void* resid_f16, int64_t ldr, void* out,
+                  int64_t ldo_bytes, cudaStream_t stream) {
+  SDW_REQUIRE(yp && out && B > 0 && H > 0 && W > 0 && pix_bytes > 0 && crop >= 1, "crop: bad arguments");
+  const int vec = (pix_bytes % 16 == 0 && ldo_bytes % 16 == 0) ? 16 : ((pix_bytes % 8 == 0 && ldo_bytes % 8 == 0) ? 8 : 1);
+  SDW_REQUIRE(!resid_f16 || (vec == 16 && ldr % 8 == 0), "crop: the residual add needs 16-byte channel chunks");
+  const int64_t n = static_cast<int64_t>(B) * H * W * (pix_bytes / vec);
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  const uint8_t* ys = static_cast<const uint8_t*>(yp);
+  const __half* rs = static_cast<const __half*>(resid_f16);
+  uint8_t* os = static_cast<uint8_t*>(out);
+  if (vec == 16) crop_kernel<16><<<blocks, 256, 0, stream>>>(ys, B, H, W, pix_bytes, crop, rs, ldr, os, ldo_bytes);
+  else if (vec == 8) crop_kernel<8><<<blocks, 256, 0, stream>>>(ys, B, H, W, pix_bytes, crop, nullptr, 0, os, ldo_bytes);
+  else crop_kernel<1><<<blocks, 256, 0, stream>>>(ys, B, H, W, pix_bytes, crop, nullptr, 0, os, ldo_bytes);
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace sdw

@@ -218,9 +218,68 @@ struct Engine {
     *cur_count += 1;
     return 0;
   }
-  // conv / linear on NHWC views
+  // tiled = True: circular padding (reference P:841-858 patches every Conv2d to padding_mode="circular").  A 3x3 conv on the
+  // torus = the zero-padded conv of the wrap-padded image, cropped: pad (1 pixel; 2 for the stride-2 conv so that the
+  // output centres stay on even coordinates), run the unchanged tcgen05 kernel on the padded lattice, crop (+ residual).
+  bool tiled = false;
   int conv(const T& x, const __half* w, const float* bias, int N, int kind, const T& out, const T* resid = nullptr,
            const float* rowvec_table = nullptr, int mode = GEMM_PLAIN) {
+    if (!tiled || kind == 0) return conv_zero_pad(x, w, bias, N, kind, out, resid, rowvec_table, mode);
+    Scope scope(this);
+    const int pad = kind == 2 ? 2 : 1;
+    T xp = tmp(x.B, x.H + 2 * pad, x.W + 2 * pad, x.C);
+    tag_next = "wrap pad (tiled)";
+    emit([=](cudaStream_t st, int) { return wrap_pad(x.p, x.ld * 2, x.B, x.H, x.W, x.C * 2, pad, xp.p, st); });
+    const int oh = kind == 2 ? xp.H / 2 : (kind == 3 ? xp.H * 2 : xp.H), ow = kind == 2 ? xp.W / 2 : (kind == 3 ? xp.W * 2 : xp.W);
+    const int crop = kind == 3 ? 2 : 1;
+    T yp = tmp(x.B, oh, ow, N);
+    if (int e = conv_zero_pad(xp, w, bias, N, kind, yp, nullptr, rowvec_table, mode)) return e;
+    const T r = resid ? *resid : T{};
+    const bool has_r = resid != nullptr;
+    tag_next = "crop (tiled)";
+    emit([=](cudaStream_t st, int) {
+      return crop_interior(yp.p, out.B, out.H, out.W, N * 2, crop, has_r ? r.p : nullptr, r.ld, out.p, out.ld * 2, st);
+    });
+    return 0;
+  }
+  // the 4-channel edge convs of both nets (CUDA-core kernels) in tiled mode: same pad / run / crop scheme
+  int conv_in_edge(const T& xin, const __half* w, const float* b, int n, const T& o) {
+    if (!tiled) {
+      emit([=](cudaStream_t st, int) { return conv_in_small(xin.p, xin.ld, xin.B, xin.H, xin.W, xin.C, w, b, n, o.p, o.ld, st); });
+      return 0;
+    }
+    Scope scope(this);
+    T xp = tmp(xin.B, xin.H + 2, xin.W + 2, xin.C);
+    T yp = tmp(xin.B, xin.H + 2, xin.W + 2, n);
+    emit([=](cudaStream_t st, int) {
+      if (int e = wrap_pad(xin.p, xin.ld * 2, xin.B, xin.H, xin.W, xin.C * 2, 1, xp.p, st)) return e;
+      if (int e = conv_in_small(xp.p, xp.ld, xp.B, xp.H, xp.W, xp.C, w, b, n, yp.p, yp.ld, st)) return e;
+      return crop_interior(yp.p, o.B, o.H, o.W, n * 2, 1, nullptr, 0, o.p, o.ld * 2, st);
+    }, 3);
+    return 0;
+  }
+  int conv_out_edge(const T& n, const __half* w, const float* b, int oc, float* out_f32, uint8_t* out_u8) {
+    if (!tiled) {
+      emit([=](cudaStream_t st, int) { return conv_out_small(n.p, n.ld, n.B, n.H, n.W, n.C, w, b, oc, out_f32, out_u8, st); });
+      return 0;
+    }
+    Scope scope(this);
+    T xp = tmp(n.B, n.H + 2, n.W + 2, n.C);
+    const size_t pp = static_cast<size_t>(n.B) * (n.H + 2) * (n.W + 2);
+    float* f32p = static_cast<float*>(salloc(pp * oc * 4));
+    uint8_t* u8p = out_u8 ? static_cast<uint8_t*>(salloc(pp * oc)) : nullptr;
+    emit([=](cudaStream_t st, int) {
+      if (int e = wrap_pad(n.p, n.ld * 2, n.B, n.H, n.W, n.C * 2, 1, xp.p, st)) return e;
+      if (int e = conv_out_small(xp.p, xp.ld, xp.B, xp.H, xp.W, xp.C, w, b, oc, f32p, u8p, st)) return e;
+      if (out_f32)
+        if (int e = crop_interior(f32p, n.B, n.H, n.W, oc * 4, 1, nullptr, 0, out_f32, oc * 4, st)) return e;
+      if (out_u8) return crop_interior(u8p, n.B, n.H, n.W, oc, 1, nullptr, 0, out_u8, oc, st);
+      return 0;
+    }, 4);
+    return 0;
+  }
+  int conv_zero_pad(const T& x, const __half* w, const float* bias, int N, int kind, const T& out, const T* resid = nullptr,
+                    const float* rowvec_table = nullptr, int mode = GEMM_PLAIN) {
     const int npar = kind == 3 ? 4 : 1;
     for (int par = 0; par < npar; ++par) {
       GemmDesc d;
@@ -481,7 +540,8 @@ struct Engine {
       const T o = h;
       const int cin = cfg.in_channels, n = ch[0];
       tag_next = "conv_in 4->C (CUDA cores)";
-      emit([=](cudaStream_t st, int) { return conv_in_small(xin.p, xin.ld, xin.B, xin.H, xin.W, cin, w, b, n, o.p, o.ld, st); });
+      (void)cin;
+      if (int e = conv_in_edge(xin, w, b, n, o)) return e;
     }
     // down path
     for (int i = 0; i < nlev; ++i) {
@@ -555,7 +615,7 @@ struct Engine {
       float* e_out = eps;
       const int oc = cfg.out_channels;
       tag_next = "conv_out C->4 (CUDA cores)";
-      emit([=](cudaStream_t st, int) { return conv_out_small(n.p, n.ld, n.B, n.H, n.W, n.C, w, b, oc, e_out, nullptr, st); });
+      if (int e = conv_out_edge(n, w, b, oc, e_out, nullptr)) return e;
     }
     return 0;
   }
@@ -584,7 +644,7 @@ struct Engine {
       const float* b = vec("vae.decoder.conv_in.bias", ctop);
       const T o = h;
       tag_next = "vae conv_in 4->C (CUDA cores)";
-      emit([=](cudaStream_t st, int) { return conv_in_small(z.p, z.ld, F, H0, W0, lc, w, b, ctop, o.p, o.ld, st); });
+      if (int e = conv_in_edge(z, w, b, ctop, o)) return e;
     }
     // mid block
     {
@@ -653,7 +713,7 @@ struct Engine {
       float* of = out_img_f32;
       const int oc = cfg.vae_out_channels;
       tag_next = "vae conv_out C->3 + uint8 (CUDA cores)";
-      emit([=](cudaStream_t st, int) { return conv_out_small(n.p, n.ld, n.B, n.H, n.W, n.C, w, b, oc, of, o8, st); });
+      if (int e = conv_out_edge(n, w, b, oc, of, o8)) return e;
     }
     return 0;
   }
@@ -779,6 +839,7 @@ int sdw_engine_create(const sdw_engine_config* cfg, sdw_engine** out) {
   if (int e = validate(cfg)) return e;
   Engine* E = new Engine();
   E->cfg = *cfg;
+  E->tiled = cfg->tiled != 0;
   if (const char* nf = std::getenv("SDW_NO_FLASH")) E->use_flash = !(nf[0] == '1');
   if (int e = E->build(true, nullptr)) {
     delete E;

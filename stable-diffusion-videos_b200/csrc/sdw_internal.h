@@ -206,6 +206,10 @@ int cfg_sched_step(const float* eps, int has_uncond, float* x, float* x_base, fl
 int latents_init(const void* latents, int is_f16, float sigma, float in_scale, float* x, void* model_in, int cpad,
                  int dup, int F, int C, int H, int W, cudaStream_t stream);
 int pack_weight(const void* w, int N, int C, int kh, int kw, int geglu, void* out, cudaStream_t stream);
+// tiled = True (circular convolution padding): wrap-padded copy of an NHWC image / interior of a padded result
+int wrap_pad(const void* x, int64_t ld_bytes, int B, int H, int W, int pix_bytes, int pad, void* y, cudaStream_t stream);
+int crop_interior(const void* yp, int B, int H, int W, int pix_bytes, int crop, const void* resid_f16, int64_t ldr, void* out,
+                  int64_t ldo_bytes, cudaStream_t stream);
 // upsampler weights: 4 parity blocks of [N][4][Cp] (taps pre-summed); block p = py*2+px at out + p*N*4*Cp
 int pack_weight_up4(const void* w, int N, int C, void* out, cudaStream_t stream);
 

@@ -22,13 +22,13 @@ class EngineConfig(C.Structure):
         ("vae_norm_num_groups", C.c_int32), ("vae_out_channels", C.c_int32), ("vae_scale", C.c_int32),
         ("vae_scaling_factor", C.c_float),
         ("latent_h", C.c_int32), ("latent_w", C.c_int32), ("frames", C.c_int32), ("guidance", C.c_int32),
-        ("max_steps", C.c_int32),
+        ("max_steps", C.c_int32), ("tiled", C.c_int32),
     ]
 
 
 class Engine:
     def __init__(self, unet_cfg: UNetConfig, vae_cfg: VAEConfig, latent_hw, frames, guidance=True, ctx_tokens=77,
-                 max_steps=128, device=None):
+                 max_steps=128, device=None, tiled=False):
         if not torch.cuda.is_available():
             raise N.SdwError("the native engine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
@@ -57,6 +57,7 @@ class Engine:
         c.vae_scaling_factor = vae_cfg.scaling_factor
         c.latent_h, c.latent_w = self.latent_hw
         c.frames, c.guidance, c.max_steps = self.frames, int(self.guidance), max_steps
+        c.tiled = int(bool(tiled))  # circular convolution padding (reference from_pretrained(tiled=True), P:841-858)
         self.cfg = c
         self.vae_scale = c.vae_scale
         lib = N.lib()

@@ -197,9 +197,6 @@ class StableDiffusionWalkPipeline:
     @classmethod
     def from_pretrained(cls, path, *args, tiled=False, torch_dtype=None, safety_checker=None, **kwargs):
         """Load a LOCAL diffusers-layout checkpoint directory (unet/, vae/, text_encoder/, tokenizer/, scheduler/)."""
-        if tiled:
-            raise NotImplementedError("tiled=True (circular padding, P:841-858) is not implemented in the native "
-                                      "conv kernels yet (SURVEY.md §8f row 4)")
         from safetensors.torch import load_file
 
         root = Path(path)
@@ -282,11 +279,11 @@ class StableDiffusionWalkPipeline:
 
     # ------------------------------------------------------------------------------------------
     def _engine(self, h, w, frames, guidance):
-        key = (h, w, frames, guidance)
+        key = (h, w, frames, guidance, bool(self.tiled))
         eng = self._engines.get(key)
         if eng is None:
             eng = Engine(self.unet.cfg, self.vae.cfg, (h, w), frames, guidance=guidance,
-                         ctx_tokens=self.tokenizer.model_max_length, device=self.device)
+                         ctx_tokens=self.tokenizer.model_max_length, device=self.device, tiled=bool(self.tiled))
             eng.load_state_dict(self.unet.state, self.vae.state)
             self._engines = {key: eng}  # one resident engine (each carries its own packed weights)
         return eng
@@ -455,7 +452,9 @@ class StableDiffusionWalkPipeline:
         h8, w8 = height // 8, width // 8
         do_cfg = guidance_scale > 1.0
         uncond = self._uncond([negative_prompt if negative_prompt is not None else ""]) if do_cfg else None
-        sink = _FrameSink(save_path, image_file_ext, (batch_size, height, width, self.vae.cfg.out_channels),
+        # decoded frame size = latent size x vae_scale_factor (the reference hard-codes // 8 for the latents, P:368)
+        out_h, out_w = h8 * self.vae_scale_factor, w8 * self.vae_scale_factor
+        sink = _FrameSink(save_path, image_file_ext, (batch_size, out_h, out_w, self.vae.cfg.out_channels),
                           self.device) if rank == 0 else None
         mine = []  # this rank's frames, on the device, when they have to travel to rank 0
         frame_index = skip + lo
@@ -476,7 +475,7 @@ class StableDiffusionWalkPipeline:
             frame_index += nb
         if world > 1:
             # decoded frames travel to rank 0 over NCCL (NVLink); rank 0 alone writes files (reference layout P:550-554)
-            shape = (0, height, width, self.vae.cfg.out_channels)
+            shape = (0, out_h, out_w, self.vae.cfg.out_channels)
             local = torch.cat(mine) if mine else torch.empty(shape, dtype=torch.uint8, device=self.device)
             allf = parallel.gather_frames(local, Tk.shape[0], dst=0)
             if rank == 0:

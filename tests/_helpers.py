@@ -53,3 +53,12 @@ TINY_VAE = OVAEConfig(block_out_channels=(32, 64), layers_per_block=1, norm_num_
 MID_UNET = OUNetConfig(block_out_channels=(320, 640, 640, 640), attention_head_dim=8, cross_attention_dim=768,
                        norm_num_groups=32, sample_size=16)
 MID_VAE = OVAEConfig(block_out_channels=(64, 128, 128), layers_per_block=1, norm_num_groups=32)
+
+
+def set_tiled(*modules):
+    """the reference's `tiled=True` (stable_diffusion_pipeline.py:841-858): every nn.Conv2d pads circularly"""
+    for m in modules:
+        for sub in m.modules():
+            if isinstance(sub, torch.nn.Conv2d) and sub.padding != (0, 0):
+                sub.padding_mode = "circular"
+    return modules

@@ -13,12 +13,16 @@ from _helpers import MID_UNET, MID_VAE, TINY_UNET, TINY_VAE, make_oracle, produc
 pytestmark = pytest.mark.gpu
 
 
-def _engine(ocfg_u, ocfg_v, hw, frames, guidance=True, seed=0):
+def _engine(ocfg_u, ocfg_v, hw, frames, guidance=True, seed=0, tiled=False):
     from stable_diffusion_videos_b200.engine import Engine
 
     unet, vae = make_oracle(ocfg_u, ocfg_v, seed=seed)
+    if tiled:
+        from _helpers import set_tiled
+
+        set_tiled(unet, vae)
     ucfg, vcfg = product_cfgs(ocfg_u, ocfg_v)
-    eng = Engine(ucfg, vcfg, hw, frames, guidance=guidance, max_steps=64)
+    eng = Engine(ucfg, vcfg, hw, frames, guidance=guidance, max_steps=64, tiled=tiled)
     eng.load_state_dict(unet.state_dict(), vae.state_dict())
     return eng, unet, vae
 
@@ -86,6 +90,34 @@ def test_full_sampler_tiny(kind, steps):
         assert _rel_l2(fin.cpu(), lat_ref) <= 1e-2, (kind, use_graph, _rel_l2(fin.cpu(), lat_ref))
         d = np.abs(u8.cpu().numpy().astype(np.int32) - to_uint8(img).astype(np.int32))
         assert d.mean() <= 1.0 and (d <= 2).mean() >= 0.99 and d.max() <= 8, (kind, d.mean(), d.max())
+
+
+@pytest.mark.parametrize("cfgs,hw,F", [((TINY_UNET, TINY_VAE), (8, 8), 2), ((MID_UNET, MID_VAE), (16, 16), 1)])
+def test_tiled_circular_padding_full_sampler(cfgs, hw, F):
+    """from_pretrained(tiled=True) (stable_diffusion_pipeline.py:841-858): every 3x3 conv of UNet and VAE pads circularly
+    (stride-2 downsamplers, the folded nearest-up convs and the 4-channel edge convs included).  Also checks that the
+    result really differs from the zero-padded one (the test would otherwise pass with the flag ignored)."""
+    from oracle.pipeline import sample_frames, synthetic_embedding, to_uint8
+    from oracle.schedulers import make_scheduler
+    from stable_diffusion_videos_b200.schedulers import PNDMScheduler
+
+    eng, unet, vae = _engine(cfgs[0], cfgs[1], hw, frames=F, tiled=True)
+    D = cfgs[0].cross_attention_dim
+    g = torch.Generator().manual_seed(9)
+    lat = torch.randn(F, 4, *hw, generator=g)
+    cond = torch.cat([synthetic_embedding(k, dim=D) for k in range(F)]).half().float()
+    unc = synthetic_embedding("", dim=D).half().float()
+    img, lat_ref, raw_ref = sample_frames(unet, vae, make_scheduler("pndm"), lat, cond, unc, 3, 7.5, return_latents=True)
+    eng.set_scheduler(PNDMScheduler(), 3, 7.5)
+    u8, fin = eng.sample(lat.cuda(), cond.cuda(), unc.cuda(), use_graph=True, return_latents=True)
+    torch.cuda.synchronize()
+    assert _rel_l2(fin.cpu(), lat_ref) <= 1e-2, _rel_l2(fin.cpu(), lat_ref)
+    d = np.abs(u8.cpu().numpy().astype(np.int32) - to_uint8(img).astype(np.int32))
+    assert d.mean() <= 1.0 and (d <= 2).mean() >= 0.99 and d.max() <= 8, (d.mean(), d.max())
+    eng0, _, _ = _engine(cfgs[0], cfgs[1], hw, frames=F, tiled=False)
+    eng0.set_scheduler(PNDMScheduler(), 3, 7.5)
+    _, fin0 = eng0.sample(lat.cuda(), cond.cuda(), unc.cuda(), use_graph=True, return_latents=True)
+    assert _rel_l2(fin0.cpu(), lat_ref) > 3e-2  # zero padding is a different function
 
 
 def test_slerp_lerp_batch_matches_reference_semantics():

@@ -43,8 +43,5 @@ for X in range(2):
     body = rows[4:-4].double()
     d = lambda a, b: float((body[:, b] - body[:, a]).mean())  # noqa: E731
     period = float((body[1:, 0] - body[:-1, 0]).mean())
-    tok = body[:, 4].min() > 0
-    print(f"query tile {'AB'[X]}: {rows.shape[0]} tiles; per KV tile: wait S {d(0, 1):.0f}, TMEM->regs {d(1, 2):.0f}, row max "
-          f"{d(2, 3):.0f}, " + (f"scale + token wait {d(3, 4):.0f}, MUFU burst {d(4, 5):.0f}, sum/pack/P store {d(5, 6):.0f}" if tok
-                               else f"exp + P store {d(3, 6):.0f}") +
-          f"; period {period:.0f} cycles (XU floor 1024 per tile, 2048 per A+B pair)")
+    print(f"query tile {'AB'[X]}: {rows.shape[0]} tiles; mean cycles between the stamps of a KV tile: "
+          + " ".join(f"{d(i, i + 1):.0f}" for i in range(6)) + f"; period {period:.0f} cycles per KV tile of {os.environ.get('BKV', '?')} keys")
