@@ -134,6 +134,9 @@ int sdw_engine_sample(sdw_engine* e, const float* latents_f32, const void* cond_
                       uint8_t* out_u8, float* out_latents, float* out_raw_f32, int use_graph, void* stream);
 /* use_graph = 1 captures the whole call into a CUDA graph on first use: `stream` must then be a real stream, not
  * the legacy default stream 0.  out_raw_f32 (optional): fp32 [F][8h][8w][3] decoder output BEFORE (x/2+0.5).clamp(0,1) — the float image of P:435 */
+/* per-sample negative prompts (P:318-358 with a list `negative_prompt`): n = frames makes `uncond_f16` of the sample calls
+ * a [frames][tokens][D] batch, n = 1 (default) one embedding shared by all frames */
+int sdw_engine_set_uncond_batch(sdw_engine* e, int n);
 int sdw_engine_launches(const sdw_engine* e, int* prologue, int* unet_per_step, int* vae);
 /* The same sampler in three segments, for per-step callbacks (stable_diffusion_pipeline.py:429-430): `begin` stages the
  * inputs and runs the prologue (context assembly, cross-attention K/V, first model input); `steps` runs denoise steps

@@ -100,7 +100,7 @@ __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.syn
 template <int REGS>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
-template <int DVP, int NS, int TOKEN>
+template <int DVP, int NS, int TOKEN, int TRACE>
 __global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = PPCfg<DVP, NS>;
   constexpr int ST = Cfg::ST, BKV = 128;
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(con
     const uint32_t t_p = tmem + lane_base + Cfg::P_COL + X * 64 + hlf * (COLS / 2);
     const uint32_t t_o = tmem + lane_base + Cfg::O_COL + X * 64;
     const float sl2 = p.scale_log2e;
-    const bool trace = p.dbg != nullptr && blockIdx.x == 0 && r == 0 && hlf == 0;
+    const bool trace = TRACE && p.dbg != nullptr && blockIdx.x == 0 && r == 0 && hlf == 0;
     constexpr float LAZY_LOG2 = 8.f;
     int gt = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
@@ -521,7 +521,8 @@ struct DBCfg {
 };
 
 // POLY: every POLY-th pair of exponentials runs on the FMA pipe (ex2_poly2) instead of the MUFU pipe (0 = none)
-template <int DVP, int POLY>
+// TRACE: compile the clock64 stamps in (tools/attn_trace.py); the shipped instantiations carry no trace code
+template <int DVP, int POLY, int TRACE>
 __global__ void __launch_bounds__(DBCfg<DVP>::THREADS, 1) attn_db_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = DBCfg<DVP>;
   constexpr int ST = Cfg::ST, BKV = Cfg::BKV, NCH = BKV / 32;
@@ -607,10 +608,12 @@ __global__ void __launch_bounds__(DBCfg<DVP>::THREADS, 1) attn_db_kernel(const _
         int kvc = 0, gt = 0, wi = 0;  // KV ring position, score tiles of THIS pipeline so far, work items
         // S of local tile j (global tile g): buffer g & 1.  Its previous content (P of tile g - 2) was consumed by PV(g - 2),
         // issued earlier by this same thread: tcgen05 operations of one thread execute in order, so no barrier is needed.
-        auto issue_s = [&](int j) {
-          const int g = gt + j, s = (kvc + j) % ST;
-          mbar_wait(&kv_full[s], ((kvc + j) / ST) & 1);
+        auto wait_kv = [&](int j) {
+          mbar_wait(&kv_full[(kvc + j) % ST], ((kvc + j) / ST) & 1);
           tc_fence_after();
+        };
+        auto issue_s = [&](int j) {  // K_j has been waited for (wait_kv)
+          const int g = gt + j, s = (kvc + j) % ST;
           const uint32_t k_addr = smem_u32(k_smem + s * Cfg::K_STAGE);
           const uint32_t ts = t_sx + (g & 1) * BKV;
           for (int ks = 0; ks < p.dk_steps; ++ks)
@@ -622,10 +625,15 @@ __global__ void __launch_bounds__(DBCfg<DVP>::THREADS, 1) attn_db_kernel(const _
         for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++wi) {
           mbar_wait(&q_full[X], wi & 1);
           tc_fence_after();
+          wait_kv(0);
           issue_s(0);
-          if (ntiles > 1) issue_s(1);
+          if (ntiles > 1) {
+            wait_kv(1);
+            issue_s(1);
+          }
           for (int j = 0; j < ntiles; ++j) {
             const int g = gt + j;
+            if (j + 2 < ntiles) wait_kv(j + 2);  // off the critical path: the softmax of tile j is still running
             mbar_wait(&p_ready[X], g & 1);
             tc_fence_after();
             const int s = (kvc + j) % ST;
@@ -656,7 +664,7 @@ __global__ void __launch_bounds__(DBCfg<DVP>::THREADS, 1) attn_db_kernel(const _
     const uint32_t t_o = tmem + lane_base + Cfg::O_COL + X * 64;
     const float sl2 = p.scale_log2e;
     const uint64_t sl2_2 = pk2(sl2, sl2);
-    const bool trace = p.dbg != nullptr && blockIdx.x == 0 && r == 0;
+    const bool trace = TRACE && p.dbg != nullptr && blockIdx.x == 0 && r == 0;
     constexpr float LAZY_LOG2 = 8.f;
     int gt = 0;
     // row max of 32 score columns (keys kv0 .. kv0 + 31; keys >= Nk do not exist)
@@ -724,8 +732,9 @@ __global__ void __launch_bounds__(DBCfg<DVP>::THREADS, 1) attn_db_kernel(const _
         const uint64_t nmb_2 = pk2(-mb, -mb);
         uint64_t sm2[4] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
         m_next = -INFINITY;
-        // ---- one stream: exponentials of S_j chunk c, row max of S_{j+1} chunk c - 1 -----------------
-        uint32_t xa[32], xb[32], y[32];
+        // ---- one stream: exponentials of S_j chunk by chunk; the row max of S_{j+1} rides on the last chunk -------------
+        // (S_{j+1} is issued behind PV_{j-1}, i.e. at the start of this tile: it lands ~600 cycles in, measured)
+        uint32_t xa[32], xb[32], y[NCH][32];
         tmem_ld_32x32(ts, xa);
         tmem_ld_wait();
 #pragma unroll
@@ -733,17 +742,17 @@ __global__ void __launch_bounds__(DBCfg<DVP>::THREADS, 1) attn_db_kernel(const _
           uint32_t(&cur)[32] = (c & 1) ? xb : xa;
           uint32_t(&nxt)[32] = (c & 1) ? xa : xb;
           if (c + 1 < NCH) tmem_ld_32x32(ts + (c + 1) * 32, nxt);
-          if (has_next && c >= 1) {
-            if (c == 1) {  // S_{j+1} was issued right behind PV_{j-1}: ready by now
-              mbar_wait(&s_full[2 * X + ((gt + 1) & 1)], ((gt + 1) >> 1) & 1);
-              tc_fence_after();
-              if (trace) ts1 = clock64();
-            }
-            tmem_ld_32x32(tn + (c - 1) * 32, y);
+          if (has_next && c == NCH - 1) {
+            mbar_wait(&s_full[2 * X + ((gt + 1) & 1)], ((gt + 1) >> 1) & 1);
+            tc_fence_after();
+            if (trace) ts1 = clock64();
+#pragma unroll
+            for (int cc = 0; cc < NCH; ++cc) tmem_ld_32x32(tn + cc * 32, y[cc]);
           }
           uint32_t pkc[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
+            if (has_next && c == NCH - 1 && i == 16) tmem_ld_wait();  // S_{j+1} is in registers: its max interleaves with the rest
             float t0, t1;
             upk2(fma2(pk2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sl2_2, nmb_2), t0, t1);
             float e0, e1;
@@ -760,15 +769,13 @@ __global__ void __launch_bounds__(DBCfg<DVP>::THREADS, 1) attn_db_kernel(const _
             sm2[(i >> 1) & 3] = add2(sm2[(i >> 1) & 3], pk2(e0, e1));
             pkc[i >> 1] = pack_h2(e0, e1);
           }
-          tmem_ld_wait();  // chunk c + 1 of S_j and chunk c - 1 of S_{j+1} have landed
+          if (c + 1 < NCH) tmem_ld_wait();  // chunk c + 1 of S_j has landed
           // P chunk c -> columns [16 c, 16 c + 16) of S_j's own buffer: those score columns were consumed in chunk c / 2
           tmem_st_32x16(ts + c * 16, pkc);
-          if (has_next && c >= 1) m_next = fmaxf(m_next, chunk_max(y, (j + 1) * BKV + (c - 1) * 32));
         }
-        if (has_next) {  // last chunk of S_{j+1}
-          tmem_ld_32x32(tn + (NCH - 1) * 32, y);
-          tmem_ld_wait();
-          m_next = fmaxf(m_next, chunk_max(y, (j + 1) * BKV + (NCH - 1) * 32));
+        if (has_next) {
+#pragma unroll
+          for (int cc = 0; cc < NCH; ++cc) m_next = fmaxf(m_next, chunk_max(y[cc], (j + 1) * BKV + cc * 32));
         }
         {
           float s0, s1, s2, s3, s4, s5, s6, s7;
@@ -1231,13 +1238,14 @@ static int attn_set_attr() {
 }
 template <int DVP>
 static int attn_pp_set_attr() {
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 1>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 2>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 1>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 2>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_db_kernel<DVP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBCfg<DVP>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_db_kernel<DVP, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBCfg<DVP>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_db_kernel<DVP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBCfg<DVP>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 1>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 1>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 1>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 1>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_db_kernel<DVP, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBCfg<DVP>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_db_kernel<DVP, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBCfg<DVP>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_db_kernel<DVP, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBCfg<DVP>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_db_kernel<DVP, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBCfg<DVP>::SMEM));
   return 0;
 }
 
@@ -1359,17 +1367,18 @@ static cudaError_t launch_pp(const AttnLaunchImpl* I, cudaStream_t stream) {
   if (I->variant >= 12) {
     // SDW_ATTN_POLY=4|2: every 4th / 2nd pair of exponentials on the FMA pipe (measurement switch)
     static const int poly = [] { const char* e = std::getenv("SDW_ATTN_POLY"); return e ? std::atoi(e) : 0; }();
-    if (poly == 4) return launch_pdl(attn_db_kernel<DVP, 4>, I->grid, dim3(DBCfg<DVP>::THREADS), DBCfg<DVP>::SMEM, stream, p);
-    if (poly == 2) return launch_pdl(attn_db_kernel<DVP, 2>, I->grid, dim3(DBCfg<DVP>::THREADS), DBCfg<DVP>::SMEM, stream, p);
-    return launch_pdl(attn_db_kernel<DVP, 0>, I->grid, dim3(DBCfg<DVP>::THREADS), DBCfg<DVP>::SMEM, stream, p);
+    if (p.dbg) return launch_pdl(attn_db_kernel<DVP, 0, 1>, I->grid, dim3(DBCfg<DVP>::THREADS), DBCfg<DVP>::SMEM, stream, p);
+    if (poly == 4) return launch_pdl(attn_db_kernel<DVP, 4, 0>, I->grid, dim3(DBCfg<DVP>::THREADS), DBCfg<DVP>::SMEM, stream, p);
+    if (poly == 2) return launch_pdl(attn_db_kernel<DVP, 2, 0>, I->grid, dim3(DBCfg<DVP>::THREADS), DBCfg<DVP>::SMEM, stream, p);
+    return launch_pdl(attn_db_kernel<DVP, 0, 0>, I->grid, dim3(DBCfg<DVP>::THREADS), DBCfg<DVP>::SMEM, stream, p);
   }
-  // SDW_ATTN_NS=1: one softmax thread per query row (A/B measurements); default two
-  static const bool ns1 = [] { const char* e = std::getenv("SDW_ATTN_NS"); return e && e[0] == '1'; }();
-  static const bool tok = [] { const char* e = std::getenv("SDW_ATTN_TOKEN"); return !(e && e[0] == '0'); }();
-  if (ns1 && tok) return launch_pdl(attn_pp_kernel<DVP, 1, 1>, I->grid, dim3(PPCfg<DVP, 1>::THREADS), PPCfg<DVP, 1>::SMEM, stream, p);
-  if (ns1) return launch_pdl(attn_pp_kernel<DVP, 1, 0>, I->grid, dim3(PPCfg<DVP, 1>::THREADS), PPCfg<DVP, 1>::SMEM, stream, p);
-  if (tok) return launch_pdl(attn_pp_kernel<DVP, 2, 1>, I->grid, dim3(PPCfg<DVP, 2>::THREADS), PPCfg<DVP, 2>::SMEM, stream, p);
-  return launch_pdl(attn_pp_kernel<DVP, 2, 0>, I->grid, dim3(PPCfg<DVP, 2>::THREADS), PPCfg<DVP, 2>::SMEM, stream, p);
+  // SDW_ATTN_TOKEN=1: the MUFU bursts of the two query tiles alternate through a token (measurement switch)
+  static const bool tok = [] { const char* e = std::getenv("SDW_ATTN_TOKEN"); return e && e[0] == '1'; }();
+  constexpr int TH = PPCfg<DVP, 1>::THREADS, SM = PPCfg<DVP, 1>::SMEM;
+  if (p.dbg) return tok ? launch_pdl(attn_pp_kernel<DVP, 1, 1, 1>, I->grid, dim3(TH), SM, stream, p)
+                        : launch_pdl(attn_pp_kernel<DVP, 1, 0, 1>, I->grid, dim3(TH), SM, stream, p);
+  return tok ? launch_pdl(attn_pp_kernel<DVP, 1, 1, 0>, I->grid, dim3(TH), SM, stream, p)
+             : launch_pdl(attn_pp_kernel<DVP, 1, 0, 0>, I->grid, dim3(TH), SM, stream, p);
 }
 
 int launch_attention(const AttnLaunch& L, cudaStream_t stream) {

@@ -68,6 +68,7 @@ struct Engine {
   __half* ctx = nullptr;        // [Bn][tokens][D]
   __half* cond_stage = nullptr; // [F][tokens][D]
   __half* uncond_stage = nullptr;
+  int uncond_batch = 1;  // 1: one unconditional embedding shared by all frames; frames: one per frame (per-sample negative prompts)
   void* lat_stage = nullptr;    // [F][4][H][W] fp32-sized
   uint8_t* out_u8 = nullptr;    // [F][8H][8W][3]
   float* out_img_f32 = nullptr; // pre-clamp decoder output (debug / parity)
@@ -746,7 +747,7 @@ struct Engine {
     const int64_t per = static_cast<int64_t>(cfg.ctx_tokens) * cfg.cross_attention_dim;
     ctx = static_cast<__half*>(alloc(static_cast<size_t>(Bn) * per * 2));
     cond_stage = static_cast<__half*>(alloc(static_cast<size_t>(Bn) * per * 2));  // room for a full [Bn] context
-    uncond_stage = static_cast<__half*>(alloc(static_cast<size_t>(per) * 2));
+    uncond_stage = static_cast<__half*>(alloc(static_cast<size_t>(cfg.frames) * per * 2));
     const int OH = H * cfg.vae_scale, OW = W * cfg.vae_scale;
     out_u8 = static_cast<uint8_t*>(alloc(static_cast<size_t>(F) * OH * OW * cfg.vae_out_channels));
     out_img_f32 = static_cast<float*>(alloc(static_cast<size_t>(F) * OH * OW * cfg.vae_out_channels * 4));
@@ -790,18 +791,18 @@ using namespace sdw;
 
 namespace sdw {
 __global__ void ctx_assemble_kernel(const __half* __restrict__ cond, const __half* __restrict__ uncond, int F, int dup,
-                                    int64_t per, __half* __restrict__ out) {
+                                    int64_t per, __half* __restrict__ out, int uncond_per_frame) {
   const int64_t total = static_cast<int64_t>(F) * (dup ? 2 : 1) * per;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t b = i / per, r = i % per;
-    if (dup) out[i] = b < F ? uncond[r] : cond[(b - F) * per + r];  // cat([uncond.repeat(F), cond]) — P:352-358
+    if (dup) out[i] = b < F ? uncond[(uncond_per_frame ? b * per : 0) + r] : cond[(b - F) * per + r];  // cat([uncond(.repeat(F)), cond]) — P:352-358
     else out[i] = cond[i];
   }
 }
 int unet_ctx_assemble(const __half* cond, const __half* uncond, int F, int dup, int64_t per, __half* out,
-                      cudaStream_t stream) {
-  ctx_assemble_kernel<<<148 * 2, 256, 0, stream>>>(cond, uncond, F, dup, per, out);
+                      cudaStream_t stream, int uncond_per_frame = 0) {
+  ctx_assemble_kernel<<<148 * 2, 256, 0, stream>>>(cond, uncond, F, dup, per, out, uncond_per_frame);
   SDW_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -961,7 +962,7 @@ static int run_all(Engine* E, cudaStream_t st) {
   const sdw_engine_config& c = E->cfg;
   const int F = c.frames, H = c.latent_h, W = c.latent_w, lc = c.in_channels;
   const int64_t per = static_cast<int64_t>(c.ctx_tokens) * c.cross_attention_dim;
-  if (int rc = unet_ctx_assemble(E->cond_stage, E->uncond_stage, F, c.guidance, per, E->ctx, st)) return rc;
+  if (int rc = unet_ctx_assemble(E->cond_stage, E->uncond_stage, F, c.guidance, per, E->ctx, st, E->uncond_batch > 1)) return rc;
   if (int rc = run_ops(E->prologue, st, 0)) return rc;
   if (int rc = latents_init(E->lat_stage, 0, E->init_sigma, E->first_in_scale, E->x, E->model_in, lc, c.guidance, F, lc,
                             H, W, st))
@@ -983,7 +984,7 @@ static int stage_inputs(Engine* E, const float* latents_f32, const void* cond_f1
   SDW_CUDA_OK(cudaMemcpyAsync(E->lat_stage, latents_f32, nlat * 4, cudaMemcpyDeviceToDevice, st));
   SDW_CUDA_OK(cudaMemcpyAsync(E->cond_stage, cond_f16, static_cast<size_t>(c.frames) * per * 2, cudaMemcpyDeviceToDevice, st));
   if (c.guidance)
-    SDW_CUDA_OK(cudaMemcpyAsync(E->uncond_stage, uncond_f16, static_cast<size_t>(per) * 2, cudaMemcpyDeviceToDevice, st));
+    SDW_CUDA_OK(cudaMemcpyAsync(E->uncond_stage, uncond_f16, static_cast<size_t>(E->uncond_batch) * per * 2, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -1045,7 +1046,7 @@ int sdw_engine_sample_begin(sdw_engine* e, const float* latents_f32, const void*
   const sdw_engine_config& c = E->cfg;
   if (int rc = stage_inputs(E, latents_f32, cond_f16, uncond_f16, st)) return rc;
   const int64_t per = static_cast<int64_t>(c.ctx_tokens) * c.cross_attention_dim;
-  if (int rc = unet_ctx_assemble(E->cond_stage, E->uncond_stage, c.frames, c.guidance, per, E->ctx, st)) return rc;
+  if (int rc = unet_ctx_assemble(E->cond_stage, E->uncond_stage, c.frames, c.guidance, per, E->ctx, st, E->uncond_batch > 1)) return rc;
   if (int rc = run_ops(E->prologue, st, 0)) return rc;
   return latents_init(E->lat_stage, 0, E->init_sigma, E->first_in_scale, E->x, E->model_in, c.in_channels, c.guidance,
                       c.frames, c.in_channels, c.latent_h, c.latent_w, st);
@@ -1072,6 +1073,18 @@ int sdw_engine_sample_end(sdw_engine* e, uint8_t* out_u8, float* out_latents, fl
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int rc = run_ops(E->vae_ops, st, 0)) return rc;
   return copy_outputs(E, out_u8, out_latents, out_raw_f32, st);
+}
+
+int sdw_engine_set_uncond_batch(sdw_engine* e, int n) {
+  Engine* E = reinterpret_cast<Engine*>(e);
+  SDW_REQUIRE(E && !E->dry, "engine not bound");
+  SDW_REQUIRE(n == 1 || n == E->cfg.frames, "the unconditional batch is 1 (shared) or `frames` (one per frame)");
+  if (n != E->uncond_batch && E->graph_exec) {  // the captured graph has the other addressing baked in
+    cudaGraphExecDestroy(E->graph_exec);
+    E->graph_exec = nullptr;
+  }
+  E->uncond_batch = n;
+  return 0;
 }
 
 int sdw_engine_launches(const sdw_engine* e, int* prologue, int* unet, int* vae) {

@@ -176,9 +176,12 @@ class Engine:
         if tuple(cond.shape) != (F, self.ctx_tokens, D):
             raise ValueError(f"Unexpected text_embeddings shape, got {tuple(cond.shape)}, expected "
                              f"{(F, self.ctx_tokens, D)}")
-        if self.guidance and (uncond is None or tuple(uncond.shape) != (1, self.ctx_tokens, D)):
+        if self.guidance and (uncond is None or tuple(uncond.shape) not in ((1, self.ctx_tokens, D), (F, self.ctx_tokens, D))):
             raise ValueError(f"Unexpected unconditional embedding shape, got "
-                             f"{None if uncond is None else tuple(uncond.shape)}, expected {(1, self.ctx_tokens, D)}")
+                             f"{None if uncond is None else tuple(uncond.shape)}, expected {(1, self.ctx_tokens, D)} "
+                             f"(shared) or {(F, self.ctx_tokens, D)} (one per sample)")
+        if self.guidance:
+            N.check(N.lib().sdw_engine_set_uncond_batch(self._h, int(uncond.shape[0])))
         lat = latents.to(torch.float32).contiguous()
         cnd = cond.to(torch.float16).contiguous()
         unc = uncond.to(torch.float16).contiguous() if uncond is not None else None

@@ -360,10 +360,10 @@ class StableDiffusionWalkPipeline:
                                  " `negative_prompt` matches the batch size of `prompt`.")
             else:
                 uncond_tokens = negative_prompt
-            if len(uncond_tokens) != 1:
-                raise NotImplementedError("per-sample negative prompts are not implemented (one shared negative "
-                                          "prompt, as walk() passes, is)")
-            uncond = self._uncond(uncond_tokens)
+            uncond = self._uncond(uncond_tokens)  # [1, ...] shared, or one per prompt (P:331-336)
+            if uncond.shape[0] > 1:  # P:352-355: duplicated per image of a prompt
+                uncond = uncond.repeat(1, num_images_per_prompt, 1).view(uncond.shape[0] * num_images_per_prompt,
+                                                                         uncond.shape[1], -1)
 
         B = batch_size * num_images_per_prompt
         latents_shape = (B, self.unet.in_channels, height // 8, width // 8)

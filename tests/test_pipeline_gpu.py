@@ -130,3 +130,19 @@ def test_callback_sees_every_step_and_does_not_change_the_frames(pipe_and_oracle
                   4, 7.5, callback=lambda i, t, x: ref.append(x.clone()))
     for (i, _, x) in seen:
         assert float((x - ref[i]).norm() / ref[i].norm()) <= 1e-2
+
+
+def test_per_sample_negative_prompts(pipe_and_oracle):
+    """a list `negative_prompt` (one per prompt, P:331-358): each sample is guided away from ITS negative embedding —
+    sample k of the batch call equals the single-sample call with negative prompt k."""
+    pipe, _, _ = pipe_and_oracle
+    g = torch.Generator(device="cuda").manual_seed(5)
+    lat = torch.randn(2, 4, 8, 8, generator=g, device="cuda", dtype=torch.float16)
+    kw = dict(height=64, width=64, num_inference_steps=3, output_type="numpy")
+    both = pipe(prompt=["0", "1"], negative_prompt=["7", "8"], latents=lat, **kw).images
+    for k, neg in enumerate(["7", "8"]):
+        one = pipe(prompt=str(k), negative_prompt=neg, latents=lat[k:k + 1], **kw).images
+        assert np.abs(both[k] - one[0]).max() <= 2e-3
+    assert np.abs(both[0] - pipe(prompt="0", negative_prompt="8", latents=lat[:1], **kw).images[0]).max() > 1e-2
+    with pytest.raises(ValueError, match="batch size"):
+        pipe(prompt=["0", "1"], negative_prompt=["7"], **kw)

@@ -38,8 +38,11 @@ def bench(B, heads, Nq, Nk, d, iters=10):
 
 if __name__ == "__main__":
     F = int(os.environ.get("F", "8"))
-    for name, B, h, Nq, Nk, d in [("self 64x64 d40", 2 * F, 8, 4096, 4096, 40), ("cross 64x64 d40", 2 * F, 8, 4096, 77, 40),
+    shapes = [("self 64x64 d40", 2 * F, 8, 4096, 4096, 40), ("cross 64x64 d40", 2 * F, 8, 4096, 77, 40),
                                   ("self 32x32 d80", 2 * F, 8, 1024, 1024, 80), ("self 16x16 d160", 2 * F, 8, 256, 256, 160),
-                                  ("cross 32x32 d80", 2 * F, 8, 1024, 77, 80)]:
+              ("cross 32x32 d80", 2 * F, 8, 1024, 77, 80)]
+    if os.environ.get("ONLY_SELF"):  # A/B runs of the dominant shape only
+        shapes = shapes[:1]
+    for name, B, h, Nq, Nk, d in shapes:
         ms, tf, floor = bench(B, h, Nq, Nk, d)
         print(f"{name:18s} B={B:3d} {ms*1e3:9.1f} us {tf:8.1f} TFLOP/s  (all-MUFU exp floor {floor:7.1f} us)", flush=True)
