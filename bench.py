@@ -92,8 +92,20 @@ def cpu_reference_leg(steps, warmup, budget_s=150.0):
     from oracle.unet import UNet2DConditionModel, UNetConfig
     from oracle.vae import AutoencoderKLDecoder, VAEConfig
 
-    # all host cores, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)
-    threads = os.cpu_count() or 1
+    # all host cores, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1).  "All cores" =
+    # the PHYSICAL cores this process may run on: with one thread per hyper-thread (os.cpu_count() = 128 on the GPU box) the
+    # same forward took 88 s instead of 7.6 s (profiles/r02_bench_F30_db_attention.json vs BENCH_r01)
+    try:
+        import psutil
+
+        physical = psutil.cpu_count(logical=False) or os.cpu_count() or 1
+    except Exception:
+        physical = max(1, (os.cpu_count() or 2) // 2)
+    try:
+        physical = min(physical, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    threads = max(1, physical)
     torch.set_num_threads(threads)
     threads = torch.get_num_threads()
     torch.manual_seed(0)

@@ -7,15 +7,17 @@
 //
 // attn_pp_kernel  (head dim <= 64, more than one KV tile: every self-attention of SD-1.x at 64x64 / SD-2.1)
 //   Persistent CTA, one per SM, working on TWO 128-query tiles (A, B) of one (b, h) at a time against a shared K / V^T
-//   ring.  Warp roles: TMA producer; one MMA-issuing warp per query tile; one softmax warpgroup per query tile.  Per KV
-//   tile and query tile:  S = Q K^T (M=128, N=128, fp32 in TMEM)  ->  the softmax warpgroup pulls the whole score row
-//   into registers with ONE pass of tcgen05.ld and immediately hands the S columns back (s_free), so S_{j+1} is computed
-//   while the exponentials of tile j run — the S -> softmax -> P -> PV hand-off that capped the one-tile kernel at 62 %
-//   MUFU occupancy (profiles/r01_ncu_attn_lazy.md) is off the critical path; row max first, then exponentials against
-//   a lazily updated reference max (O is rescaled in TMEM only when a row max moves by more than 2^8), P written back to
-//   tensor memory as fp16 pairs and O += P V issued as a TS-mode MMA.  The two warpgroups share each scheduler's MUFU
-//   pipe (one ex2 per score, 16 / clk / SM — the bound of this kernel at head dim 40), so one tile's exponentials fill
-//   the other's TMEM-load / row-max / barrier gaps.  Registers are re-balanced with setmaxnreg (softmax 224, rest 48).
+//   ring.  Warp roles: TMA producer; one MMA-issuing warp per query tile; one softmax warpgroup per query tile (thread =
+//   query row).  Per KV tile and query tile:  S = Q K^T (M=128, N=128, fp32 in TMEM)  ->  the softmax warpgroup pulls the
+//   whole score row into registers with ONE pass of tcgen05.ld and immediately hands the S columns back (s_free), so
+//   S_{j+1} is computed while the exponentials of tile j run — the S -> softmax -> P -> PV hand-off that capped the
+//   one-tile kernel at 62 % MUFU occupancy (profiles/r01_ncu_attn_lazy.md) is off the critical path; row max first, then
+//   exponentials against a lazily updated reference max (O is rescaled in TMEM only when a row max moves by more than
+//   2^8), P written back to tensor memory as fp16 pairs and O += P V issued as a TS-mode MMA.  The two warpgroups share each
+//   scheduler's MUFU pipe (one ex2 per score, 16 / clk / SM — the bound of this kernel at head dim 40), so one tile's
+//   exponentials fill the other's TMEM-load / row-max / barrier gaps.  Registers are re-balanced with setmaxnreg (softmax
+//   224, rest 48).  Self-attention 64x64, d = 40, batch 60: 2528 us against 2991 us for the one-tile kernel (1.41x the
+//   exponential floor; profiles/r02_attn_ab_matrix.txt).
 //
 // attn_fwd_kernel  (everything else: single-KV-tile cross attention with a query-tile loop, head dims 80 / 160)
 //   One CTA = one 128-query tile of one (b, h) (several tiles in turn when all keys fit one KV tile):
@@ -56,64 +58,45 @@ __device__ __forceinline__ float ex2f(float x) {
 // =============================================================================================
 // attn_pp_kernel
 // =============================================================================================
-// NS = softmax warpgroups per query tile.  NS = 1: thread = query row (128 score columns per thread and KV tile).
-// NS = 2: two threads per query row, 64 columns each (half maxima exchanged through shared memory, row sums merged in the
-// epilogue).  A single warp issues MUFU.EX2 only every ~11.4 cycles (8 is the pipe rate, tools/softmax_loop_bench.cu):
-// with one softmax warp per scheduler bursting at a time the XU pipe idles 30 % of the time; with NS = 2 every scheduler
-// holds four softmax warps, two of which burst together.
-template <int DVP, int NS>
+// Variants of this kernel that were built, measured on a B200 and removed again (evidence: profiles/r02_attn_*.txt,
+// DESIGN.md §4): two softmax threads per query row (four warps per scheduler: 2941 vs 2633 us at batch 60), a token that
+// makes the MUFU bursts of the two query tiles alternate (2558 vs 2528 us), a double-buffered-score version with BKV = 96
+// and P written in place (3411 us), exponentials partly on the FMA pipe on top of it (3449 / 3720 us).
+template <int DVP>
 struct PPCfg {
   static constexpr int ST = 4;                       // K / V^T ring depth
-  static constexpr int THREADS = 128 + 256 * NS;     // warpgroup 0: warp 0 TMA, warp 1 MMA(A), warp 2 MMA(B), warp 3 idle;
-                                                     // then NS softmax warpgroups of query tile A, NS of query tile B
+  static constexpr int THREADS = 384;                // warpgroup 0: warp 0 TMA, warp 1 MMA(A), warp 2 MMA(B), warp 3 idle;
+                                                     // warpgroup 1: softmax of query tile A; warpgroup 2: of query tile B
   static constexpr int Q_BYTES = ATT_BQ * 128;       // one 128 x 64 fp16 tile, SWIZZLE_128B
   static constexpr int K_STAGE = 128 * 128;          // BKV = 128 keys x 64 (zero-filled head dim) fp16
   static constexpr int V_STAGE = 2 * DVP * 128;      // V^T: two 64-key boxes of DVP rows
-  static constexpr int XCH_BYTES = NS == 2 ? (2 * 2 * 2 * 128 + 2 * 2 * 128) * 4 : 0;  // half maxima [X][parity][half][row], sums [X][half][row]
-  static constexpr int SMEM = 2 * Q_BYTES + ST * (K_STAGE + V_STAGE) + XCH_BYTES + 1024 + 512;
+  static constexpr int SMEM = 2 * Q_BYTES + ST * (K_STAGE + V_STAGE) + 1024 + 512;
   // tensor memory (512 columns, one CTA per SM): S_A S_B | P_A P_B | O_A O_B
   static constexpr int S_COL = 0, P_COL = 256, O_COL = 384;
-  static constexpr int REGS_SOFTMAX = NS == 2 ? 112 : 224, REGS_OTHER = NS == 2 ? 32 : 48;
+  static constexpr int REGS_SOFTMAX = 224, REGS_OTHER = 48;
   static_assert(DVP <= 64 && DVP % 16 == 0, "head dim <= 64");
-  static_assert(128 * REGS_OTHER + 256 * NS * REGS_SOFTMAX <= 65536 - 1024, "register file (an exact fit hung setmaxnreg.inc on hardware: keep slack)");
+  static_assert(128 * REGS_OTHER + 256 * REGS_SOFTMAX <= 65536 - 1024, "register file (an exact fit hung setmaxnreg.inc on hardware: keep slack)");
 };
-
-// named barriers 1 / 2 carry the MUFU token between the softmax warpgroups of query tile A and those of B, 3 / 4 pair the
-// two column halves of a query tile (NS = 2); barrier 0 is __syncthreads
-template <int ID>
-__device__ __forceinline__ void named_bar_sync(uint32_t threads) {
-  asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(threads) : "memory");
-}
-template <int ID>
-__device__ __forceinline__ void named_bar_arrive(uint32_t threads) {
-  asm volatile("bar.arrive %0, %1;" ::"n"(ID), "r"(threads) : "memory");
-}
-// volatile: stays behind the token barrier (a plain asm could be scheduled across it)
-__device__ __forceinline__ uint32_t ex2_ordered(uint32_t x) {
-  uint32_t y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
-}
 
 template <int REGS>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
-template <int DVP, int NS, int TOKEN, int TRACE>
-__global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(const __grid_constant__ AttnKParams p) {
-  using Cfg = PPCfg<DVP, NS>;
+// TRACE: compile the clock64 stamps in (tools/attn_trace.py); the shipped instantiation carries no trace code — with the
+// stamps merely predicated off the kernel was 8 % slower
+template <int DVP, int TRACE>
+__global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const __grid_constant__ AttnKParams p) {
+  using Cfg = PPCfg<DVP>;
   constexpr int ST = Cfg::ST, BKV = 128;
-  constexpr int COLS = BKV / NS, NCH = COLS / 32;   // score columns / 32-column chunks per softmax thread
-  constexpr uint32_t GROUP = 128 * NS;              // softmax threads per query tile
+  constexpr int NCH = BKV / 32;                     // 32-column chunks of a score row
+  constexpr uint32_t GROUP = 128;                   // softmax threads per query tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;                          // [2][Q_BYTES]
   uint8_t* k_smem = q_smem + 2 * Cfg::Q_BYTES;     // [ST][K_STAGE]
   uint8_t* v_smem = k_smem + ST * Cfg::K_STAGE;    // [ST][V_STAGE]
-  float* xch_max = reinterpret_cast<float*>(v_smem + ST * Cfg::V_STAGE);  // NS = 2: [X][parity][half][128]
-  float* xch_sum = xch_max + (NS == 2 ? 2 * 2 * 2 * 128 : 0);             //         [X][half][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xch_max) + Cfg::XCH_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + ST * Cfg::V_STAGE);
   uint64_t* q_full = bars;            // [2] TMA -> MMA(X)
   uint64_t* q_empty = q_full + 2;     // [2] MMA(X) commit -> TMA: every S of this work item has completed
   uint64_t* kv_full = q_empty + 2;    // [ST] TMA -> both MMA warps
@@ -160,7 +143,7 @@ __global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(con
     reg_dealloc<Cfg::REGS_OTHER>();
     if (warp == 0) {
       // ============================ TMA producer ============================================
-      if (lane == 0) {
+      if (elect_one_sync()) {  // one lane, and ptxas knows it: no per-instruction uniformity loops around tcgen05.mma
         int kvc = 0, wi = 0;
         for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++wi) {
           const int qp = w % p.qpairs, head = (w / p.qpairs) % p.heads, b = w / (p.qpairs * p.heads);
@@ -181,7 +164,7 @@ __global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(con
       }
     } else if (warp <= 2) {
       // ============================ MMA issuer of query tile X ===============================
-      if (lane == 0) {
+      if (elect_one_sync()) {  // one lane, and ptxas knows it: no per-instruction uniformity loops around tcgen05.mma
         const int X = warp - 1;
         constexpr uint32_t idesc_s = make_idesc_f16(ATT_BQ, BKV);
         constexpr uint32_t idesc_o = make_idesc_f16(ATT_BQ, DVP);
@@ -236,24 +219,22 @@ __global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(con
   } else {
     // ============================ softmax / correction / epilogue of query tile X ==============
     reg_alloc<Cfg::REGS_SOFTMAX>();
-    const int g = (warp >> 2) - 1;
-    const int X = g / NS;            // query tile
-    const int hlf = g % NS;          // column half of the score tile (NS = 2)
+    const int X = (warp >> 2) - 1;   // query tile
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t t_s = tmem + lane_base + Cfg::S_COL + X * 128 + hlf * COLS;
-    const uint32_t t_p = tmem + lane_base + Cfg::P_COL + X * 64 + hlf * (COLS / 2);
+    const uint32_t t_s = tmem + lane_base + Cfg::S_COL + X * 128;
+    const uint32_t t_p = tmem + lane_base + Cfg::P_COL + X * 64;
     const uint32_t t_o = tmem + lane_base + Cfg::O_COL + X * 64;
     const float sl2 = p.scale_log2e;
-    const bool trace = TRACE && p.dbg != nullptr && blockIdx.x == 0 && r == 0 && hlf == 0;
+    const bool trace = TRACE && p.dbg != nullptr && blockIdx.x == 0 && r == 0;
     constexpr float LAZY_LOG2 = 8.f;
     int gt = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const int qp = w % p.qpairs, head = (w / p.qpairs) % p.heads, b = w / (p.qpairs * p.heads);
       float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < ntiles; ++j, ++gt) {
-        long long ts0 = 0, ts1 = 0, ts2 = 0, ts3 = 0, ts4 = 0, ts5 = 0;
+        long long ts0 = 0, ts1 = 0, ts2 = 0, ts3 = 0;
         if (trace) ts0 = clock64();
         mbar_wait(&s_full[X], gt & 1);
         tc_fence_after();
@@ -266,10 +247,10 @@ __global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(con
         tc_fence_before();
         mbar_arrive(&s_free[X]);
         if (trace) ts2 = clock64();
-        const int kv0 = j * BKV + hlf * COLS;
-        if (kv0 + COLS > p.Nk) {  // ragged last tile: keys >= Nk do not exist
+        const int kv0 = j * BKV;
+        if (kv0 + BKV > p.Nk) {  // ragged last tile: keys >= Nk do not exist
 #pragma unroll
-          for (int i = 0; i < COLS; ++i)
+          for (int i = 0; i < BKV; ++i)
             if (kv0 + i >= p.Nk) v[i >> 5][i & 31] = 0xff800000u;  // -inf
         }
         // ---- row max, lazy reference update ------------------------------------------------------
@@ -290,13 +271,6 @@ __global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(con
 #pragma unroll
           for (int c = 1; c < NCH; ++c) m_t = fmaxf(m_t, mx[c]);
         }
-        if (NS == 2) {  // the other half of the row lives in the partner warpgroup
-          float* slot = xch_max + ((X * 2 + (gt & 1)) * 2) * 128;
-          slot[hlf * 128 + r] = m_t;
-          if (X == 0) named_bar_sync<3>(GROUP);
-          else named_bar_sync<4>(GROUP);
-          m_t = fmaxf(m_t, slot[(hlf ^ 1) * 128 + r]);  // both threads of a row now hold the same maximum
-        }
         bool pv_waited = (j == 0);  // tile 0: the epilogue of the previous work item has waited for its last PV
         if (j == 0) {
           m_ref = m_t;
@@ -311,7 +285,6 @@ __global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(con
           pv_waited = true;
 #pragma unroll
           for (int c = 0; c < DVP / 16; ++c) {
-            if (NS == 2 && (c & 1) != hlf) continue;  // the two threads of a row split the accumulator columns
             uint32_t o[16];
             tmem_ld_32x16(t_o + c * 16, o);
             tmem_ld_wait();
@@ -323,81 +296,25 @@ __global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(con
         }
         if (trace) ts3 = clock64();
         // ---- exponentials against the reference max, P -> tensor memory chunk by chunk -------------
-        // The softmax warps share each scheduler's MUFU pipe.  Left alone the two query tiles fall into lock step (both
-        // exponentiate at half rate, then both do their FMA / pack / TMEM / barrier work with the pipe idle: measured
-        // 3086 cycles per A+B tile pair against 2048 of MUFU work, profiles/r02_attn_pp_trace.txt).  A token passed
-        // through two named barriers makes the MUFU bursts of tile A and tile B alternate instead, so one tile's burst
-        // covers the other's non-MUFU phase.
         const float mb = m_ref * sl2;
         const uint64_t sl2_2 = pk2(sl2, sl2), nmb_2 = pk2(-mb, -mb);
         uint64_t sm2[4] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
-        if (TOKEN) {
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float t0, t1;
-            upk2(fma2(pk2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sl2_2, nmb_2), t0, t1);
-            v[c][i] = __float_as_uint(t0);
-            v[c][i + 1] = __float_as_uint(t1);
-          }
-        }
-        if (X == 0) {
-          if (gt > 0) named_bar_sync<2>(2 * GROUP);
-        } else {
-          named_bar_sync<1>(2 * GROUP);
-        }
-        if (trace) ts4 = clock64();
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[c][i] = ex2_ordered(v[c][i]);
-        }
-        {
-          // ptxas is free to hoist a bar.arrive above independent MUFU instructions (it did): tie the token release to the
-          // tail of the burst through a data dependency — the sign bits of a few late results, zero at run time
-          uint32_t dep = v[NCH - 1][31] | v[NCH - 1][30] | v[NCH - 1][15] | v[0][31];
-          if (NCH > 2) dep |= v[NCH - 2][31] | v[1][31];
-          dep >>= 31;
-          if (X == 0) named_bar_arrive<1>(2 * GROUP + dep);
-          else named_bar_arrive<2>(2 * GROUP + dep);
-          if (trace) ts5 = clock64() + dep;
+        if (!pv_waited) {
+          mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has read P_{j-1}: the P columns may be overwritten
+          tc_fence_after();
         }
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           uint32_t pkc[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float e0 = __uint_as_float(v[c][i]), e1 = __uint_as_float(v[c][i + 1]);
+            float t0, t1;
+            upk2(fma2(pk2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sl2_2, nmb_2), t0, t1);
+            const float e0 = ex2f(t0), e1 = ex2f(t1);
             sm2[(i >> 1) & 3] = add2(sm2[(i >> 1) & 3], pk2(e0, e1));
             pkc[i >> 1] = pack_h2(e0, e1);
           }
-          if (c == 0 && !pv_waited) {
-            mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has read P_{j-1}: the P columns may be overwritten
-            tc_fence_after();
-          }
           tmem_st_32x16(t_p + c * 16, pkc);  // row = lane, column k = keys (2k, 2k+1) as an fp16 pair (TS-mode A layout)
-        }
-        } else {
-          // free-running variant: no token, the scale / exponential / sum / pack work of a chunk is left to the instruction
-          // scheduler to interleave, P chunks leave as they are produced
-          if (!pv_waited) {
-            mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has read P_{j-1}: the P columns may be overwritten
-            tc_fence_after();
-          }
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            uint32_t pkc[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float t0, t1;
-              upk2(fma2(pk2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sl2_2, nmb_2), t0, t1);
-              const float e0 = ex2f(t0), e1 = ex2f(t1);
-              sm2[(i >> 1) & 3] = add2(sm2[(i >> 1) & 3], pk2(e0, e1));
-              pkc[i >> 1] = pack_h2(e0, e1);
-            }
-            tmem_st_32x16(t_p + c * 16, pkc);
-          }
         }
         {
           float s0, s1, s2, s3, s4, s5, s6, s7;
@@ -412,16 +329,10 @@ __global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(con
         mbar_arrive(&p_ready[X]);
         if (trace) {
           long long* o = p.dbg + (static_cast<long long>(X) * 4096 + (gt & 4095)) * 8;
-          o[0] = ts0; o[1] = ts1; o[2] = ts2; o[3] = ts3; o[4] = ts4; o[5] = ts5; o[6] = clock64();
+          o[0] = ts0; o[1] = ts1; o[2] = ts2; o[3] = ts3; o[4] = ts3; o[5] = ts3; o[6] = clock64();
         }
       }
       // ---- epilogue: O / l -> fp16 ------------------------------------------------------------
-      if (NS == 2) {  // the row sum is the sum of the two halves
-        xch_sum[(X * 2 + hlf) * 128 + r] = l_run;
-        if (X == 0) named_bar_sync<3>(GROUP);
-        else named_bar_sync<4>(GROUP);
-        l_run += xch_sum[(X * 2 + (hlf ^ 1)) * 128 + r];
-      }
       mbar_wait(&pv_done[X], (gt - 1) & 1);
       tc_fence_after();
       const float inv_l = 1.f / l_run;
@@ -430,7 +341,6 @@ __global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(con
       const bool vec_ok = ((p.out_ld & 7) == 0) && ((p.d & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
 #pragma unroll
       for (int c = 0; c < DVP / 16; ++c) {
-        if (NS == 2 && (c & 1) != hlf) continue;  // the two threads of a row split the output columns
         uint32_t o[16];
         tmem_ld_32x16(t_o + c * 16, o);
         tmem_ld_wait();
@@ -459,377 +369,6 @@ __global__ void __launch_bounds__(PPCfg<DVP, NS>::THREADS, 1) attn_pp_kernel(con
       }
       // the next work item's first PV overwrites O (accumulate = 0) only after this tile's next p_ready, which every
       // softmax thread of the tile signals after this read-out: no separate "O free" barrier is needed
-    }
-    if (TOKEN && X == 0 && gt > 0) named_bar_sync<2>(2 * GROUP);  // consume B's last token so no named barrier is left half-arrived
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
-
-// 2^t for two values on the FMA / ALU pipes (what FlashAttention-4 does for part of its exponentials): floor by a
-// round-down magic add, degree-3 minimax polynomial on the fraction (max rel. error 7.5e-5, below the fp16 rounding of P),
-// exponent spliced in with one integer multiply-add per value
-__device__ __forceinline__ void ex2_poly2(float t0, float t1, float& e0, float& e1) {
-  t0 = fmaxf(t0, -126.f);
-  t1 = fmaxf(t1, -126.f);
-  const uint64_t magic = pk2(12582912.f, 12582912.f);
-  const uint64_t t = pk2(t0, t1);
-  uint64_t xr, f;
-  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(xr) : "l"(t), "l"(magic));
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(xr), "l"(magic));
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(t), "l"(f));
-  uint64_t q = fma2(f, pk2(0.0780244991f, 0.0780244991f), pk2(0.2260671854f, 0.2260671854f));
-  q = fma2(q, f, pk2(0.6958335042f, 0.6958335042f));
-  q = fma2(q, f, pk2(0.9999251962f, 0.9999251962f));
-  float q0, q1, r0, r1;
-  upk2(q, q0, q1);
-  upk2(xr, r0, r1);
-  e0 = __int_as_float(__float_as_int(r0) * 8388608 + __float_as_int(q0));
-  e1 = __int_as_float(__float_as_int(r1) * 8388608 + __float_as_int(q1));
-}
-
-// =============================================================================================
-// attn_db_kernel — the two-query-tile persistent kernel with DOUBLE-BUFFERED scores (BKV = 96, P written in place)
-// =============================================================================================
-// What bounds attn_pp_kernel (profiles/r02_attn_pp_matrix.txt): a warp that issues nothing but MUFU.EX2 gets one every
-// ~11.4 cycles, two warps of a scheduler together one every 9 (8 is the pipe rate, tools/softmax_loop_bench.cu) — and the
-// TMEM-load / row-max / pack / P-store phases of a softmax warp issue no MUFU at all.  With one score buffer per query tile
-// those phases are serial per KV tile (the exponentials need the row max, the row max needs the whole score row), so the
-// XU pipe sees ~1.4 warps' worth of MUFU demand: 3040 cycles per A+B tile pair against 2048 of MUFU work.
-// Here every query tile owns TWO score buffers of 96 columns (2 x 2 x 96 + 2 x 64 = 512 TMEM columns): while a warp
-// exponentiates S_j chunk by chunk it also takes the row max of S_{j+1}, so the max is known before tile j+1 starts and
-// the whole KV loop is ONE homogeneous stream (load, max, scale, ex2, sum, pack, store) the scheduler can interleave — the
-// structure the microbenchmark reaches 8.8 cycles per MUFU with.  P_j (fp16 pairs) overwrites the first 48 columns of
-// S_j's own buffer; O += P_j V_j reads it as a TS-mode MMA, and S_{j+2} is issued into the buffer right behind that MMA,
-// so buffer reuse is ordered by the MMA warp's own program order (no "S free" barrier at all).
-template <int DVP>
-struct DBCfg {
-  static constexpr int BKV = 96;
-  static constexpr int ST = 5;                       // K / V^T ring depth (S runs two tiles ahead of PV)
-  static constexpr int THREADS = 384;                // as attn_pp_kernel<.., 1, ..>
-  static constexpr int Q_BYTES = ATT_BQ * 128;
-  static constexpr int K_STAGE = BKV * 128;          // 96 keys x 64 (zero-filled head dim) fp16
-  static constexpr int V_STAGE = 2 * DVP * 128;      // V^T: two 64-key boxes (the MMA uses the first 96 keys)
-  static constexpr int SMEM = 2 * Q_BYTES + ST * (K_STAGE + V_STAGE) + 1024 + 512;
-  static constexpr int S_COL = 0, O_COL = 384;       // S buffers: X * 192 + buf * 96;  O: 384 + X * 64
-  static_assert(DVP <= 64 && DVP % 16 == 0, "head dim <= 64");
-};
-
-// POLY: every POLY-th pair of exponentials runs on the FMA pipe (ex2_poly2) instead of the MUFU pipe (0 = none)
-// TRACE: compile the clock64 stamps in (tools/attn_trace.py); the shipped instantiations carry no trace code
-template <int DVP, int POLY, int TRACE>
-__global__ void __launch_bounds__(DBCfg<DVP>::THREADS, 1) attn_db_kernel(const __grid_constant__ AttnKParams p) {
-  using Cfg = DBCfg<DVP>;
-  constexpr int ST = Cfg::ST, BKV = Cfg::BKV, NCH = BKV / 32;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* q_smem = smem;                          // [2][Q_BYTES]
-  uint8_t* k_smem = q_smem + 2 * Cfg::Q_BYTES;     // [ST][K_STAGE]
-  uint8_t* v_smem = k_smem + ST * Cfg::K_STAGE;    // [ST][V_STAGE]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + ST * Cfg::V_STAGE);
-  uint64_t* q_full = bars;            // [2] TMA -> MMA(X)
-  uint64_t* q_empty = q_full + 2;     // [2] MMA(X) commit -> TMA: every S of this work item has completed
-  uint64_t* kv_full = q_empty + 2;    // [ST] TMA -> both MMA warps
-  uint64_t* kv_empty = kv_full + ST;  // [ST] PV_A(j) and PV_B(j) commits (count 2) -> TMA
-  uint64_t* s_full = kv_empty + ST;   // [2][2] MMA(X) commit -> softmax(X), one per score buffer
-  uint64_t* p_ready = s_full + 4;     // [2] softmax(X) (128) -> MMA(X): P_j is in tensor memory
-  uint64_t* pv_done = p_ready + 2;    // [2] MMA(X) commit -> softmax(X): O is stable (rescale / epilogue only)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntiles = (p.Nk + BKV - 1) / BKV;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.mapQ);
-    tma_prefetch_desc(&p.mapK);
-    tma_prefetch_desc(&p.mapV);
-    for (int x = 0; x < 2; ++x) {
-      mbar_init(&q_full[x], 1);
-      mbar_init(&q_empty[x], 1);
-      mbar_init(&s_full[2 * x], 1);
-      mbar_init(&s_full[2 * x + 1], 1);
-      mbar_init(&p_ready[x], 128);
-      mbar_init(&pv_done[x], 1);
-    }
-    for (int s = 0; s < ST; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 2);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr_smem;
-  pdl_wait();
-  pdl_launch_dependents();
-
-  if (warp < 4) {
-    reg_dealloc<48>();
-    if (warp == 0) {
-      // ============================ TMA producer ============================================
-      if (lane == 0) {
-        int kvc = 0, wi = 0;
-        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++wi) {
-          const int qp = w % p.qpairs, head = (w / p.qpairs) % p.heads, b = w / (p.qpairs * p.heads);
-          for (int x = 0; x < 2; ++x) {
-            if (wi > 0) mbar_wait(&q_empty[x], (wi - 1) & 1);
-            mbar_expect_tx(&q_full[x], Cfg::Q_BYTES);
-            tma_load_4d(&p.mapQ, &q_full[x], q_smem + x * Cfg::Q_BYTES, 0, qp * 2 * ATT_BQ + x * ATT_BQ, head, b);
-          }
-          for (int j = 0; j < ntiles; ++j, ++kvc) {
-            const int s = kvc % ST;
-            mbar_wait(&kv_empty[s], ((kvc / ST) & 1) ^ 1);
-            mbar_expect_tx(&kv_full[s], Cfg::K_STAGE + Cfg::V_STAGE);
-            tma_load_4d(&p.mapK, &kv_full[s], k_smem + s * Cfg::K_STAGE, 0, j * BKV, head, b);
-            tma_load_4d(&p.mapV, &kv_full[s], v_smem + s * Cfg::V_STAGE, j * BKV, 0, head, b);
-            tma_load_4d(&p.mapV, &kv_full[s], v_smem + s * Cfg::V_STAGE + DVP * 128, j * BKV + 64, 0, head, b);
-          }
-        }
-      }
-    } else if (warp <= 2) {
-      // ============================ MMA issuer of query tile X ===============================
-      if (lane == 0) {
-        const int X = warp - 1;
-        constexpr uint32_t idesc_s = make_idesc_f16(ATT_BQ, BKV);
-        constexpr uint32_t idesc_o = make_idesc_f16(ATT_BQ, DVP);
-        const uint32_t q_addr = smem_u32(q_smem + X * Cfg::Q_BYTES);
-        const uint32_t t_sx = tmem + Cfg::S_COL + X * 192;
-        const uint32_t t_o = tmem + Cfg::O_COL + X * 64;
-        int kvc = 0, gt = 0, wi = 0;  // KV ring position, score tiles of THIS pipeline so far, work items
-        // S of local tile j (global tile g): buffer g & 1.  Its previous content (P of tile g - 2) was consumed by PV(g - 2),
-        // issued earlier by this same thread: tcgen05 operations of one thread execute in order, so no barrier is needed.
-        auto wait_kv = [&](int j) {
-          mbar_wait(&kv_full[(kvc + j) % ST], ((kvc + j) / ST) & 1);
-          tc_fence_after();
-        };
-        auto issue_s = [&](int j) {  // K_j has been waited for (wait_kv)
-          const int g = gt + j, s = (kvc + j) % ST;
-          const uint32_t k_addr = smem_u32(k_smem + s * Cfg::K_STAGE);
-          const uint32_t ts = t_sx + (g & 1) * BKV;
-          for (int ks = 0; ks < p.dk_steps; ++ks)
-            umma_f16_ss(ts, make_desc_k_sw128(q_addr + ks * 32), make_desc_k_sw128(k_addr + ks * 32), idesc_s,
-                        ks != 0 ? 1u : 0u);
-          umma_commit(&s_full[2 * X + (g & 1)]);
-          if (j == ntiles - 1) umma_commit(&q_empty[X]);  // every S of this work item is issued: Q may be refilled when done
-        };
-        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++wi) {
-          mbar_wait(&q_full[X], wi & 1);
-          tc_fence_after();
-          wait_kv(0);
-          issue_s(0);
-          if (ntiles > 1) {
-            wait_kv(1);
-            issue_s(1);
-          }
-          for (int j = 0; j < ntiles; ++j) {
-            const int g = gt + j;
-            if (j + 2 < ntiles) wait_kv(j + 2);  // off the critical path: the softmax of tile j is still running
-            mbar_wait(&p_ready[X], g & 1);
-            tc_fence_after();
-            const int s = (kvc + j) % ST;
-            const uint32_t v_addr = smem_u32(v_smem + s * Cfg::V_STAGE);
-            const uint32_t t_p = t_sx + (g & 1) * BKV;  // P_j sits in the first 48 columns of S_j's buffer
-#pragma unroll
-            for (int ks = 0; ks < BKV / 16; ++ks) {
-              const uint64_t db = make_desc_k_sw128(v_addr + (ks >> 2) * (DVP * 128) + (ks & 3) * 32);
-              umma_f16_ts(t_o, t_p + ks * 8, db, idesc_o, (j | ks) != 0 ? 1u : 0u);
-            }
-            umma_commit(&pv_done[X]);
-            umma_commit(&kv_empty[s]);
-            if (j + 2 < ntiles) issue_s(j + 2);
-          }
-          kvc += ntiles;
-          gt += ntiles;
-        }
-      }
-    }
-  } else {
-    // ============================ softmax / correction / epilogue of query tile X ==============
-    reg_alloc<224>();
-    const int X = (warp >> 2) - 1;
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t t_sx = tmem + lane_base + Cfg::S_COL + X * 192;
-    const uint32_t t_o = tmem + lane_base + Cfg::O_COL + X * 64;
-    const float sl2 = p.scale_log2e;
-    const uint64_t sl2_2 = pk2(sl2, sl2);
-    const bool trace = TRACE && p.dbg != nullptr && blockIdx.x == 0 && r == 0;
-    constexpr float LAZY_LOG2 = 8.f;
-    int gt = 0;
-    // row max of 32 score columns (keys kv0 .. kv0 + 31; keys >= Nk do not exist)
-    auto chunk_max = [&](const uint32_t (&y)[32], int kv0) {
-      float a0 = -INFINITY, a1 = -INFINITY;
-      if (kv0 + 32 <= p.Nk) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          a0 = fmaxf(a0, __uint_as_float(y[i]));
-          a1 = fmaxf(a1, __uint_as_float(y[i + 1]));
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kv0 + i < p.Nk) a0 = fmaxf(a0, __uint_as_float(y[i]));
-      }
-      return fmaxf(a0, a1);
-    };
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-      const int qp = w % p.qpairs, head = (w / p.qpairs) % p.heads, b = w / (p.qpairs * p.heads);
-      float m_ref = -INFINITY, l_run = 0.f, m_next = -INFINITY;
-      {
-        // first tile of the work item: its row max has no previous tile to hide behind
-        mbar_wait(&s_full[2 * X + (gt & 1)], (gt >> 1) & 1);
-        tc_fence_after();
-        const uint32_t ts = t_sx + (gt & 1) * BKV;
-        uint32_t y[NCH][32];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) tmem_ld_32x32(ts + c * 32, y[c]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) m_next = fmaxf(m_next, chunk_max(y[c], c * 32));
-      }
-      for (int j = 0; j < ntiles; ++j, ++gt) {
-        long long ts0 = 0, ts1 = 0;
-        if (trace) ts0 = clock64();
-        const uint32_t ts = t_sx + (gt & 1) * BKV;         // S_j (already waited for: its max is m_next)
-        const uint32_t tn = t_sx + ((gt + 1) & 1) * BKV;   // S_{j+1}
-        const bool has_next = j + 1 < ntiles;
-        const int kv0 = j * BKV;
-        const bool ragged = kv0 + BKV > p.Nk;
-        // ---- lazy reference update with the max taken during the previous tile ---------------------
-        const float m_t = m_next;
-        if (j == 0) {
-          m_ref = m_t;
-        } else if (__any_sync(0xffffffffu, (m_t - m_ref) * sl2 > LAZY_LOG2)) {
-          const float m_new = fmaxf(m_ref, m_t);
-          const float alpha = ex2f((m_ref - m_new) * sl2);
-          m_ref = m_new;
-          l_run *= alpha;
-          mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has completed: O is stable
-          tc_fence_after();
-#pragma unroll
-          for (int c = 0; c < DVP / 16; ++c) {
-            uint32_t o[16];
-            tmem_ld_32x16(t_o + c * 16, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x16(t_o + c * 16, o);
-          }
-          tmem_st_wait();
-        }
-        const float mb = m_ref * sl2;
-        const uint64_t nmb_2 = pk2(-mb, -mb);
-        uint64_t sm2[4] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
-        m_next = -INFINITY;
-        // ---- one stream: exponentials of S_j chunk by chunk; the row max of S_{j+1} rides on the last chunk -------------
-        // (S_{j+1} is issued behind PV_{j-1}, i.e. at the start of this tile: it lands ~600 cycles in, measured)
-        uint32_t xa[32], xb[32], y[NCH][32];
-        tmem_ld_32x32(ts, xa);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          uint32_t(&cur)[32] = (c & 1) ? xb : xa;
-          uint32_t(&nxt)[32] = (c & 1) ? xa : xb;
-          if (c + 1 < NCH) tmem_ld_32x32(ts + (c + 1) * 32, nxt);
-          if (has_next && c == NCH - 1) {
-            mbar_wait(&s_full[2 * X + ((gt + 1) & 1)], ((gt + 1) >> 1) & 1);
-            tc_fence_after();
-            if (trace) ts1 = clock64();
-#pragma unroll
-            for (int cc = 0; cc < NCH; ++cc) tmem_ld_32x32(tn + cc * 32, y[cc]);
-          }
-          uint32_t pkc[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            if (has_next && c == NCH - 1 && i == 16) tmem_ld_wait();  // S_{j+1} is in registers: its max interleaves with the rest
-            float t0, t1;
-            upk2(fma2(pk2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sl2_2, nmb_2), t0, t1);
-            float e0, e1;
-            if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1) {
-              ex2_poly2(t0, t1, e0, e1);
-            } else {
-              e0 = ex2f(t0);
-              e1 = ex2f(t1);
-            }
-            if (ragged) {
-              if (kv0 + c * 32 + i >= p.Nk) e0 = 0.f;
-              if (kv0 + c * 32 + i + 1 >= p.Nk) e1 = 0.f;
-            }
-            sm2[(i >> 1) & 3] = add2(sm2[(i >> 1) & 3], pk2(e0, e1));
-            pkc[i >> 1] = pack_h2(e0, e1);
-          }
-          if (c + 1 < NCH) tmem_ld_wait();  // chunk c + 1 of S_j has landed
-          // P chunk c -> columns [16 c, 16 c + 16) of S_j's own buffer: those score columns were consumed in chunk c / 2
-          tmem_st_32x16(ts + c * 16, pkc);
-        }
-        if (has_next) {
-#pragma unroll
-          for (int cc = 0; cc < NCH; ++cc) m_next = fmaxf(m_next, chunk_max(y[cc], (j + 1) * BKV + cc * 32));
-        }
-        {
-          float s0, s1, s2, s3, s4, s5, s6, s7;
-          upk2(sm2[0], s0, s1);
-          upk2(sm2[1], s2, s3);
-          upk2(sm2[2], s4, s5);
-          upk2(sm2[3], s6, s7);
-          l_run += ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_ready[X]);
-        if (trace) {
-          long long* o = p.dbg + (static_cast<long long>(X) * 4096 + (gt & 4095)) * 8;
-          o[0] = ts0; o[1] = ts0; o[2] = ts0; o[3] = ts0; o[4] = ts1 ? ts1 : ts0; o[5] = ts1 ? ts1 : ts0; o[6] = clock64();
-        }
-      }
-      // ---- epilogue: O / l -> fp16 ------------------------------------------------------------
-      mbar_wait(&pv_done[X], (gt - 1) & 1);
-      tc_fence_after();
-      const float inv_l = 1.f / l_run;
-      const int row = qp * 2 * ATT_BQ + X * ATT_BQ + r;
-      __half* orow = p.out + (static_cast<int64_t>(b) * p.Nq + row) * p.out_ld + head * p.d;
-      const bool vec_ok = ((p.out_ld & 7) == 0) && ((p.d & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
-#pragma unroll
-      for (int c = 0; c < DVP / 16; ++c) {
-        uint32_t o[16];
-        tmem_ld_32x16(t_o + c * 16, o);
-        tmem_ld_wait();
-        if (row < p.Nq) {
-#pragma unroll
-          for (int h8 = 0; h8 < 2; ++h8) {
-            const int dd = c * 16 + h8 * 8;
-            if (dd >= p.d) break;
-            float f[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[h8 * 8 + i]) * inv_l;
-            if (vec_ok && dd + 8 <= p.d) {
-              uint4 u;
-              u.x = pack_h2(f[0], f[1]);
-              u.y = pack_h2(f[2], f[3]);
-              u.z = pack_h2(f[4], f[5]);
-              u.w = pack_h2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(orow + dd) = u;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (dd + i < p.d) orow[dd + i] = __float2half_rn(f[i]);
-            }
-          }
-        }
-      }
-      // the next work item's first PV (accumulate = 0) is issued only after this tile's next p_ready, which every softmax
-      // thread signals after this read-out; its first S may already sit in the other score buffer
     }
   }
 
@@ -921,7 +460,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
 
   if (warp == 0) {
     // ============================ TMA producer ============================================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int t = 0; t < nqt; ++t) {
         const int q0 = (qt_first + t) * ATT_BQ;
         if (t > 0) mbar_wait(q_empty, (t - 1) & 1);
@@ -945,7 +484,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ================================================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc_s = make_idesc_f16(ATT_BQ, BKV);
       constexpr uint32_t idesc_o = make_idesc_f16(ATT_BQ, DVP);
       const uint32_t q_addr = smem_u32(q_smem);
@@ -1222,8 +761,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<DKA, DVP, BKV, ST, SB, PT
 // variants: 0..3 attn_fwd_kernel, head dim <= 16 / 32 / 48 / 64 (BKV 128, P in TMEM, two CTAs per SM)
 //           4    attn_fwd_kernel, head dim <= 80  (BKV 64, P in TMEM)
 //           5    attn_fwd_kernel, head dim <= 160 (BKV 64, double-buffered S, P in shared memory)
-//           8..11 attn_pp_kernel, head dim <= 16 / 32 / 48 / 64, more than one KV tile (single score buffer per query tile)
-//           12..15 attn_db_kernel, same head dims, double-buffered scores (BKV = 96): the default for long key sequences
+//           8..11 attn_pp_kernel, head dim <= 16 / 32 / 48 / 64, more than one KV tile
 struct AttnLaunchImpl {
   AttnKParams p;
   dim3 grid;
@@ -1238,14 +776,8 @@ static int attn_set_attr() {
 }
 template <int DVP>
 static int attn_pp_set_attr() {
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 1>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 1>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 1>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP, 1>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_db_kernel<DVP, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBCfg<DVP>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_db_kernel<DVP, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBCfg<DVP>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_db_kernel<DVP, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBCfg<DVP>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_db_kernel<DVP, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DBCfg<DVP>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
   return 0;
 }
 
@@ -1274,10 +806,8 @@ void attention_set_trace(long long* buf) { g_attn_dbg = buf; }
 static int variant_for(int d, int Nk) {
   // SDW_ATTN_PP=0: the one-query-tile kernel everywhere (A/B measurements)
   static const bool pp = [] { const char* e = std::getenv("SDW_ATTN_PP"); return !(e && e[0] == '0'); }();
-  // SDW_ATTN_DB=0: single score buffer per query tile (attn_pp_kernel) instead of the double-buffered kernel
-  static const bool db = [] { const char* e = std::getenv("SDW_ATTN_DB"); return !(e && e[0] == '0'); }();
   const int cls = d <= 16 ? 0 : (d <= 32 ? 1 : (d <= 48 ? 2 : 3));
-  if (d <= 64) return (pp && Nk > 128) ? (db && Nk > 192 ? 12 : 8) + cls : cls;
+  if (d <= 64) return (pp && Nk > 128) ? 8 + cls : cls;
   return d <= 80 ? 4 : 5;
 }
 
@@ -1290,8 +820,8 @@ int plan_attention(const AttnDesc& a, AttnLaunch* L) {
   std::memset(I, 0, sizeof(*I));
   I->variant = variant_for(a.d, a.Nk);
   const bool pp = I->variant >= 8;
-  const int bkv = (I->variant == 4 || I->variant == 5) ? 64 : (I->variant >= 12 ? 96 : 128);
-  const int dvp_tab[16] = {16, 32, 48, 64, 80, 160, 0, 0, 16, 32, 48, 64, 16, 32, 48, 64};
+  const int bkv = (I->variant == 4 || I->variant == 5) ? 64 : 128;
+  const int dvp_tab[12] = {16, 32, 48, 64, 80, 160, 0, 0, 16, 32, 48, 64};
   const int dvp = dvp_tab[I->variant];
   AttnKParams& p = I->p;
   p.Nq = a.Nq; p.Nk = a.Nk; p.d = a.d; p.heads = a.heads;
@@ -1364,21 +894,8 @@ template <int DVP>
 static cudaError_t launch_pp(const AttnLaunchImpl* I, cudaStream_t stream) {
   AttnKParams p = I->p;
   p.dbg = g_attn_dbg;
-  if (I->variant >= 12) {
-    // SDW_ATTN_POLY=4|2: every 4th / 2nd pair of exponentials on the FMA pipe (measurement switch)
-    static const int poly = [] { const char* e = std::getenv("SDW_ATTN_POLY"); return e ? std::atoi(e) : 0; }();
-    if (p.dbg) return launch_pdl(attn_db_kernel<DVP, 0, 1>, I->grid, dim3(DBCfg<DVP>::THREADS), DBCfg<DVP>::SMEM, stream, p);
-    if (poly == 4) return launch_pdl(attn_db_kernel<DVP, 4, 0>, I->grid, dim3(DBCfg<DVP>::THREADS), DBCfg<DVP>::SMEM, stream, p);
-    if (poly == 2) return launch_pdl(attn_db_kernel<DVP, 2, 0>, I->grid, dim3(DBCfg<DVP>::THREADS), DBCfg<DVP>::SMEM, stream, p);
-    return launch_pdl(attn_db_kernel<DVP, 0, 0>, I->grid, dim3(DBCfg<DVP>::THREADS), DBCfg<DVP>::SMEM, stream, p);
-  }
-  // SDW_ATTN_TOKEN=1: the MUFU bursts of the two query tiles alternate through a token (measurement switch)
-  static const bool tok = [] { const char* e = std::getenv("SDW_ATTN_TOKEN"); return e && e[0] == '1'; }();
-  constexpr int TH = PPCfg<DVP, 1>::THREADS, SM = PPCfg<DVP, 1>::SMEM;
-  if (p.dbg) return tok ? launch_pdl(attn_pp_kernel<DVP, 1, 1, 1>, I->grid, dim3(TH), SM, stream, p)
-                        : launch_pdl(attn_pp_kernel<DVP, 1, 0, 1>, I->grid, dim3(TH), SM, stream, p);
-  return tok ? launch_pdl(attn_pp_kernel<DVP, 1, 1, 0>, I->grid, dim3(TH), SM, stream, p)
-             : launch_pdl(attn_pp_kernel<DVP, 1, 0, 0>, I->grid, dim3(TH), SM, stream, p);
+  if (p.dbg) return launch_pdl(attn_pp_kernel<DVP, 1>, I->grid, dim3(PPCfg<DVP>::THREADS), PPCfg<DVP>::SMEM, stream, p);
+  return launch_pdl(attn_pp_kernel<DVP, 0>, I->grid, dim3(PPCfg<DVP>::THREADS), PPCfg<DVP>::SMEM, stream, p);
 }
 
 int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
@@ -1395,10 +912,6 @@ int launch_attention(const AttnLaunch& L, cudaStream_t stream) {
     case 9: SDW_CUDA_OK(launch_pp<32>(I, stream)); break;
     case 10: SDW_CUDA_OK(launch_pp<48>(I, stream)); break;
     case 11: SDW_CUDA_OK(launch_pp<64>(I, stream)); break;
-    case 12: SDW_CUDA_OK(launch_pp<16>(I, stream)); break;
-    case 13: SDW_CUDA_OK(launch_pp<32>(I, stream)); break;
-    case 14: SDW_CUDA_OK(launch_pp<48>(I, stream)); break;
-    case 15: SDW_CUDA_OK(launch_pp<64>(I, stream)); break;
     default: set_error("bad attention variant"); return 1;
   }
   SDW_CUDA_OK(cudaGetLastError());

@@ -7,8 +7,8 @@ post-process) through the C ABI (`sdw_engine_sample`, CUDA graph replay).
 
 Tolerances are CALIBRATED: tests/golden/calibration.json records, per case, the spread between the fp32
 oracle and the same oracle with fp16 storage emulation (what the reference's own fp16 CUDA pipeline stores).  The native
-path (fp16 activations, fp32 accumulate, fp32 latent state) must sit within TOL_X x that spread of the fp32 oracle, with a
-floor for cases whose spread is tiny.
+path (fp16 activations, fp32 accumulate, fp32 latent state) must sit within TOL_X x that spread of the fp32 oracle
+(measured on a B200: 0.4x - 0.9x of the spread in every metric of every case, profiles/r02_parity_full_size.json).
 """
 import json
 import os
@@ -24,8 +24,8 @@ sys.path.insert(0, G)
 
 pytestmark = pytest.mark.gpu
 
-TOL_X = 1.5  # native-vs-oracle error allowed as a multiple of the calibrated fp16-storage spread
-FLOOR = {"latents_rel_l2": 2e-3, "raw_rel_l2": 2e-3, "frames_mean_lsb": 0.25, "frames_p999_lsb": 2.0}
+TOL_X = 1.25  # native-vs-oracle error allowed as a multiple of the calibrated fp16-storage spread (measured: 0.4x - 0.9x)
+FLOOR = {"latents_rel_l2": 0.0, "raw_rel_l2": 0.0, "frames_mean_lsb": 0.0, "frames_p999_lsb": 1.0}  # no slack beyond TOL_X x spread
 
 
 def _run_native(case):

@@ -104,13 +104,13 @@ def _attn(n, B, Nq, Nk, heads, d):
 
 
 def test_attention_variants_for_the_sd14_head_dims(native):
-    # head dims <= 64, long key sequences: the two-query-tile persistent kernel with double-buffered scores (variants 12-15,
-    # one CTA per SM); 129..192 keys: its single-buffer sibling (8-11); 80: the BKV = 64 P-in-TMEM tile; 160: double-buffered S
-    assert _attn(native, 32, 4096, 4096, 8, 40)["variant"] == 14
+    # head dims <= 64 with more than one KV tile: the two-query-tile persistent kernel (variants 8-11, one CTA per SM);
+    # 80: the BKV = 64 P-in-TMEM tile; 160: double-buffered S
+    assert _attn(native, 32, 4096, 4096, 8, 40)["variant"] == 10
     assert _attn(native, 32, 4096, 160, 8, 40)["variant"] == 10
     assert _attn(native, 32, 1024, 1024, 8, 80)["variant"] == 4
     assert _attn(native, 32, 256, 256, 8, 160)["variant"] == 5
-    assert _attn(native, 16, 9216, 9216, 5, 64)["variant"] == 15   # SD-2.1, 96x96 latent
+    assert _attn(native, 16, 9216, 9216, 5, 64)["variant"] == 11   # SD-2.1, 96x96 latent
     assert _attn(native, 32, 4096, 77, 8, 40)["variant"] == 2       # single KV tile: the one-tile kernel with a query loop
     p = _attn(native, 32, 4096, 4096, 8, 40)
     assert (p["qt"], p["gx"], p["gy"], p["gz"]) == (2, 148, 1, 1)   # persistent: 148 CTAs over 32 * 8 * 16 work items

@@ -44,4 +44,4 @@ for X in range(2):
     d = lambda a, b: float((body[:, b] - body[:, a]).mean())  # noqa: E731
     period = float((body[1:, 0] - body[:-1, 0]).mean())
     print(f"query tile {'AB'[X]}: {rows.shape[0]} tiles; mean cycles between the stamps of a KV tile: "
-          + " ".join(f"{d(i, i + 1):.0f}" for i in range(6)) + f"; period {period:.0f} cycles per KV tile of {os.environ.get('BKV', '?')} keys")
+          + "wait S %.0f, TMEM->regs %.0f, row max %.0f, exp + P store %.0f" % (d(0, 1), d(1, 2), d(2, 3), d(3, 6)) + f"; period {period:.0f} cycles per KV tile of {os.environ.get('BKV', '?')} keys")
