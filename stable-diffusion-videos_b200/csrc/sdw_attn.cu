@@ -55,6 +55,29 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// 2^t for two values on the FMA pipe (Cody-Waite: floor by a round-down magic add, degree-3 minimax polynomial on the
+// fraction — relative error 7.5e-5, a sixth of the fp16 rounding P gets anyway — exponent spliced in with one integer
+// multiply-add per value).  Takes a share of the exponentials off the MUFU pipe, which bounds this kernel.
+__device__ __forceinline__ void ex2_poly2(float t0, float t1, float& e0, float& e1) {
+  t0 = fmaxf(t0, -126.f);
+  t1 = fmaxf(t1, -126.f);
+  const uint64_t magic = pk2(12582912.f, 12582912.f);
+  const uint64_t t = pk2(t0, t1);
+  uint64_t xr;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(xr) : "l"(t), "l"(magic));
+  uint64_t fl, f;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(fl) : "l"(xr), "l"(magic));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(t), "l"(fl));
+  uint64_t q = fma2(f, pk2(0.0780244991f, 0.0780244991f), pk2(0.2260671854f, 0.2260671854f));
+  q = fma2(q, f, pk2(0.6958335042f, 0.6958335042f));
+  q = fma2(q, f, pk2(0.9999251962f, 0.9999251962f));
+  float q0, q1, r0, r1;
+  upk2(q, q0, q1);
+  upk2(xr, r0, r1);
+  e0 = __int_as_float(__float_as_int(r0) * 8388608 + __float_as_int(q0));
+  e1 = __int_as_float(__float_as_int(r1) * 8388608 + __float_as_int(q1));
+}
+
 // =============================================================================================
 // attn_pp_kernel
 // =============================================================================================
@@ -85,7 +108,7 @@ __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.
 
 // TRACE: compile the clock64 stamps in (tools/attn_trace.py); the shipped instantiation carries no trace code — with the
 // stamps merely predicated off the kernel was 8 % slower
-template <int DVP, int TRACE>
+template <int DVP, int TRACE, int POLY>
 __global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = PPCfg<DVP>;
   constexpr int ST = Cfg::ST, BKV = 128;
@@ -253,9 +276,8 @@ __global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const _
           for (int i = 0; i < BKV; ++i)
             if (kv0 + i >= p.Nk) v[i >> 5][i & 31] = 0xff800000u;  // -inf
         }
-        // ---- row max, lazy reference update ------------------------------------------------------
-        float m_t;
-        {
+        // ---- tile 0 of a work item: the reference is this tile's row max (one explicit pass) -------
+        if (j == 0) {
           float mx[NCH];
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
@@ -267,22 +289,67 @@ __global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const _
             }
             mx[c] = fmaxf(a0, a1);
           }
-          m_t = mx[0];
+          m_ref = mx[0];
 #pragma unroll
-          for (int c = 1; c < NCH; ++c) m_t = fmaxf(m_t, mx[c]);
+          for (int c = 1; c < NCH; ++c) m_ref = fmaxf(m_ref, mx[c]);
+        } else {
+          mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has read P_{j-1}: the P columns may be overwritten, O is stable
+          tc_fence_after();
         }
-        bool pv_waited = (j == 0);  // tile 0: the epilogue of the previous work item has waited for its last PV
-        if (j == 0) {
-          m_ref = m_t;
-        } else if (__any_sync(0xffffffffu, (m_t - m_ref) * sl2 > LAZY_LOG2)) {
-          // exact online-softmax step for this warp's rows: new reference, O and l rescaled (rare after the first tiles)
+        if (trace) ts3 = clock64();
+        // ---- exponentials against the REFERENCE max with the row max taken on the fly; P -> tensor memory chunk by
+        //      chunk.  No separate max pass: the scores stay in registers, so the (rare, warp-uniform) case of a row max
+        //      more than 2^8 above its reference simply re-runs the pass after the exact online-softmax correction -------
+        float sum_t;
+#pragma unroll 1
+        for (int attempt = 0; attempt < 2; ++attempt) {
+          const float mb = m_ref * sl2;
+          const uint64_t sl2_2 = pk2(sl2, sl2), nmb_2 = pk2(-mb, -mb);
+          uint64_t sm2[4] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            uint32_t pkc[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float x0 = __uint_as_float(v[c][i]), x1 = __uint_as_float(v[c][i + 1]);
+              const float x2 = __uint_as_float(v[c][i + 2]), x3 = __uint_as_float(v[c][i + 3]);
+              mx0 = fmaxf(fmaxf(mx0, x0), x1);  // one 3-input FMNMX per pair
+              mx1 = fmaxf(fmaxf(mx1, x2), x3);
+              float t0, t1, t2, t3, e0, e1, e2, e3;
+              upk2(fma2(pk2(x0, x1), sl2_2, nmb_2), t0, t1);
+              upk2(fma2(pk2(x2, x3), sl2_2, nmb_2), t2, t3);
+              e0 = ex2f(t0);
+              e1 = ex2f(t1);
+              if (POLY && ((i >> 2) % POLY) == POLY - 1) {
+                ex2_poly2(t2, t3, e2, e3);  // this pair on the FMA pipe
+              } else {
+                e2 = ex2f(t2);
+                e3 = ex2f(t3);
+              }
+              sm2[(i >> 1) & 3] = add2(sm2[(i >> 1) & 3], pk2(e0, e1));
+              sm2[((i >> 1) + 1) & 3] = add2(sm2[((i >> 1) + 1) & 3], pk2(e2, e3));
+              pkc[i >> 1] = pack_h2(e0, e1);
+              pkc[(i >> 1) + 1] = pack_h2(e2, e3);
+            }
+            tmem_st_32x16(t_p + c * 16, pkc);  // row = lane, column k = keys (2k, 2k+1) as an fp16 pair (TS-mode A layout)
+          }
+          {
+            float s0, s1, s2, s3, s4, s5, s6, s7;
+            upk2(sm2[0], s0, s1);
+            upk2(sm2[1], s2, s3);
+            upk2(sm2[2], s4, s5);
+            upk2(sm2[3], s6, s7);
+            sum_t = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+          }
+          const float m_t = fmaxf(mx0, mx1);
+          if (j == 0 || attempt == 1 || !__any_sync(0xffffffffu, (m_t - m_ref) * sl2 > LAZY_LOG2)) break;
+          // exact online-softmax step for this warp's rows: new reference, O and l rescaled, then the pass again
           const float m_new = fmaxf(m_ref, m_t);
           const float alpha = ex2f((m_ref - m_new) * sl2);
           m_ref = m_new;
           l_run *= alpha;
-          mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has completed: O is stable, the P columns are free
-          tc_fence_after();
-          pv_waited = true;
+          tmem_st_wait();
 #pragma unroll
           for (int c = 0; c < DVP / 16; ++c) {
             uint32_t o[16];
@@ -292,38 +359,8 @@ __global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const _
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tmem_st_32x16(t_o + c * 16, o);
           }
-          tmem_st_wait();
         }
-        if (trace) ts3 = clock64();
-        // ---- exponentials against the reference max, P -> tensor memory chunk by chunk -------------
-        const float mb = m_ref * sl2;
-        const uint64_t sl2_2 = pk2(sl2, sl2), nmb_2 = pk2(-mb, -mb);
-        uint64_t sm2[4] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
-        if (!pv_waited) {
-          mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has read P_{j-1}: the P columns may be overwritten
-          tc_fence_after();
-        }
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          uint32_t pkc[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float t0, t1;
-            upk2(fma2(pk2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sl2_2, nmb_2), t0, t1);
-            const float e0 = ex2f(t0), e1 = ex2f(t1);
-            sm2[(i >> 1) & 3] = add2(sm2[(i >> 1) & 3], pk2(e0, e1));
-            pkc[i >> 1] = pack_h2(e0, e1);
-          }
-          tmem_st_32x16(t_p + c * 16, pkc);  // row = lane, column k = keys (2k, 2k+1) as an fp16 pair (TS-mode A layout)
-        }
-        {
-          float s0, s1, s2, s3, s4, s5, s6, s7;
-          upk2(sm2[0], s0, s1);
-          upk2(sm2[1], s2, s3);
-          upk2(sm2[2], s4, s5);
-          upk2(sm2[3], s6, s7);
-          l_run += ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
-        }
+        l_run += sum_t;
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_ready[X]);
@@ -776,8 +813,11 @@ static int attn_set_attr() {
 }
 template <int DVP>
 static int attn_pp_set_attr() {
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
+  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
   return 0;
 }
 
@@ -894,8 +934,16 @@ template <int DVP>
 static cudaError_t launch_pp(const AttnLaunchImpl* I, cudaStream_t stream) {
   AttnKParams p = I->p;
   p.dbg = g_attn_dbg;
-  if (p.dbg) return launch_pdl(attn_pp_kernel<DVP, 1>, I->grid, dim3(PPCfg<DVP>::THREADS), PPCfg<DVP>::SMEM, stream, p);
-  return launch_pdl(attn_pp_kernel<DVP, 0>, I->grid, dim3(PPCfg<DVP>::THREADS), PPCfg<DVP>::SMEM, stream, p);
+  // SDW_ATTN_POLY = 0 | 4 | 2: share of the exponentials evaluated on the FMA pipe (none, 1/4, 1/2) — A/B switch
+  static const int poly = [] { const char* e = std::getenv("SDW_ATTN_POLY"); return e ? std::atoi(e) : 0; }();
+  const dim3 blk(PPCfg<DVP>::THREADS);
+  if (p.dbg) {
+    if (poly == 4) return launch_pdl(attn_pp_kernel<DVP, 1, 4>, I->grid, blk, PPCfg<DVP>::SMEM, stream, p);
+    return launch_pdl(attn_pp_kernel<DVP, 1, 0>, I->grid, blk, PPCfg<DVP>::SMEM, stream, p);
+  }
+  if (poly == 4) return launch_pdl(attn_pp_kernel<DVP, 0, 4>, I->grid, blk, PPCfg<DVP>::SMEM, stream, p);
+  if (poly == 2) return launch_pdl(attn_pp_kernel<DVP, 0, 2>, I->grid, blk, PPCfg<DVP>::SMEM, stream, p);
+  return launch_pdl(attn_pp_kernel<DVP, 0, 0>, I->grid, blk, PPCfg<DVP>::SMEM, stream, p);
 }
 
 int launch_attention(const AttnLaunch& L, cudaStream_t stream) {

@@ -132,6 +132,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
     tmem_relinquish_2cta();
   }
   tc_fence_before();
+  __syncthreads();  // CTA-scope barrier between tcgen05.alloc's shared-memory write and its readers: the cluster barrier
+                    // below already orders them, but compute-sanitizer racecheck only models bar.sync (108 false hazards)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
