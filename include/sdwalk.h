@@ -192,17 +192,17 @@ typedef struct sdw_gemm_desc {
   int32_t bn;                /* BLOCK_N: 0 auto, 64/128/160/256 */
   int32_t ver;               /* 0 auto, 1: one CTA per 128xBN tile, 2: persistent CTA pairs (256xBN) */
   int32_t nsub;              /* 0 auto, 1 / 2: accumulators per activation tile in the CTA-pair kernel */
-  int32_t cl;                /* 0 auto, 2 / 4: cluster size (4: activation tile multicast to two CTA pairs) */
+  int32_t ew;                /* 0 auto, 2 / 4: epilogue warps per TMEM lane quarter of the CTA-pair kernel (4: needs the TMA epilogue) */
   int32_t tr;                /* 0 auto, 1 never, 2 require: 3x3 taps reuse one activation box in shared memory */
   int32_t et;                /* 0 auto, 1 never, 2 require: TMA-store epilogue with a TMA-fed residual ring.  With mode 2 the
                               * V^T rows are written through TMA, which clips the token extent at 16-byte granularity: the
                               * vt_ld padding up to the next multiple of 8 tokens may receive finite filler values */
-  int32_t as;                /* 0 auto, 1 never, 2 require: activation rows of an M pair stay in shared memory across its N tiles */
+  int32_t reserved0;         /* must be 0 */
 } sdw_gemm_desc;
 
 int sdw_gemm(const sdw_gemm_desc* desc, void* stream);
-/* planner introspection, host only (also in plan-only mode): out = {kernel version, BLOCK_N, accumulators, cluster size,
- * tap reuse, TMA epilogue, pipeline stages, A-stationary, grid size, tile w, tile h, tile b} */
+/* planner introspection, host only (also in plan-only mode): out = {kernel version, BLOCK_N, accumulators, epilogue warps
+ * per lane quarter, tap reuse, TMA epilogue, pipeline stages, 0, grid size, tile w, tile h, tile b} */
 int sdw_debug_plan(const sdw_gemm_desc* desc, int32_t out[12]);
 
 /* fused attention on tcgen05 (tests / tooling): O = softmax(Q K^T d^-1/2) V per (batch, head).

@@ -39,7 +39,7 @@ class GemmDesc(C.Structure):
         ("o_sW", C.c_int64), ("o_sH", C.c_int64), ("o_sB", C.c_int64),
         ("mode", C.c_int32), ("act", C.c_int32), ("alpha", C.c_float),
         ("vt_col0", C.c_int32), ("vt_d", C.c_int32), ("vt_heads", C.c_int32), ("vt_ntok", C.c_int32),
-        ("vt", C.c_void_p), ("vt_ld", C.c_int64), ("bn", C.c_int32), ("ver", C.c_int32), ("nsub", C.c_int32), ("cl", C.c_int32), ("tr", C.c_int32), ("et", C.c_int32), ("as_", C.c_int32),
+        ("vt", C.c_void_p), ("vt_ld", C.c_int64), ("bn", C.c_int32), ("ver", C.c_int32), ("nsub", C.c_int32), ("ew", C.c_int32), ("tr", C.c_int32), ("et", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

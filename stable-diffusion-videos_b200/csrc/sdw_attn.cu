@@ -101,17 +101,14 @@ struct PPCfg {
   static_assert(128 * REGS_OTHER + 256 * REGS_SOFTMAX <= 65536 - 1024, "register file (an exact fit hung setmaxnreg.inc on hardware: keep slack)");
 };
 
-template <int REGS>
-__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
-template <int REGS>
-__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
 // TRACE: compile the clock64 stamps in (tools/attn_trace.py); the shipped instantiation carries no trace code — with the
 // stamps merely predicated off the kernel was 8 % slower
-template <int DVP, int TRACE, int POLY>
+template <int DVP, int TRACE, int POLY, int MODE>
 __global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = PPCfg<DVP>;
   constexpr int ST = Cfg::ST, BKV = 128;
+  constexpr bool FUSE = (MODE & 1) != 0, LATE = (MODE & 2) != 0;  // A/B switches of the softmax loop (launch_pp)
   constexpr int NCH = BKV / 32;                     // 32-column chunks of a score row
   constexpr uint32_t GROUP = 128;                   // softmax threads per query tile
   extern __shared__ uint8_t smem_raw[];
@@ -276,8 +273,10 @@ __global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const _
           for (int i = 0; i < BKV; ++i)
             if (kv0 + i >= p.Nk) v[i >> 5][i & 31] = 0xff800000u;  // -inf
         }
-        // ---- tile 0 of a work item: the reference is this tile's row max (one explicit pass) -------
-        if (j == 0) {
+        // ---- row max by an explicit pass: always for tile 0 of a work item (it sets the reference); for every tile when
+        //      the max is not fused into the exponential pass (FUSE = 0) -------------------------------------------
+        bool pv_waited = (j == 0);  // tile 0: the epilogue of the previous work item has waited for its last PV
+        if (!FUSE || j == 0) {
           float mx[NCH];
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
@@ -289,17 +288,41 @@ __global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const _
             }
             mx[c] = fmaxf(a0, a1);
           }
-          m_ref = mx[0];
+          float m_t = mx[0];
 #pragma unroll
-          for (int c = 1; c < NCH; ++c) m_ref = fmaxf(m_ref, mx[c]);
-        } else {
-          mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has read P_{j-1}: the P columns may be overwritten, O is stable
-          tc_fence_after();
+          for (int c = 1; c < NCH; ++c) m_t = fmaxf(m_t, mx[c]);
+          if (j == 0) {
+            m_ref = m_t;
+          } else if (__any_sync(0xffffffffu, (m_t - m_ref) * sl2 > LAZY_LOG2)) {
+            // exact online-softmax step for this warp's rows: new reference, O and l rescaled (rare after the first tiles)
+            const float m_new = fmaxf(m_ref, m_t);
+            const float alpha = ex2f((m_ref - m_new) * sl2);
+            m_ref = m_new;
+            l_run *= alpha;
+            mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has completed: O is stable, the P columns are free
+            tc_fence_after();
+            pv_waited = true;
+#pragma unroll
+            for (int c = 0; c < DVP / 16; ++c) {
+              uint32_t o[16];
+              tmem_ld_32x16(t_o + c * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x16(t_o + c * 16, o);
+            }
+            tmem_st_wait();
+          }
         }
         if (trace) ts3 = clock64();
-        // ---- exponentials against the REFERENCE max with the row max taken on the fly; P -> tensor memory chunk by
-        //      chunk.  No separate max pass: the scores stay in registers, so the (rare, warp-uniform) case of a row max
-        //      more than 2^8 above its reference simply re-runs the pass after the exact online-softmax correction -------
+        if (!LATE && !pv_waited) {
+          mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has read P_{j-1}: the P columns may be overwritten, O is stable
+          tc_fence_after();
+          pv_waited = true;
+        }
+        // ---- exponentials against the REFERENCE max; P -> tensor memory chunk by chunk.  FUSE: the row max is taken on
+        //      the fly instead of by a separate pass — the scores stay in registers, so the (rare, warp-uniform) case of
+        //      a row max more than 2^8 above its reference re-runs the pass after the exact online-softmax correction ---
         float sum_t;
 #pragma unroll 1
         for (int attempt = 0; attempt < 2; ++attempt) {
@@ -314,8 +337,10 @@ __global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const _
             for (int i = 0; i < 32; i += 4) {
               const float x0 = __uint_as_float(v[c][i]), x1 = __uint_as_float(v[c][i + 1]);
               const float x2 = __uint_as_float(v[c][i + 2]), x3 = __uint_as_float(v[c][i + 3]);
-              mx0 = fmaxf(fmaxf(mx0, x0), x1);  // one 3-input FMNMX per pair
-              mx1 = fmaxf(fmaxf(mx1, x2), x3);
+              if (FUSE) {
+                mx0 = fmaxf(fmaxf(mx0, x0), x1);  // one 3-input FMNMX per pair
+                mx1 = fmaxf(fmaxf(mx1, x2), x3);
+              }
               float t0, t1, t2, t3, e0, e1, e2, e3;
               upk2(fma2(pk2(x0, x1), sl2_2, nmb_2), t0, t1);
               upk2(fma2(pk2(x2, x3), sl2_2, nmb_2), t2, t3);
@@ -332,6 +357,12 @@ __global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const _
               pkc[i >> 1] = pack_h2(e0, e1);
               pkc[(i >> 1) + 1] = pack_h2(e2, e3);
             }
+            if (LATE && c == 0 && !pv_waited) {
+              // PV_{j-1} has read P_{j-1} and O is stable — waited for only after the first chunk's exponentials
+              mbar_wait(&pv_done[X], (gt - 1) & 1);
+              tc_fence_after();
+              pv_waited = true;
+            }
             tmem_st_32x16(t_p + c * 16, pkc);  // row = lane, column k = keys (2k, 2k+1) as an fp16 pair (TS-mode A layout)
           }
           {
@@ -343,7 +374,7 @@ __global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const _
             sum_t = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
           }
           const float m_t = fmaxf(mx0, mx1);
-          if (j == 0 || attempt == 1 || !__any_sync(0xffffffffu, (m_t - m_ref) * sl2 > LAZY_LOG2)) break;
+          if (!FUSE || j == 0 || attempt == 1 || !__any_sync(0xffffffffu, (m_t - m_ref) * sl2 > LAZY_LOG2)) break;
           // exact online-softmax step for this warp's rows: new reference, O and l rescaled, then the pass again
           const float m_new = fmaxf(m_ref, m_t);
           const float alpha = ex2f((m_ref - m_new) * sl2);
@@ -811,14 +842,17 @@ static int attn_set_attr() {
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<DKA, DVP, BKV, ST, SB, PT>::SMEM));
   return 0;
 }
-template <int DVP>
-static int attn_pp_set_attr() {
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
-  SDW_CUDA_OK(cudaFuncSetAttribute(attn_pp_kernel<DVP, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPCfg<DVP>::SMEM));
-  return 0;
+// instantiations: the shipped configuration for every head-dim class; the A/B grid (POLY x MODE) for head dim 40 only
+template <int DVP, int TRACE, int POLY, int MODE>
+static cudaError_t pp_launch_one(const AttnKParams& p, dim3 grid, cudaStream_t stream) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_pp_kernel<DVP, TRACE, POLY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         PPCfg<DVP>::SMEM);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  return launch_pdl(attn_pp_kernel<DVP, TRACE, POLY, MODE>, grid, dim3(PPCfg<DVP>::THREADS), PPCfg<DVP>::SMEM, stream, p);
 }
 
 static bool g_attn_init = false;
@@ -830,10 +864,6 @@ static int attn_init() {
   if (int e = attn_set_attr<1, 64, 128, 2, 1, 1>()) return e;
   if (int e = attn_set_attr<2, 80, 64, 2, 1, 1>()) return e;
   if (int e = attn_set_attr<3, 160, 64, 3, 2, 0>()) return e;
-  if (int e = attn_pp_set_attr<16>()) return e;
-  if (int e = attn_pp_set_attr<32>()) return e;
-  if (int e = attn_pp_set_attr<48>()) return e;
-  if (int e = attn_pp_set_attr<64>()) return e;
   g_attn_init = true;
   return 0;
 }
@@ -843,11 +873,13 @@ bool attn_supported(int d) { return d % 8 == 0 && d >= 8 && d <= 160; }
 static long long* g_attn_dbg = nullptr;
 void attention_set_trace(long long* buf) { g_attn_dbg = buf; }
 
-static int variant_for(int d, int Nk) {
+static int variant_for(int d, int Nk, int Nq) {
   // SDW_ATTN_PP=0: the one-query-tile kernel everywhere (A/B measurements)
   static const bool pp = [] { const char* e = std::getenv("SDW_ATTN_PP"); return !(e && e[0] == '0'); }();
   const int cls = d <= 16 ? 0 : (d <= 32 ? 1 : (d <= 48 ? 2 : 3));
-  if (d <= 64) return (pp && Nk > 128) ? 8 + cls : cls;
+  // SDW_ATTN_PP_CROSS=1: single-KV-tile (cross) attention through the two-tile kernel as well (A/B switch)
+  static const bool pp_cross = [] { const char* e = std::getenv("SDW_ATTN_PP_CROSS"); return e && e[0] == '1'; }();
+  if (d <= 64) return (pp && (Nk > 128 || (pp_cross && Nq >= 256))) ? 8 + cls : cls;
   return d <= 80 ? 4 : 5;
 }
 
@@ -858,7 +890,7 @@ int plan_attention(const AttnDesc& a, AttnLaunch* L) {
   static_assert(sizeof(AttnLaunchImpl) <= sizeof(AttnLaunch::storage), "AttnLaunch storage too small");
   AttnLaunchImpl* I = reinterpret_cast<AttnLaunchImpl*>(L->storage);
   std::memset(I, 0, sizeof(*I));
-  I->variant = variant_for(a.d, a.Nk);
+  I->variant = variant_for(a.d, a.Nk, a.Nq);
   const bool pp = I->variant >= 8;
   const int bkv = (I->variant == 4 || I->variant == 5) ? 64 : 128;
   const int dvp_tab[12] = {16, 32, 48, 64, 80, 160, 0, 0, 16, 32, 48, 64};
@@ -930,20 +962,34 @@ static cudaError_t launch_fwd(const AttnLaunchImpl* I, cudaStream_t stream) {
   return launch_pdl(attn_fwd_kernel<DKA, DVP, BKV, ST, SB, PT>, I->grid, dim3(ATT_THREADS),
                     AttnCfg<DKA, DVP, BKV, ST, SB, PT>::SMEM, stream, I->p);
 }
+static constexpr int PP_POLY = 0, PP_MODE = 0;  // shipped softmax-loop configuration
 template <int DVP>
 static cudaError_t launch_pp(const AttnLaunchImpl* I, cudaStream_t stream) {
   AttnKParams p = I->p;
   p.dbg = g_attn_dbg;
-  // SDW_ATTN_POLY = 0 | 4 | 2: share of the exponentials evaluated on the FMA pipe (none, 1/4, 1/2) — A/B switch
-  static const int poly = [] { const char* e = std::getenv("SDW_ATTN_POLY"); return e ? std::atoi(e) : 0; }();
-  const dim3 blk(PPCfg<DVP>::THREADS);
-  if (p.dbg) {
-    if (poly == 4) return launch_pdl(attn_pp_kernel<DVP, 1, 4>, I->grid, blk, PPCfg<DVP>::SMEM, stream, p);
-    return launch_pdl(attn_pp_kernel<DVP, 1, 0>, I->grid, blk, PPCfg<DVP>::SMEM, stream, p);
+  if (DVP == 48) {
+    // A/B grid for the dominant shape (head dim 40): SDW_ATTN_POLY = 0 | 4 (share of exponentials on the FMA pipe),
+    // SDW_ATTN_MODE bit 0 = row max fused into the exponential pass, bit 1 = PV_{j-1} awaited after the first chunk
+    static const int poly = [] { const char* e = std::getenv("SDW_ATTN_POLY"); return e ? std::atoi(e) : PP_POLY; }();
+    static const int mode = [] { const char* e = std::getenv("SDW_ATTN_MODE"); return e ? std::atoi(e) : PP_MODE; }();
+    const int key = (p.dbg ? 100 : 0) + (poly == 4 ? 10 : 0) + (mode & 3);
+    switch (key) {
+      case 0: return pp_launch_one<48, 0, 0, 0>(p, I->grid, stream);
+      case 1: return pp_launch_one<48, 0, 0, 1>(p, I->grid, stream);
+      case 2: return pp_launch_one<48, 0, 0, 2>(p, I->grid, stream);
+      case 3: return pp_launch_one<48, 0, 0, 3>(p, I->grid, stream);
+      case 10: return pp_launch_one<48, 0, 4, 0>(p, I->grid, stream);
+      case 11: return pp_launch_one<48, 0, 4, 1>(p, I->grid, stream);
+      case 12: return pp_launch_one<48, 0, 4, 2>(p, I->grid, stream);
+      case 13: return pp_launch_one<48, 0, 4, 3>(p, I->grid, stream);
+      case 100: return pp_launch_one<48, 1, 0, 0>(p, I->grid, stream);
+      case 101: return pp_launch_one<48, 1, 0, 1>(p, I->grid, stream);
+      case 110: return pp_launch_one<48, 1, 4, 0>(p, I->grid, stream);
+      case 111: return pp_launch_one<48, 1, 4, 1>(p, I->grid, stream);
+      default: return pp_launch_one<48, 1, PP_POLY, PP_MODE>(p, I->grid, stream);
+    }
   }
-  if (poly == 4) return launch_pdl(attn_pp_kernel<DVP, 0, 4>, I->grid, blk, PPCfg<DVP>::SMEM, stream, p);
-  if (poly == 2) return launch_pdl(attn_pp_kernel<DVP, 0, 2>, I->grid, blk, PPCfg<DVP>::SMEM, stream, p);
-  return launch_pdl(attn_pp_kernel<DVP, 0, 0>, I->grid, blk, PPCfg<DVP>::SMEM, stream, p);
+  return pp_launch_one<DVP, 0, PP_POLY, PP_MODE>(p, I->grid, stream);
 }
 
 int launch_attention(const AttnLaunch& L, cudaStream_t stream) {

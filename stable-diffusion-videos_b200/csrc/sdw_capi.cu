@@ -52,8 +52,8 @@ int sdw_debug_plan(const sdw_gemm_desc* c, int32_t out[12]) {
   if (int e = to_desc(c, d)) return e;
   GemmLaunch L;
   if (int e = plan_gemm(d, &L)) return e;
-  out[0] = L.ver; out[1] = L.bn; out[2] = L.nsub; out[3] = L.cl; out[4] = L.tr;
-  out[5] = L.p.epi_tma; out[6] = L.p.nstages; out[7] = L.p.a_stationary;
+  out[0] = L.ver; out[1] = L.bn; out[2] = L.nsub; out[3] = L.ew; out[4] = L.tr;
+  out[5] = L.p.epi_tma; out[6] = L.p.nstages; out[7] = 0;
   out[8] = static_cast<int32_t>(L.grid.x); out[9] = L.p.bw; out[10] = L.p.bh; out[11] = L.p.bb;
   return 0;
 }
@@ -85,10 +85,9 @@ static int to_desc(const sdw_gemm_desc* c, GemmDesc& d) {
   d.bn = c->bn;
   d.ver = c->ver;
   d.nsub = c->nsub;
-  d.cl = c->cl;
+  d.ew = c->ew;
   d.tr = c->tr;
   d.et = c->et;
-  d.as = c->as;
   return 0;
 }
 

@@ -309,7 +309,7 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
   bool reuse = false;
   {
     static const int tr_env = [] { const char* e = std::getenv("SDW_GEMM_TR"); return e ? std::atoi(e) : -1; }();
-    const bool can = ver == 2 && d.conv == 1 && Wd % 16 == 0 && Hd % 8 == 0 && d.cl != 4;
+    const bool can = ver == 2 && d.conv == 1 && Wd % 16 == 0 && Hd % 8 == 0;
     if (d.tr == 2) SDW_REQUIRE(can, "tap reuse needs a 3x3 stride-1 conv on the CTA-pair kernel with W % 16 == 0, H % 8 == 0");
     reuse = can && d.tr != 1 && (d.tr == 2 || tr_env != 0);
     if (reuse) {
@@ -383,23 +383,28 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
     const int64_t max_off = static_cast<int64_t>(d.B) * OH * OW * std::max<int64_t>(d.ldc, d.ldr ? d.ldr : d.ldc);
     SDW_REQUIRE(max_off < (int64_t(1) << 31) || ver == 1, "output too large for the 2-CTA epilogue (>= 2^31 elements)");
   }
-  L->cl = 2;
+  L->ew = 2;
   if (ver == 2) {
     p.m_pairs = (m_tiles_f + 1) / 2;
     p.n_tiles = (d.N + bn * nsub - 1) / (bn * nsub);
-    // 4-CTA clusters (activation-tile multicast across two N tiles) when there are >= 2 N tiles of a supported width
-    static const int cl_env = [] { const char* e = std::getenv("SDW_GEMM_CL"); return e ? std::atoi(e) : 0; }();
-    int cl = d.cl ? d.cl : (cl_env ? cl_env : 2);
-    if (cl == 4 && !(nsub == 1 && (bn == 160 || bn == 256) && p.n_tiles >= 2 && !d.b_batched && !reuse)) cl = 2;
-    L->cl = cl;
-    if (cl == 4) {
-      int maxc = g_plan_only ? 32 : (gemm2_init() == 0 ? gemm2_max_clusters4() : 32);
-      const int groups = p.m_pairs * ((p.n_tiles + 1) / 2);
-      L->grid = dim3(4 * std::min(groups, maxc), 1, 1);
-    } else {
-      const int clusters = std::min(p.m_pairs * p.n_tiles, 74);
-      L->grid = dim3(2 * clusters, 1, 1);
+    L->grid = dim3(2 * std::min(p.m_pairs * p.n_tiles, 74), 1, 1);  // one CTA pair per SM pair
+    // division-free tile coordinates (sdw_gemm2.cu: tile_coords)
+    {
+      const int n_groups = p.n_tiles;
+      const int64_t max_t = static_cast<int64_t>(p.m_pairs) * n_groups, max_m = 2 * static_cast<int64_t>(p.m_pairs) + 1;
+      auto magic = [](int64_t dv) { return dv <= 1 ? 0u : static_cast<uint32_t>(((int64_t(1) << 32) + dv - 1) / dv); };
+      const int64_t twh = static_cast<int64_t>(p.tiles_w) * p.tiles_h;
+      SDW_REQUIRE(max_t * n_groups < (int64_t(1) << 32) && max_m * twh < (int64_t(1) << 32), "tile grid too large for the 32-bit fast division");
+      p.mg_ng = magic(n_groups);
+      p.mg_tw = magic(p.tiles_w);
+      p.mg_twh = magic(twh);
     }
+  }
+  {
+    auto lg2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+    p.lg_bw = lg2(p.bw);
+    p.lg_bh = lg2(p.bh);
+    SDW_REQUIRE((1 << p.lg_bw) == p.bw && (1 << p.lg_bh) == p.bh, "tile extents must be powers of two");
   }
   // tensor maps: A
   for (int m = 0; m < nmaps; ++m) {
@@ -453,7 +458,7 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
     const bool vt_ok = d.mode != GEMM_QKV_VT ||
                        (Hd == 1 && bw == BM && d.conv == 0 && d.vt_col0 % 32 == 0 && d.vt_ld % 8 == 0 && ok16(d.vt) &&
                         d.vt_ntok == Wd && !d.resid);
-    bool can = L->cl == 2 && nsub == 1 && !d.b_batched && vt_ok && (!d.rowvec || d.rowvec_ld == 0) &&
+    bool can = nsub == 1 && !d.b_batched && vt_ok && (!d.rowvec || d.rowvec_ld == 0) &&
                d.N % 8 == 0 && bn <= 256 && ok16(d.out) && ok_strides(osW, osH, osB) && (!d.bias || ok16(d.bias)) &&
                (!d.resid || (ok16(d.resid) && ok_strides(rsW, rsH, rsB) && d.mode == GEMM_PLAIN));
     if (d.et == 2) SDW_REQUIRE(can, "the TMA epilogue needs the CTA-pair kernel, plain/GEGLU mode, no row vector and 16-byte aligned views");
@@ -469,21 +474,18 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
     const int epi_bytes = p.epi_tma ? G2_EPI_OUT + G2_EPI_BIAS + (d.resid ? G2_RES_STAGES * G2_RES_STAGE : 0) : G2_EPI_OLD;
     p.nstages = std::min(8, (G2_SMEM_USABLE - G2_BAR_BYTES - epi_bytes) / (a_stage + b_stage));
     SDW_REQUIRE(p.nstages >= 2, "no room for a two-stage operand pipeline");
-    // A-stationary: (kchunks + 1) resident activation slots, the ring carries weights only
-    p.a_stationary = 0;
-    p.a_slots = 0;
+    // epilogue width: four warps per TMEM lane quarter where the epilogue, not the MMA, sets the tile time — the per-tap
+    // kernels up to 24 K blocks (every transformer linear / 1x1 conv of the UNet; profiles/r02_ncu_epilogue_shortk.md).
+    // SDW_GEMM_EW=2 keeps the 8-warp epilogue everywhere (A/B)
     {
-      static const int as_env = [] { const char* e = std::getenv("SDW_GEMM_AS"); return e ? std::atoi(e) : 0; }();
-      const int slots = kchunks + 1;
-      const int b_st = std::min(8, (G2_SMEM_USABLE - G2_BAR_BYTES - epi_bytes - slots * 16384) / b_stage);
-      const bool can_as = L->cl == 2 && nsub == 1 && d.conv == 0 && !d.b_batched && !reuse && kchunks <= 7 && slots <= 8 &&
-                          p.n_tiles >= 3 && p.m_pairs >= 74 && b_st >= 3;
-      if (d.as == 2) SDW_REQUIRE(can_as, "A-stationary needs a 1x1 / linear GEMM with K <= 448, >= 3 N tiles and >= 74 M pairs");
-      if (can_as && d.as != 1 && (d.as == 2 || as_env == 1)) {
-        p.a_stationary = 1;
-        p.a_slots = slots;
-        p.nstages = b_st;
-        L->grid = dim3(2 * std::min(p.m_pairs, 74), 1, 1);
+      static const int ew_env = [] { const char* e = std::getenv("SDW_GEMM_EW"); return e ? std::atoi(e) : 0; }();
+      const bool can4 = p.epi_tma && nsub == 1 && !reuse;
+      if (d.ew == 4) SDW_REQUIRE(can4, "the 16-warp epilogue needs the TMA epilogue, one accumulator and the per-tap mainloop");
+      const int want4 = d.ew ? d.ew == 4 : (ew_env ? ew_env == 4 : kblocks <= 24);
+      L->ew = can4 && want4 ? 4 : 2;
+      if (L->ew == 4) {  // 16 per-warp bias copies instead of 8
+        p.nstages = std::min(8, (G2_SMEM_USABLE - G2_BAR_BYTES - epi_bytes - G2_EPI_BIAS) / (a_stage + b_stage));
+        SDW_REQUIRE(p.nstages >= 2, "no room for a two-stage operand pipeline");
       }
     }
     if (p.epi_tma) {

@@ -18,8 +18,13 @@
 // Mainloop flavours (all in this kernel; chosen per GEMM by plan_gemm, sdw_gemm.cu):
 //   per-tap      one activation box per (tap, channel chunk)              every conv / linear (the original form)
 //   TR = 1       tap reuse: one (8+2)-row box per (channel chunk, kx) feeds the three ky taps      3x3 stride-1 convs
-//   a_stationary the activation rows of an M pair stay resident across its N tiles (opt-in, no gain measured)
-//   CL = 4       activation tile TMA-multicast to two CTA pairs (opt-in, slower)
+// (two more flavours were built, measured slower and removed again: the activation rows of an M pair kept resident
+//  across its N tiles, and 4-CTA clusters with the activation tile TMA-multicast to two CTA pairs — profiles/
+//  r01_epi_bench_a_stationary.txt, r01_gemm_shapes_cluster4_multicast.txt.)
+// EW = epilogue warps per TMEM lane quarter.  EW = 2 (384 threads) everywhere; EW = 4 (640 threads, registers
+// re-balanced with setmaxnreg) for the short-K GEMMs, whose tile time is set by the epilogue — ncu: the MMA issuer
+// spins on tmem_empty and the TMA producer on the full ring while two epilogue warps per scheduler run at 0.44 IPC
+// (profiles/r02_ncu_epilogue_shortk.md).
 // Shared memory is carved at run time: [barriers 1 KB | operand ring | epilogue buffers]; the planner sizes the ring
 // from what the chosen epilogue (classic: 16 KB, TMA: 40-72 KB) leaves of the 227 KB.
 #include "sdw_gemm_epi.cuh"
@@ -28,7 +33,9 @@
 
 namespace sdw {
 
-static constexpr int G2_THREADS = 384;  // warpgroup 0: producer, MMA (+2 idle warps); warpgroups 1-2: 8 epilogue warps
+// warpgroup 0: producer, MMA, residual producer (+1 idle warp); then EW warpgroups of epilogue warps
+template <int EW> struct G2Threads { static constexpr int value = 128 + 128 * EW; };
+static constexpr int G2_REGS_ROLE = 56, G2_REGS_EPI = 112;  // EW = 4: 128 * 56 + 512 * 112 = 64512 registers
 static constexpr int G2_A_STAGE = 128 * 64 * 2;
 
 // NSUB = accumulators per activation tile: NSUB = 2 computes a 256 x (2*BN) tile per CTA pair — the A tile is pulled
@@ -58,13 +65,11 @@ struct Gemm2Cfg {
   static constexpr int SMEM_BYTES = G2_SMEM_DYN;
 };
 
-// CL = cluster size.  CL = 4: two CTA pairs of one cluster compute the two neighbouring N tiles of the same M pair; the
-// activation tile is loaded ONCE per cluster (TMA multicast from pair 0 into both pairs' shared memory), which removes
-// a third of the L2->SM operand traffic that bounds this kernel (profiles/r01_mma_eff_vs_blockN.txt).
-template <int BN, int NSUB, int CL, int TR = 0>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
+template <int BN, int NSUB, int EW, int TR = 0>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2Threads<EW>::value, 1)
     gemm2_tc_kernel(const __grid_constant__ GemmKParams p) {
-  static_assert(!(TR && CL != 2), "tap reuse is a CTA-pair variant");
+  static_assert(EW == 2 || (EW == 4 && NSUB == 1), "four epilogue warps per lane quarter: TMA epilogue, one accumulator");
+  constexpr int CL = 2;
   using Cfg = Gemm2Cfg<BN, NSUB, TR>;
   constexpr int A_STAGE = Cfg::A_STAGE;
   constexpr int NBUF = Cfg::NBUF;
@@ -77,27 +82,22 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
   uint64_t* tmem_empty = tmem_full + 2;               // [2]  (leader's copy is the one in use)
   uint64_t* res_full = tmem_empty + 2;                // [G2_RES_STAGES]  residual ring (TMA epilogue)
   uint64_t* res_empty = res_full + G2_RES_STAGES;
-  uint64_t* a_full = res_empty + G2_RES_STAGES;  // [8]  A-stationary: resident activation slots
-  uint64_t* a_empty = a_full + 8;                // [8]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(a_empty + 8);
-  const bool AS = !TR && NSUB == 1 && CL == 2 && p.a_stationary != 0;
-  const int NA = p.a_slots;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty + G2_RES_STAGES);
   uint8_t* smem_a = smem + G2_BAR_BYTES;
-  uint8_t* smem_b = smem_a + (AS ? NA : STAGES) * A_STAGE;
-  uint8_t* epi_stage = smem_b + STAGES * Cfg::B_STAGE;  // classic: 8 x 2 KB; TMA: 8 x 4 KB slabs, 8 x 1 KB bias, ring
+  uint8_t* smem_b = smem_a + STAGES * A_STAGE;
+  // epilogue buffers.  classic: 2 KB per warp; TMA: output slabs (EW = 2: two 2 KB slabs per warp, EW = 4: one),
+  // 1 KB bias copy per warp, residual ring
+  uint8_t* epi_stage = smem_b + STAGES * Cfg::B_STAGE;
   uint8_t* epi_bias = epi_stage + G2_EPI_OUT;
-  uint8_t* res_ring = epi_bias + G2_EPI_BIAS;
+  uint8_t* res_ring = epi_bias + (EW / 2) * G2_EPI_BIAS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();  // rank in the cluster
-  const uint32_t rank = crank & 1;           // rank in the CTA pair
-  const uint32_t pair_id = crank >> 1;       // 0 for CL = 2
-  const uint32_t lead_rank = crank & ~1u;    // cluster rank of this pair's leader
+  const uint32_t rank = cluster_ctarank();  // rank in the CTA pair (cluster of two)
+  constexpr uint32_t lead_rank = 0;         // cluster rank of the pair's leader
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x / CL;
   const int nclusters = gridDim.x / CL;
-  constexpr int NPAIR = CL / 2;
-  const int n_groups = (p.n_tiles + NPAIR - 1) / NPAIR;  // N tiles are handed out NPAIR at a time
+  const int n_groups = p.n_tiles;
   const int total_tiles = p.m_pairs * n_groups;
   const int num_kb = TR ? 3 * p.kchunks : p.ntaps * p.kchunks;  // pipeline stages per tile
 
@@ -106,20 +106,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
     tma_prefetch_desc(&p.mapB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      // pair 0 also fills pair 1's activation stage, so its slot is free only when BOTH pairs' MMAs have drained it
-      mbar_init(&empty_bar[s], (CL == 4 && pair_id == 0) ? 2 : 1);
+      mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 16);  // 8 epilogue warps x 2 CTAs
+      mbar_init(&tmem_empty[a], 8 * EW);  // 4 * EW epilogue warps x 2 CTAs
     }
     for (int r = 0; r < G2_RES_STAGES; ++r) {
       mbar_init(&res_full[r], 1);
       mbar_init(&res_empty[r], 4);  // the four warps (one per TMEM lane quarter) that own the chunk's parity
-    }
-    for (int r = 0; r < 8; ++r) {
-      mbar_init(&a_full[r], 1);
-      mbar_init(&a_empty[r], 1);
     }
     if (p.epi_tma) {
       tma_prefetch_desc(&p.mapOut);
@@ -132,8 +127,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
     tmem_relinquish_2cta();
   }
   tc_fence_before();
-  __syncthreads();  // CTA-scope barrier between tcgen05.alloc's shared-memory write and its readers: the cluster barrier
-                    // below already orders them, but compute-sanitizer racecheck only models bar.sync (108 false hazards)
+  // (compute-sanitizer racecheck reports tcgen05.alloc's shared-memory write of the TMEM address against the read below
+  // as a hazard — with or without an extra bar.sync here: it does not model the tensor-core unit's write; the cluster
+  // barrier orders the two.  profiles/r02_sanitizer_racecheck.md)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
@@ -142,69 +138,46 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
   auto tile_coords = [&](int t, int& x0, int& y0, int& b0, int& n0) {
     // N fastest: the n_tiles column tiles of one M pair run on neighbouring clusters at the same time, so the
     // activation tile is fetched from DRAM once and re-read from L2 (the whole weight matrix is L2-resident anyway)
-    const int m_pair = t / n_groups;
-    const int n_tile = (t - m_pair * n_groups) * NPAIR + static_cast<int>(pair_id);
+    const int m_pair = fast_div(t, p.mg_ng);
+    const int n_tile = t - m_pair * n_groups;
     const int m_tile = m_pair * 2 + static_cast<int>(rank);
-    const int tw = m_tile % p.tiles_w;
-    const int th = (m_tile / p.tiles_w) % p.tiles_h;
-    const int tb = m_tile / (p.tiles_w * p.tiles_h);
+    const int tb = fast_div(m_tile, p.mg_twh);
+    const int rem = m_tile - tb * (p.tiles_w * p.tiles_h);
+    const int th = fast_div(rem, p.mg_tw);
+    const int tw = rem - th * p.tiles_w;
     x0 = tw * p.bw;
     y0 = th * p.bh;
     b0 = tb * p.bb;
     n0 = n_tile * (NSUB * BN);
   };
 
-  // i-th tile of this cluster.  Default: t = cluster_id + i * nclusters (N fastest across clusters).  A-stationary: the
-  // cluster owns M pairs cluster_id, cluster_id + nclusters, ... and walks all N tiles of each in turn.
+  // i-th tile of this cluster: t = cluster_id + i * nclusters (N fastest across clusters)
   auto tile_index = [&](int i, int& t) {
-    if (AS) {
-      const int mp = cluster_id + (i / n_groups) * nclusters;
-      t = mp * n_groups + i % n_groups;
-      return mp < p.m_pairs;
-    }
     t = cluster_id + i * nclusters;
     return t < total_tiles;
   };
 
+  // EW = 4: registers re-balanced inside the two branches (they only meet again at the teardown) — the role warps need
+  // few, the 16 epilogue warps take the rest
+  if (warp < 4) {
+  if (EW == 4) reg_dealloc<G2_REGS_ROLE>();
   if (warp == 0) {
     // =========================== TMA producer (both CTAs) ==========================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t ga = 0;  // A-stationary: activation chunks loaded so far
       int t;
       for (int i = 0; tile_index(i, t); ++i) {
         int x0, y0, b0, n0;
         tile_coords(t, x0, y0, b0, n0);
-        if (AS) {
-          const bool first_n = (t % n_groups) == 0;
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            if (first_n) {
-              const uint32_t slot = ga % NA;
-              mbar_wait(&a_empty[slot], ((ga / NA) & 1) ^ 1);
-              if (leader) mbar_expect_tx(&a_full[slot], 2 * A_STAGE);
-              tma_load_4d_2sm(&p.mapA[0], mapa_rank(smem_u32(&a_full[slot]), lead_rank), smem_a + slot * A_STAGE, kc * 64, x0,
-                              y0, b0);
-              ++ga;
-            }
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::B_STAGE);
-            tma_load_4d_2sm(&p.mapB, mapa_rank(smem_u32(&full_bar[stage]), lead_rank), smem_b + stage * Cfg::B_STAGE, kc * 64,
-                            n0 + static_cast<int>(rank) * Cfg::BH, 0, 0);
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
-          continue;
-        }
+        int tap = 0, kc = 0;  // per-tap mainloop: (tap, channel chunk) of K block kb, advanced without a division
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE + Cfg::B_STAGE));
           const uint32_t bar = mapa_rank(smem_u32(&full_bar[stage]), lead_rank);
           if (TR) {
             // stage = (channel chunk kc, column tap kx): one (bh+2)-row box + the weight tiles of taps (ky, kx), ky = 0..2
-            const int kc = kb / 3, kx = kb - kc * 3;
+            const int kx = tap;  // tap reuse: `tap` counts the column tap kx = 0..2 of channel chunk kc
             tma_load_4d_2sm(&p.mapA[0], bar, smem_a + stage * A_STAGE, kc * 64, x0 + kx - 1, y0 - 1, b0);
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
@@ -217,18 +190,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
               stage = 0;
               phase ^= 1;
             }
+            if (++tap == 3) {
+              tap = 0;
+              ++kc;
+            }
             continue;
           }
-          const int tap = kb / p.kchunks;
-          const int kc = kb - tap * p.kchunks;
-          if (CL == 2) {
-            tma_load_4d_2sm(&p.mapA[p.tap_map[tap]], bar, smem_a + stage * A_STAGE, kc * 64, x0 + p.tap_dx[tap],
-                            y0 + p.tap_dy[tap], b0);
-          } else if (pair_id == 0) {
-            // one L2 read feeds CTA `rank` of both pairs; each pair's leader barrier gets the bytes
-            tma_load_4d_2sm_mc(&p.mapA[p.tap_map[tap]], bar, smem_a + stage * A_STAGE, kc * 64, x0 + p.tap_dx[tap],
-                               y0 + p.tap_dy[tap], b0, static_cast<uint16_t>(0x5u << rank));
-          }
+          tma_load_4d_2sm(&p.mapA[p.tap_map[tap]], bar, smem_a + stage * A_STAGE, kc * 64, x0 + p.tap_dx[tap],
+                          y0 + p.tap_dy[tap], b0);
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub)
             tma_load_4d_2sm(&p.mapB, bar, smem_b + stage * Cfg::B_STAGE + sub * Cfg::B_SUB, kb * 64,
@@ -237,6 +206,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
+          }
+          if (++kc == p.kchunks) {
+            kc = 0;
+            ++tap;
           }
         }
       }
@@ -247,35 +220,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
       constexpr uint32_t idesc = make_idesc_f16(256, BN);
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t ga_base = 0;  // A-stationary: first activation chunk of the current M pair
       int t;
       for (int it = 0; tile_index(it, t); ++it) {
         const int a = it % NBUF;
         mbar_wait(&tmem_empty[a], ((it / NBUF) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + a * Cfg::ACC_COLS;
-        if (AS) {
-          const int nidx = t % n_groups;
-          for (int kc = 0; kc < p.kchunks; ++kc) {
-            const uint32_t g = ga_base + kc, slot = g % NA;
-            if (nidx == 0) mbar_wait(&a_full[slot], (g / NA) & 1);
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint64_t da = make_desc_k_sw128(smem_u32(smem_a + slot * A_STAGE));
-            const uint64_t db = make_desc_k_sw128(smem_u32(smem_b + stage * Cfg::B_STAGE));
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_ss_2cta(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
-            umma_commit_2cta(&empty_bar[stage], 0b11);
-            if (nidx == n_groups - 1) umma_commit_2cta(&a_empty[slot], 0b11);  // last N tile of this M pair
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
-          if (nidx == n_groups - 1) ga_base += p.kchunks;
-          umma_commit_2cta(&tmem_full[a], 0b11);
-          continue;
-        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -301,14 +251,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
                                  (kb | k) != 0 ? 1u : 0u);
             }
           }
-          // frees this pair's stage; pair 1 additionally releases pair 0's (whose producer also fills pair 1's A)
-          umma_commit_2cta(&empty_bar[stage], CL == 2 ? 0b11 : (pair_id == 0 ? 0b0011 : 0b1111));
+          umma_commit_2cta(&empty_bar[stage], 0b11);  // frees the stage in both CTAs
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2cta(&tmem_full[a], static_cast<uint16_t>(0b11u << (2 * pair_id)));
+        umma_commit_2cta(&tmem_full[a], 0b11);
       }
     }
   } else if (warp == 2) {
@@ -330,20 +279,22 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
         }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // =========================== epilogue (both CTAs, own 128 rows) ==================
+    if (EW == 4) reg_alloc<G2_REGS_EPI>();
     EpiTmaState est;
     int t;
     for (int it = 0; tile_index(it, t); ++it) {
       int x0, y0, b0, n0;
       tile_coords(t, x0, y0, b0, n0);
       const int a = it % NBUF;
-      // the two warps of a lane quarter interleave 32-column chunks: twice the loads / stores in flight
-      if (NSUB == 1 && p.epi_tma) {
-        gemm_epilogue_tma<BN>(p, tmem_base + a * Cfg::ACC_COLS, warp, lane, x0, y0, b0, n0, &tmem_full[a], (it / NBUF) & 1,
-                              (warp - 4) >> 2, epi_stage + (warp - 4) * 4096,
-                              reinterpret_cast<float*>(epi_bias + (warp - 4) * 1024), res_ring, res_full, res_empty, est);
-      } else {
+      // the EW warps of a lane quarter interleave 32-column chunks: EW times the loads / stores / math in flight
+      if (EW == 4 || (NSUB == 1 && p.epi_tma)) {
+        gemm_epilogue_tma<BN, EW>(p, tmem_base + a * Cfg::ACC_COLS, warp, lane, x0, y0, b0, n0, &tmem_full[a], (it / NBUF) & 1,
+                                  (warp - 4) >> 2, epi_stage + (warp - 4) * (EW == 4 ? 2048 : 4096),
+                                  reinterpret_cast<float*>(epi_bias + (warp - 4) * 1024), res_ring, res_full, res_empty, est);
+      } else if (EW == 2) {
 #pragma unroll
         for (int sub = 0; sub < NSUB; ++sub)
           gemm_epilogue<BN>(p, tmem_base + a * Cfg::ACC_COLS + sub * BN, warp, lane, x0, y0, b0, n0 + sub * BN,
@@ -364,116 +315,45 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(G2_THREADS, 1)
   }
 }
 
-template <int BN, int NSUB, int CL, int TR = 0>
-static int set_attr2() {
-  SDW_CUDA_OK(cudaFuncSetAttribute(gemm2_tc_kernel<BN, NSUB, CL, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Gemm2Cfg<BN, NSUB, TR>::SMEM_BYTES));
-  return 0;
-}
-
-static int g_max_clusters4 = 0;
-int gemm2_max_clusters4() { return g_max_clusters4; }
-
-static bool g_init2 = false;
-int gemm2_init() {
-  if (g_init2) return 0;
-  if (int e = set_attr2<128, 1, 2>()) return e;
-  if (int e = set_attr2<160, 1, 2>()) return e;
-  if (int e = set_attr2<192, 1, 2>()) return e;
-  if (int e = set_attr2<256, 1, 2>()) return e;
-  if (int e = set_attr2<160, 2, 2>()) return e;
-  if (int e = set_attr2<160, 1, 4>()) return e;
-  if (int e = set_attr2<256, 1, 4>()) return e;
-  if (int e = set_attr2<128, 1, 2, 1>()) return e;
-  if (int e = set_attr2<160, 1, 2, 1>()) return e;
-  if (int e = set_attr2<192, 1, 2, 1>()) return e;
-  if (int e = set_attr2<256, 1, 2, 1>()) return e;
-  if (int e = set_attr2<160, 2, 2, 1>()) return e;
-  {
-    // how many 4-CTA clusters of this kernel the device can hold at once (GPC boundaries strand some SMs)
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(148);
-    cfg.blockDim = dim3(G2_THREADS);
-    cfg.dynamicSmemBytes = Gemm2Cfg<256, 1>::SMEM_BYTES;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 4;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm2_tc_kernel<256, 1, 4>, &cfg) != cudaSuccess || n <= 0) {
-      (void)cudaGetLastError();
-      n = 32;
-    }
-    g_max_clusters4 = n;
+template <int BN, int NSUB, int EW, int TR>
+static int launch2(const GemmLaunch& l, cudaStream_t stream) {
+  static bool attr = false;
+  if (!attr) {
+    SDW_CUDA_OK(cudaFuncSetAttribute(gemm2_tc_kernel<BN, NSUB, EW, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Gemm2Cfg<BN, NSUB, TR>::SMEM_BYTES));
+    attr = true;
   }
-  g_init2 = true;
-  return 0;
-}
-
-int launch_gemm2(const GemmLaunch& l, cudaStream_t stream) {
-  if (int e = gemm2_init()) return e;
-  if (l.tr) {
-    if (l.cl != 2) {
-      set_error("tap reuse is a CTA-pair variant");
-      return 1;
-    }
-#define SDW_TR_CASE(BN_, NSUB_)                                                                                       \
-  SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<BN_, NSUB_, 2, 1>, l.grid, dim3(G2_THREADS), Gemm2Cfg<BN_, NSUB_, 1>::SMEM_BYTES, \
-                         stream, l.p))
-    if (l.nsub == 2 && l.bn == 160) SDW_TR_CASE(160, 2);
-    else if (l.nsub == 1 && l.bn == 128) SDW_TR_CASE(128, 1);
-    else if (l.nsub == 1 && l.bn == 160) SDW_TR_CASE(160, 1);
-    else if (l.nsub == 1 && l.bn == 192) SDW_TR_CASE(192, 1);
-    else if (l.nsub == 1 && l.bn == 256) SDW_TR_CASE(256, 1);
-    else {
-      set_error("bad BLOCK_N / nsub for the tap-reuse kernel");
-      return 1;
-    }
-#undef SDW_TR_CASE
-    return 0;
-  }
-  if (l.cl == 4) {
-    if (l.nsub != 1 || (l.bn != 160 && l.bn != 256)) {
-      set_error("the 4-CTA cluster variant exists for BLOCK_N = 160 / 256, one accumulator");
-      return 1;
-    }
-    if (l.bn == 160)
-      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<160, 1, 4>, l.grid, dim3(G2_THREADS), Gemm2Cfg<160, 1>::SMEM_BYTES, stream, l.p));
-    else
-      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<256, 1, 4>, l.grid, dim3(G2_THREADS), Gemm2Cfg<256, 1>::SMEM_BYTES, stream, l.p));
-    return 0;
-  }
-  if (l.nsub == 2) {
-    if (l.bn != 160) {
-      set_error("the two-accumulator variant exists for BLOCK_N = 160 only");
-      return 1;
-    }
-    SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<160, 2, 2>, l.grid, dim3(G2_THREADS), Gemm2Cfg<160, 2>::SMEM_BYTES, stream, l.p));
-    SDW_CUDA_OK(cudaGetLastError());
-    return 0;
-  }
-  switch (l.bn) {
-    case 128:
-      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<128, 1, 2>, l.grid, dim3(G2_THREADS), Gemm2Cfg<128, 1>::SMEM_BYTES, stream, l.p));
-      break;
-    case 160:
-      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<160, 1, 2>, l.grid, dim3(G2_THREADS), Gemm2Cfg<160, 1>::SMEM_BYTES, stream, l.p));
-      break;
-    case 192:
-      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<192, 1, 2>, l.grid, dim3(G2_THREADS), Gemm2Cfg<192, 1>::SMEM_BYTES, stream, l.p));
-      break;
-    case 256:
-      SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<256, 1, 2>, l.grid, dim3(G2_THREADS), Gemm2Cfg<256, 1>::SMEM_BYTES, stream, l.p));
-      break;
-    default:
-      set_error("bad BLOCK_N for the 2-CTA kernel");
-      return 1;
-  }
+  SDW_CUDA_OK(launch_pdl(gemm2_tc_kernel<BN, NSUB, EW, TR>, l.grid, dim3(G2Threads<EW>::value),
+                         Gemm2Cfg<BN, NSUB, TR>::SMEM_BYTES, stream, l.p));
   SDW_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int gemm2_init() { return 0; }
+
+// instantiations: BLOCK_N 128 / 160 / 192 / 256 x {per-tap, tap reuse} with one accumulator, 160 x 2 accumulators; the
+// wide epilogue (EW = 4) for the per-tap kernels with one accumulator (the short-K linears / 1x1 convs)
+int launch_gemm2(const GemmLaunch& l, cudaStream_t stream) {
+  const int key = l.bn * 1000 + l.nsub * 100 + l.ew * 10 + (l.tr ? 1 : 0);
+  switch (key) {
+    case 128120: return launch2<128, 1, 2, 0>(l, stream);
+    case 160120: return launch2<160, 1, 2, 0>(l, stream);
+    case 192120: return launch2<192, 1, 2, 0>(l, stream);
+    case 256120: return launch2<256, 1, 2, 0>(l, stream);
+    case 128140: return launch2<128, 1, 4, 0>(l, stream);
+    case 160140: return launch2<160, 1, 4, 0>(l, stream);
+    case 192140: return launch2<192, 1, 4, 0>(l, stream);
+    case 256140: return launch2<256, 1, 4, 0>(l, stream);
+    case 160220: return launch2<160, 2, 2, 0>(l, stream);
+    case 128121: return launch2<128, 1, 2, 1>(l, stream);
+    case 160121: return launch2<160, 1, 2, 1>(l, stream);
+    case 192121: return launch2<192, 1, 2, 1>(l, stream);
+    case 256121: return launch2<256, 1, 2, 1>(l, stream);
+    case 160221: return launch2<160, 2, 2, 1>(l, stream);
+    default: break;
+  }
+  set_error("no CTA-pair kernel for this BLOCK_N / accumulators / epilogue width / tap reuse combination");
+  return 1;
 }
 
 }  // namespace sdw

@@ -268,9 +268,9 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, uint32_t tme
                                               int chunk0 = 0, int chunk_step = 1, uint8_t* stage = nullptr) {
   const int quarter = warp & 3;  // TMEM lane quarter this warp may read
   const int r = quarter * 32 + lane;
-  const int lx = r % p.bw;
-  const int ly = (r / p.bw) % p.bh;
-  const int lb = r / (p.bw * p.bh);
+  const int lx = r & (p.bw - 1);  // bw, bh, bb are powers of two
+  const int ly = (r >> p.lg_bw) & (p.bh - 1);
+  const int lb = r >> (p.lg_bw + p.lg_bh);
   const int x = x0 + lx, y = y0 + ly, b = b0 + lb;
   const bool row_ok = (x < p.W) && (y < p.H) && (b < p.B);
   const int64_t pix_in = (static_cast<int64_t>(b) * p.H + y) * p.W + x;  // lattice-linear index
@@ -364,7 +364,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, uint32_t tme
 // 8.6 us per 256 x 160 tile against a 1.7 us operand-ingest floor).  Here
 //   * the bias slice of the tile is copied to shared memory once per tile (before the accumulator is awaited),
 //   * the residual tile arrives in a 4-deep ring of [128 rows x 32 columns] chunks filled by TMA from a producer
-//     thread that runs ahead across tiles (consumers: the 4 warps that own this chunk's parity),
+//     thread that runs ahead across tiles (consumers: the 4 warps — one per lane quarter — that own this chunk),
 //   * each warp writes its 32-row x 32-column output slab to shared memory (64B-swizzled, conflict-free) and one lane
 //     hands it to a TMA store; rows / columns outside the tensor are clipped by the tensor map.
 // State carried across tiles: `res_chunk` (ring position at tile start) and `nstore` (output double-buffer position).
@@ -374,7 +374,10 @@ struct EpiTmaState {
   uint32_t nstore = 0;
 };
 
-template <int BN>
+// EW = warps per TMEM lane quarter (2 or 4); warp `cpar` of a quarter takes the 32-column chunks c = cpar, cpar + EW, ...
+// EW = 2: two output slabs per warp (the store of chunk i overlaps the math of chunk i + 1); EW = 4: one slab per warp
+// (a warp has one or two chunks per tile; the overlap comes from the other three warps of its quarter).
+template <int BN, int EW>
 __device__ __forceinline__ void gemm_epilogue_tma(const GemmKParams& p, uint32_t tmem_acc, int warp, int lane, int x0,
                                                   int y0, int b0, int n0, uint64_t* tmem_full_bar, uint32_t full_parity,
                                                   int cpar, uint8_t* out_stage, float* bias_s, const uint8_t* res_ring,
@@ -400,7 +403,7 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKParams& p, uint32_t
   __syncwarp();
   // this warp's 32-row slab of the tile in lattice coordinates
   const int row0 = quarter * 32;
-  const int sx = x0 + row0 % p.bw, sy = y0 + (row0 / p.bw) % p.bh, sb = b0 + row0 / (p.bw * p.bh);
+  const int sx = x0 + (row0 & (p.bw - 1)), sy = y0 + ((row0 >> p.lg_bw) & (p.bh - 1)), sb = b0 + (row0 >> (p.lg_bw + p.lg_bh));
   const int sw = (lane >> 1) & 3;  // 64B-swizzle phase of this thread's row (slab and ring bases are 512B aligned)
 
   mbar_wait(tmem_full_bar, full_parity);
@@ -411,9 +414,9 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKParams& p, uint32_t
   if (geglu) {
     const uint64_t alpha_h = pk2(0.5f * p.alpha, 0.5f * p.alpha);
 #pragma unroll 1
-    for (int c = cpar; c * 64 < nmax; c += 2) {
-      uint8_t* ob = out_stage + (st.nstore & 1) * 2048;
-      if (lane == 0) bulk_wait_group_read<1>();  // the slab written two stores ago has left shared memory
+    for (int c = cpar; c * 64 < nmax; c += EW) {
+      uint8_t* ob = out_stage + (EW == 2 ? (st.nstore & 1) * 2048 : 0);
+      if (lane == 0) bulk_wait_group_read<EW == 2 ? 1 : 0>();  // the slab about to be overwritten has left shared memory
       __syncwarp();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -456,9 +459,9 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKParams& p, uint32_t
   const bool silu = p.act == 1;
   const bool vt_mode = p.mode == GEMM_QKV_VT;
 #pragma unroll 1
-  for (int c = cpar; c < nch; c += 2) {
-    uint8_t* ob = out_stage + (st.nstore & 1) * 2048;
-    if (lane == 0) bulk_wait_group_read<1>();
+  for (int c = cpar; c < nch; c += EW) {
+    uint8_t* ob = out_stage + (EW == 2 ? (st.nstore & 1) * 2048 : 0);
+    if (lane == 0) bulk_wait_group_read<EW == 2 ? 1 : 0>();
     __syncwarp();
     if (vt_mode && n0 + c * 32 >= p.vt_col0) {
       // V columns leave transposed: slab[row = column of this chunk][token = lane] (32 x 64 B, unswizzled), one TMA

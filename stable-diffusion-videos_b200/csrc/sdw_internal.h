@@ -72,6 +72,11 @@ struct alignas(64) GemmKParams {
   int W, H, B;              // tile-grid domain (the A lattice extents)
   int bw, bh, bb;           // M tile = bw*bh*bb = 128 lattice points
   int tiles_w, tiles_h;     // tiles per (w,h); tiles along b = gridDim.x / (tiles_w*tiles_h)
+  // 2-CTA kernel: tile coordinates without integer divisions (7 per tile per warp used to be a quarter of the epilogue's
+  // instruction stream on short-K GEMMs: profiles/r02_ncu_epilogue_shortk.md).  bw, bh, bb are powers of two (shifts);
+  // n_groups, tiles_w, tiles_w * tiles_h go through q = umulhi(n, ceil(2^32 / d)), exact for n * d < 2^32 (planner-checked)
+  int lg_bw, lg_bh;
+  uint32_t mg_ng, mg_tw, mg_twh;  // 0 = divisor 1
   int N;                    // GEMM N (packed columns)
   int b_batched;            // 1: weight map coords (.., y0, b0) = lattice (h, b) (batched matmul)
   int stage_stores;         // 1: bounce output chunks through shared memory for coalesced stores (wide-N GEMMs)
@@ -84,10 +89,6 @@ struct alignas(64) GemmKParams {
   CUtensorMap mapVt;        // GEMM_QKV_VT: V^T as (token, head * d + dd, sample), box (32 tokens, 32 rows), no swizzle
   int epi_tma;
   int nstages;              // mainloop pipeline depth (what the epilogue buffers leave of the 227 KB)
-  // A-stationary mainloop (short-K linears with several N tiles): a cluster keeps the activation rows of ONE M pair
-  // resident ((kchunks + 1) slots of 128 x 64) and walks all N tiles of it, so only weights stream through the ring
-  int a_stationary;
-  int a_slots;
   // epilogue
   const float* bias;        // [N] or null
   const float* rowvec;      // [B][rowvec_ld] per-sample vector added per column (time-embedding proj) or null
@@ -112,7 +113,7 @@ struct GemmLaunch {
   int bn;   // BLOCK_N variant
   int ver;  // 1: one 128xBN tile per CTA (sdw_gemm.cu); 2: persistent CTA pairs, 256xBN tiles (sdw_gemm2.cu)
   int nsub = 1;  // ver 2: accumulators per activation tile (2 -> 256 x 2*BN tiles, single-buffered TMEM)
-  int cl = 2;    // ver 2: cluster size (4 -> two CTA pairs share each activation tile via TMA multicast)
+  int ew = 2;    // ver 2: epilogue warps per TMEM lane quarter (4 -> the 640-thread kernel for epilogue-bound short-K GEMMs)
   int tr = 0;    // ver 2: 1 -> tap-reuse mainloop (3x3 stride-1 convs; GemmKParams::tap_reuse)
 };
 
@@ -148,17 +149,15 @@ struct GemmDesc {
   int bn = 0;   // 0 = auto
   int ver = 0;  // 0 = auto, 1 / 2 force a kernel version
   int nsub = 0; // 0 = auto, 1 / 2: accumulators per activation tile in the 2-CTA kernel
-  int cl = 0;   // 0 = auto, 2 / 4: cluster size of the 2-CTA kernel
+  int ew = 0;   // 0 = auto, 2 / 4: epilogue warps per TMEM lane quarter in the 2-CTA kernel (4 needs the TMA epilogue)
   int tr = 0;   // 0 = auto, 1 = never, 2 = require the tap-reuse mainloop (3x3 stride-1 conv, W % 16 == 0, H % 8 == 0)
   int et = 0;   // 0 = auto, 1 = never, 2 = require the TMA epilogue
-  int as = 0;   // 0 = auto, 1 = never, 2 = require the A-stationary mainloop
 };
 
 int plan_gemm(const GemmDesc& d, GemmLaunch* out);
 int launch_gemm(const GemmLaunch& l, cudaStream_t stream);
 int launch_gemm2(const GemmLaunch& l, cudaStream_t stream);
 int gemm2_init();
-int gemm2_max_clusters4();
 void set_plan_only(bool on);
 int gemm_init();  // resolves the driver entry point, sets smem attributes
 // shared-memory budget of the 2-CTA kernel (sdw_gemm2.cu): barriers, then the operand ring, then the epilogue buffers
@@ -166,8 +165,8 @@ constexpr int G2_SMEM_DYN = 227 * 1024;                    // requested dynamic 
 constexpr int G2_SMEM_USABLE = G2_SMEM_DYN - 1024;         // after the 1 KB alignment slack
 constexpr int G2_BAR_BYTES = 1024;
 constexpr int G2_EPI_OLD = 8 * 2048;                       // 2 KB store-coalescing buffer per epilogue warp
-constexpr int G2_EPI_OUT = 8 * 2 * 2048;                   // TMA epilogue: two 32-row x 64-byte output slabs per warp
-constexpr int G2_EPI_BIAS = 8 * 1024;                      //   per-warp bias copy (<= 256 fp32 columns)
+constexpr int G2_EPI_OUT = 8 * 2 * 2048;                   // TMA epilogue: 32-row x 64-byte output slabs, two per warp (8 warps) or one (16)
+constexpr int G2_EPI_BIAS = 8 * 1024;                      //   per-warp bias copy (<= 256 fp32 columns); twice that for 16 warps
 constexpr int G2_RES_STAGES = 4, G2_RES_STAGE = 128 * 64;  //   residual ring: [128 rows x 32 columns] fp16 chunks
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                const uint32_t* box, int swizzle_bytes = 128);

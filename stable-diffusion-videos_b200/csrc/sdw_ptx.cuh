@@ -326,6 +326,15 @@ __device__ __forceinline__ float gelu_fast_f(float g) {
   return 0.5f * g * (1.f + copysignf(erf_abs, g));
 }
 // packed fp32x2 math (sm_100a FFMA2 / FMUL2 / FADD2): one issue slot for two values
+// register re-balancing between warpgroups (all warps of a warpgroup execute it)
+template <int REGS>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+// n / d for a divisor known at plan time: magic = ceil(2^32 / d) (0 encodes d = 1); exact while n * d < 2^32
+__device__ __forceinline__ int fast_div(int n, uint32_t magic) {
+  return magic ? static_cast<int>(__umulhi(static_cast<uint32_t>(n), magic)) : n;
+}
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));

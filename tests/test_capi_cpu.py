@@ -114,10 +114,10 @@ def test_launch_plans_validate_without_a_gpu():
         lib.sdw_debug_plan_only(0)
 
 
-@pytest.mark.parametrize("toggle", ["SDW_GEMM_AS=1", "SDW_EPI_TMA=0", "SDW_EPI_TMA=2", "SDW_GEMM_TR=0", "SDW_GEMM_CL=4",
+@pytest.mark.parametrize("toggle", ["SDW_GEMM_EW=2", "SDW_EPI_TMA=0", "SDW_EPI_TMA=2", "SDW_GEMM_TR=0",
                                     "SDW_GN_FUSED=1", "SDW_NO_FLASH=1"])
 def test_launch_plans_validate_under_every_opt_in_switch(toggle):
-    """the opt-in kernel variants (A-stationary mainloop, classic epilogue, per-tap conv loads, 4-CTA clusters, ...) must
+    """the kernel A/B switches (8-warp epilogue everywhere, classic epilogue, per-tap conv loads, ...) must
     plan the full SD-1.4 engine too: shared-memory budgets, tensor-map alignment, stage counts (plan-only, no GPU)."""
     import os
     import subprocess

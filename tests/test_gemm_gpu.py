@@ -21,7 +21,7 @@ def _tol(ref):
     return float(ref.abs().max()) * 2.0 ** -9 + 1e-3
 
 
-def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None, ver=0, nsub=0, cl=0, tr=0, et=0, out_buf=None, out_c0=0, as_=0):
+def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn=0, mode=0, N_out=None, ver=0, nsub=0, ew=0, tr=0, et=0, out_buf=None, out_c0=0):
     """x: [B,H,W,C] fp16 cuda; returns NHWC fp16 output computed by the native kernel."""
     n = _native()
     B, H, W, Cc = x_nhwc.shape
@@ -63,10 +63,9 @@ def run_conv(x_nhwc, w_oihw, conv, bias=None, rowvec=None, resid=None, act=0, bn
         d.bn = bn
         d.ver = ver
         d.nsub = nsub
-        d.cl = cl
+        d.ew = ew
         d.tr = tr
         d.et = et
-        d.as_ = as_
         n.gemm(d)
     torch.cuda.synchronize()
     return out
@@ -312,26 +311,6 @@ def test_gemm_2cta_two_accumulators(B, H, W, Cc, N, conv):
     assert err <= _tol(ref), (err, _tol(ref))
 
 
-# ---- 4-CTA clusters: the activation tile is TMA-multicast to two CTA pairs working on neighbouring N tiles -------------
-@pytest.mark.parametrize("B,H,W,Cc,N,conv,bn", [(4, 64, 64, 320, 320, 1, 160), (2, 32, 32, 640, 640, 1, 160),
-                                                 (2, 16, 16, 128, 1280, 1, 256), (1, 8, 8, 64, 480, 1, 160),
-                                                 (2, 64, 64, 64, 320, 2, 160), (2, 16, 16, 64, 640, 3, 160),
-                                                 (1, 1, 5000, 1280, 960, 0, 160), (8, 64, 64, 320, 2560, 0, 256),
-                                                 (1, 1, 300, 64, 768, 0, 256)])
-def test_gemm_4cta_cluster_multicast(B, H, W, Cc, N, conv, bn):
-    x = _rand(B, H, W, Cc, seed=61)
-    k = 3 if conv else 1
-    w = _rand(N, Cc, k, k, scale=(k * k * Cc) ** -0.5, seed=62)
-    bias = _rand(N, seed=63).float()
-    oh, ow = (H // 2, W // 2) if conv == 2 else ((2 * H, 2 * W) if conv == 3 else (H, W))
-    resid = _rand(B, oh, ow, N, seed=64)
-    out = run_conv(x, w, conv, bias=bias, resid=resid, ver=2, bn=bn, nsub=1, cl=4)
-    ref = ref_conv(x, w if conv else w.reshape(N, Cc), conv, bias=bias, resid=resid)
-    assert torch.isfinite(out.float()).all()
-    err = (out.float() - ref).abs().max().item()
-    assert err <= _tol(ref), (err, _tol(ref))
-
-
 # ---- tap reuse: one 10-row activation box per (channel chunk, kx) feeds the three ky taps of a 3x3 stride-1 conv ---------
 @pytest.mark.parametrize("B,H,W,Cc,N,bn,nsub", [(4, 64, 64, 320, 320, 160, 1), (4, 64, 64, 320, 320, 160, 2),
                                                  (2, 32, 32, 640, 640, 256, 1), (2, 16, 16, 128, 1280, 256, 1),
@@ -451,16 +430,19 @@ def test_qkv_vt_tma_epilogue(Bn, Ntok, Cc, heads, et):
     assert torch.isfinite(vt.float()).all()
 
 
-# ---- A-stationary mainloop: the activation rows of an M pair stay in shared memory across all of its N tiles ---------------
+# ---- epilogue width: 2 or 4 warps per TMEM lane quarter (the 640-thread kernel of the short-K GEMMs) --------------------
+@pytest.mark.parametrize("ew", [2, 4])
 @pytest.mark.parametrize("T,Cc,N,bn,mode,res", [
     (20000, 320, 960, 256, 0, False),     # QKV-like, 4 N tiles, ragged last M pair
-    (19200, 320, 2560, 256, 1, False),    # GEGLU
-    (24000, 320, 640, 160, 0, True),      # residual ring + 4 N tiles
+    (19200, 320, 2560, 256, 1, False),    # GEGLU: one 64-column chunk per warp and tile
+    (24000, 320, 640, 160, 0, True),      # residual ring, five 32-column chunks over four warps
     (19000, 64, 512, 128, 0, True),       # one K chunk
-    (19000, 448, 480, 160, 0, False),     # seven K chunks (eight slots)
-    (40000, 320, 960, 0, 0, True),        # several M pairs per cluster (slot ring wraps), auto BLOCK_N
+    (19000, 448, 480, 160, 0, False),     # seven K chunks, ragged last N tile (480 = 3 x 160)
+    (40000, 320, 960, 0, 0, True),        # several tiles per cluster, auto BLOCK_N
+    (9000, 1280, 320, 192, 0, True),      # ff.out-like: 20 K blocks
+    (300, 320, 320, 160, 0, True),        # fewer tiles than clusters
 ])
-def test_gemm_a_stationary(T, Cc, N, bn, mode, res):
+def test_gemm_epilogue_width(T, Cc, N, bn, mode, res, ew):
     x = _rand(1, 1, T, Cc, seed=95)
     w = _rand(N, Cc, scale=Cc ** -0.5, seed=96)
     bias = _rand(N, seed=97).float()
@@ -470,12 +452,12 @@ def test_gemm_a_stationary(T, Cc, N, bn, mode, res):
         blk = torch.arange(N, device="cuda")
         b64, within = blk // 64, blk % 64
         src = torch.where(within < 32, b64 * 32 + within, ncols + b64 * 32 + within - 32)
-        out = run_conv(x, w, 0, bias=bias[src].contiguous(), mode=1, ver=2, bn=bn, as_=2)
+        out = run_conv(x, w, 0, bias=bias[src].contiguous(), mode=1, ver=2, bn=bn, et=2, ew=ew)
         h = x.float().reshape(T, Cc) @ w.float().t() + bias
         a, g = h.chunk(2, dim=-1)
         ref = (a * Fn.gelu(g)).reshape(1, 1, T, ncols)
     else:
-        out = run_conv(x, w.reshape(N, Cc, 1, 1), 0, bias=bias, resid=resid, ver=2, bn=bn, as_=2)
+        out = run_conv(x, w.reshape(N, Cc, 1, 1), 0, bias=bias, resid=resid, ver=2, bn=bn, et=2, ew=ew)
         ref = ref_conv(x, w, 0, bias=bias, resid=resid)
     assert torch.isfinite(out.float()).all()
     err = (out.float() - ref).abs().max().item()

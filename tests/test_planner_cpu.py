@@ -41,7 +41,7 @@ def _plan(n, B, H, W, Cc, N, conv, mode=0, resid=True, rowvec_ld=None, **kw):
         setattr(d, k, v)
     out = (C.c_int32 * 12)()
     n.check(n.lib().sdw_debug_plan(C.byref(d), out))
-    keys = ("ver", "bn", "nsub", "cl", "tr", "epi_tma", "nstages", "a_stationary", "grid", "bw", "bh", "bb")
+    keys = ("ver", "bn", "nsub", "ew", "tr", "epi_tma", "nstages", "reserved", "grid", "bw", "bh", "bb")
     return dict(zip(keys, list(out)))
 
 
@@ -84,7 +84,7 @@ def test_shared_memory_budget_bounds_the_pipeline_depth(native):
         p = _plan(native, 32, hw, hw, c, nn, conv, mode=mode, resid=resid)
         a = 20480 if p["tr"] else 16384
         b = (3 if p["tr"] else 1) * p["nsub"] * (p["bn"] // 2) * 128
-        epi = (32768 + 8192 + (32768 if resid else 0)) if p["epi_tma"] else 16384
+        epi = (32768 + (16384 if p["ew"] == 4 else 8192) + (32768 if resid else 0)) if p["epi_tma"] else 16384
         assert 2 <= p["nstages"] <= 8 and p["nstages"] * (a + b) + epi + 1024 <= 227 * 1024 - 1024, p
 
 
@@ -92,9 +92,13 @@ def test_opt_in_variants_are_refused_outside_their_domain(native):
     with pytest.raises(native.SdwError):
         _plan(native, 32, 8, 8, 1280, 1280, 1, tr=2)          # tap reuse needs W % 16 == 0
     with pytest.raises(native.SdwError):
-        _plan(native, 1, 1, 4096, 320, 320, 0, **{"as_": 2})   # A-stationary needs >= 3 N tiles and >= 74 M pairs
-    p = _plan(native, 1, 1, 131072, 320, 2560, 0, mode=1, resid=False, **{"as_": 2})
-    assert p["a_stationary"] == 1 and p["grid"] == 148, p
+        _plan(native, 32, 64, 64, 320, 320, 1, ew=4)           # the 16-warp epilogue belongs to the per-tap kernels
+    p = _plan(native, 1, 1, 131072, 320, 2560, 0, mode=1, resid=False, ew=4)
+    assert p["ew"] == 4 and p["epi_tma"] == 1 and p["grid"] == 148, p
+    p = _plan(native, 1, 1, 131072, 320, 2560, 0, mode=1, resid=False)      # short K: chosen automatically
+    assert p["ew"] == 4, p
+    p = _plan(native, 1, 1, 131072, 320, 2560, 0, mode=1, resid=False, ew=2)
+    assert p["ew"] == 2, p
 
 
 def _attn(n, B, Nq, Nk, heads, d):

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stable_diffusion_videos_b200 import _native as n  # noqa: E402
 
 
-def bench(T, C, N, mode=0, bias=True, resid=False, iters=20, bn=0, et=0, as_=0):
+def bench(T, C, N, mode=0, bias=True, resid=False, iters=20, bn=0, et=0, ew=0):
     x = torch.randn(T, C, device="cuda").half()
     w = (torch.randn(N, C, 1, 1, device="cuda") * C ** -0.5).half()
     wp = n.pack_weight(w, geglu=(mode == 1))
@@ -20,7 +20,7 @@ def bench(T, C, N, mode=0, bias=True, resid=False, iters=20, bn=0, et=0, as_=0):
     d.sW = C
     d.Wt = wp.data_ptr(); d.N = N
     d.out = out.data_ptr(); d.ldc = ncols
-    d.alpha = 1.0; d.mode = mode; d.bn = bn; d.et = et; d.as_ = as_
+    d.alpha = 1.0; d.mode = mode; d.bn = bn; d.et = et; d.ew = ew
     keep = []
     if bias:
         b = torch.randn(N, device="cuda"); keep.append(b); d.bias = b.data_ptr()
@@ -58,12 +58,9 @@ if __name__ == "__main__":
         if only is not None and int(only) != i:
             continue
         et_env = int(os.environ.get("ET", "0"))
-        as_mode = os.environ.get("AS")
-        variants = ((0, et_env, 0),) if only is not None else ((0, 1, 1), (0, 2, 1), (128, 2, 1), (160, 2, 1), (256, 2, 1))
-        if as_mode:  # A-stationary vs default on the shapes where it applies (K <= 448, >= 3 N tiles)
-            variants = ((0, 2, 1), (0, 2, 2), (160, 2, 2), (256, 2, 2)) if c <= 448 and nn >= 640 and t >= 74 * 256 else ((0, 2, 1),)
-        for bn, et, as_ in variants:
-            if mode == 1 and bn == 160:
-                continue
-            ms, tf, gbs = bench(t, c, nn, mode, bias, resid, iters=iters, bn=bn, et=et, as_=as_)
-            print(f"{name:34s} bn={bn or 'auto':>4} et={et} as={as_} {ms*1e3:8.1f} us {tf:7.1f} TFLOP/s {gbs:7.1f} GB/s algorithmic", flush=True)
+        ew_env = int(os.environ.get("EW", "0"))
+        # ONLY=<i>: one variant (ncu target); otherwise the epilogue-width A/B (8 vs 16 epilogue warps) at auto BLOCK_N
+        variants = ((0, et_env, ew_env),) if only is not None else ((0, 2, 2), (0, 2, 4))
+        for bn, et, ew in variants:
+            ms, tf, gbs = bench(t, c, nn, mode, bias, resid, iters=iters, bn=bn, et=et, ew=ew)
+            print(f"{name:34s} bn={bn or 'auto':>4} et={et} ew={ew} {ms*1e3:8.1f} us {tf:7.1f} TFLOP/s {gbs:7.1f} GB/s algorithmic", flush=True)

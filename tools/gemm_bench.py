@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from stable_diffusion_videos_b200 import _native as n  # noqa: E402
 
 
-def bench(B, H, W, C, N, conv, iters=20, bn=0, ver=0, epi=False, nsub=0, cl=0, tr=0):
+def bench(B, H, W, C, N, conv, iters=20, bn=0, ver=0, epi=False, nsub=0, tr=0):
     x = torch.randn(B, H, W, C, device="cuda").half()
     k = 3 if conv else 1
     w = (torch.randn(N, C, k, k, device="cuda") * (C * k * k) ** -0.5).half()
@@ -21,7 +21,7 @@ def bench(B, H, W, C, N, conv, iters=20, bn=0, ver=0, epi=False, nsub=0, cl=0, t
     d.conv = 1 if conv else 0
     d.Wt = wp.data_ptr(); d.N = N
     d.out = out.data_ptr(); d.ldc = N
-    d.alpha = 1.0; d.bn = bn; d.ver = ver; d.nsub = nsub; d.cl = cl; d.tr = tr
+    d.alpha = 1.0; d.bn = bn; d.ver = ver; d.nsub = nsub; d.tr = tr
     if epi:  # bias + residual epilogue, as the ResBlock conv2 / attention out-projections run
         bias = torch.randn(N, device="cuda")
         resid = torch.randn(B, H, W, N, device="cuda").half()
@@ -58,12 +58,12 @@ if __name__ == "__main__":
     ]
     for name, B, H, W, C, N, conv in shapes:
         for ver in ((1, 2) if os.environ.get('BOTH') else (2,)):
-            variants = ((0, 0, 0, 0), (160, 1, 2, 1), (256, 1, 2, 1))
+            variants = ((0, 0, 0), (160, 1, 1), (256, 1, 1))
             if conv and W % 16 == 0 and H % 8 == 0:  # tr: 1 = per-tap activation tiles, 2 = tap-reuse mainloop
-                variants = ((0, 0, 0, 0), (0, 0, 0, 1), (128, 1, 2, 1), (128, 1, 2, 2), (160, 1, 2, 1), (160, 1, 2, 2), (192, 1, 2, 2),
-                            (256, 1, 2, 1), (256, 1, 2, 2), (160, 2, 2, 1), (160, 2, 2, 2))
-            for bn, nsub, cl, tr in variants:
+                variants = ((0, 0, 0), (0, 0, 1), (128, 1, 1), (128, 1, 2), (160, 1, 1), (160, 1, 2), (192, 1, 2),
+                            (256, 1, 1), (256, 1, 2), (160, 2, 1), (160, 2, 2))
+            for bn, nsub, tr in variants:
                 for epi in (True,):
-                    ms, tf = bench(B, H, W, C, N, conv, bn=bn, ver=ver, epi=epi, nsub=nsub, cl=cl, tr=tr)
-                    print(f"{name:36s} B={B:3d} v{ver} bn={bn or 'auto':>4} nsub={nsub} cl={cl} tr={tr} "
+                    ms, tf = bench(B, H, W, C, N, conv, bn=bn, ver=ver, epi=epi, nsub=nsub, tr=tr)
+                    print(f"{name:36s} B={B:3d} v{ver} bn={bn or 'auto':>4} nsub={nsub} tr={tr} "
                           f"epi={'bias+res' if epi else 'none':8s} {ms*1e3:9.1f} us {tf:8.1f} TFLOP/s", flush=True)
