@@ -257,6 +257,24 @@ int sdw_clip_missing_params(const sdw_clip* e, const char** first_missing);
  * out: device fp16 [B][max_positions][hidden] = last_hidden_state after the final LayerNorm */
 int sdw_clip_forward(sdw_clip* e, const int32_t* ids, int B, void* out_f16, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Frame-sharded walk over the GPUs of one box (one process per GPU): the three exchanges of the path, as thin NCCL
+ * wrappers (NCCL bound at run time with dlopen; no collective exists inside the sampler — frames are independent).
+ * Replaces what the reference's Flax twin does with replicate / shard / unshard
+ * (flax_stable_diffusion_pipeline.py:546, 568-578, 594-597, 898-902, 935).
+ *   rank 0: sdw_nccl_unique_id(id) -> the 128 bytes travel to every rank by the host's own means (torch.distributed
+ *   object broadcast in parallel.py) -> every rank: sdw_nccl_init(id, rank, world) with its CUDA device current.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sdw_comm sdw_comm;
+int sdw_nccl_unique_id(void* id128);
+int sdw_nccl_init(const void* id128, int rank, int world, sdw_comm** out);
+void sdw_nccl_destroy(sdw_comm* c);
+/* in place: `root`'s bytes reach every rank (the flat fp16 weight buffer, once per pipeline) */
+int sdw_nccl_broadcast_weights(sdw_comm* c, void* buf, uint64_t bytes, int root, void* stream);
+/* every rank sends `bytes_per_rank` bytes (its padded uint8 frame block); `root` receives [world][bytes_per_rank] in
+ * `recv` (ignored elsewhere): one grouped ncclSend / ncclRecv round over NVLink */
+int sdw_nccl_gather_frames(sdw_comm* c, const void* send, void* recv, uint64_t bytes_per_rank, int root, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

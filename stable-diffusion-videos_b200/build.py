@@ -52,7 +52,7 @@ def build(verbose=False):
         print(log)
     if any(l for _, l in res) or not os.path.exists(OUT) or any(os.path.getmtime(o) > os.path.getmtime(OUT) for o in objs):
         r = subprocess.run([NVCC, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-                            "-lcudart"], capture_output=True, text=True)
+                            "-lcudart", "-ldl"], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(os.path.join(HERE, "build", "ptxas.log"), "a") as f:

@@ -16,8 +16,11 @@
 //   2^8), P written back to tensor memory as fp16 pairs and O += P V issued as a TS-mode MMA.  The two warpgroups share each
 //   scheduler's MUFU pipe (one ex2 per score, 16 / clk / SM — the bound of this kernel at head dim 40), so one tile's
 //   exponentials fill the other's TMEM-load / row-max / barrier gaps.  Registers are re-balanced with setmaxnreg (softmax
-//   224, rest 48).  Self-attention 64x64, d = 40, batch 60: 2528 us against 2991 us for the one-tile kernel (1.41x the
-//   exponential floor; profiles/r02_attn_ab_matrix.txt).
+//   224, rest 48), and one exponential pair in four is evaluated on the FMA pipe (Cody-Waite + degree-3 polynomial), which
+//   takes a quarter of the load off the MUFU.  Self-attention 64x64, d = 40, batch 60: 2249 us (0.33 of the burst tensor
+//   peak, 1.26x the all-MUFU exponential floor) against 2383 us with every exponential on the MUFU and 2991 us for the
+//   one-tile kernel (profiles/r02_attn_ab_matrix.txt, r02_attn_softmax_loop_ab_same_box.txt).  Single-KV-tile (cross)
+//   attention with >= 2 query tiles runs here too (155.6 vs 193.1 us at 64x64, 77 keys).
 //
 // attn_fwd_kernel  (everything else: single-KV-tile cross attention with a query-tile loop, head dims 80 / 160)
 //   One CTA = one 128-query tile of one (b, h) (several tiles in turn when all keys fit one KV tile):
@@ -84,7 +87,10 @@ __device__ __forceinline__ void ex2_poly2(float t0, float t1, float& e0, float& 
 // Variants of this kernel that were built, measured on a B200 and removed again (evidence: profiles/r02_attn_*.txt,
 // DESIGN.md §4): two softmax threads per query row (four warps per scheduler: 2941 vs 2633 us at batch 60), a token that
 // makes the MUFU bursts of the two query tiles alternate (2558 vs 2528 us), a double-buffered-score version with BKV = 96
-// and P written in place (3411 us), exponentials partly on the FMA pipe on top of it (3449 / 3720 us).
+// and P written in place (3411 us), exponentials partly on the FMA pipe on top of it (3449 / 3720 us); on the shipped
+// two-tile kernel, same box, cycles under ncu (profiles/r02_attn_softmax_loop_ab_same_box.txt): the row max fused into
+// the exponential pass (4.69 M vs 4.43 M cycles) and PV_{j-1} awaited only after the first chunk's exponentials (4.57 M).
+// What did pay: one exponential pair in four as a degree-3 polynomial on the FMA pipe (4.18 M cycles, 2249 us).
 template <int DVP>
 struct PPCfg {
   static constexpr int ST = 4;                       // K / V^T ring depth
@@ -104,11 +110,10 @@ struct PPCfg {
 
 // TRACE: compile the clock64 stamps in (tools/attn_trace.py); the shipped instantiation carries no trace code — with the
 // stamps merely predicated off the kernel was 8 % slower
-template <int DVP, int TRACE, int POLY, int MODE>
+template <int DVP, int TRACE, int POLY>
 __global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = PPCfg<DVP>;
   constexpr int ST = Cfg::ST, BKV = 128;
-  constexpr bool FUSE = (MODE & 1) != 0, LATE = (MODE & 2) != 0;  // A/B switches of the softmax loop (launch_pp)
   constexpr int NCH = BKV / 32;                     // 32-column chunks of a score row
   constexpr uint32_t GROUP = 128;                   // softmax threads per query tile
   extern __shared__ uint8_t smem_raw[];
@@ -273,10 +278,9 @@ __global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const _
           for (int i = 0; i < BKV; ++i)
             if (kv0 + i >= p.Nk) v[i >> 5][i & 31] = 0xff800000u;  // -inf
         }
-        // ---- row max by an explicit pass: always for tile 0 of a work item (it sets the reference); for every tile when
-        //      the max is not fused into the exponential pass (FUSE = 0) -------------------------------------------
-        bool pv_waited = (j == 0);  // tile 0: the epilogue of the previous work item has waited for its last PV
-        if (!FUSE || j == 0) {
+        // ---- row max, lazy reference update ------------------------------------------------------
+        float m_t;
+        {
           float mx[NCH];
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
@@ -288,99 +292,22 @@ __global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const _
             }
             mx[c] = fmaxf(a0, a1);
           }
-          float m_t = mx[0];
+          m_t = mx[0];
 #pragma unroll
           for (int c = 1; c < NCH; ++c) m_t = fmaxf(m_t, mx[c]);
-          if (j == 0) {
-            m_ref = m_t;
-          } else if (__any_sync(0xffffffffu, (m_t - m_ref) * sl2 > LAZY_LOG2)) {
-            // exact online-softmax step for this warp's rows: new reference, O and l rescaled (rare after the first tiles)
-            const float m_new = fmaxf(m_ref, m_t);
-            const float alpha = ex2f((m_ref - m_new) * sl2);
-            m_ref = m_new;
-            l_run *= alpha;
-            mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has completed: O is stable, the P columns are free
-            tc_fence_after();
-            pv_waited = true;
-#pragma unroll
-            for (int c = 0; c < DVP / 16; ++c) {
-              uint32_t o[16];
-              tmem_ld_32x16(t_o + c * 16, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_32x16(t_o + c * 16, o);
-            }
-            tmem_st_wait();
-          }
         }
-        if (trace) ts3 = clock64();
-        if (!LATE && !pv_waited) {
-          mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has read P_{j-1}: the P columns may be overwritten, O is stable
-          tc_fence_after();
-          pv_waited = true;
-        }
-        // ---- exponentials against the REFERENCE max; P -> tensor memory chunk by chunk.  FUSE: the row max is taken on
-        //      the fly instead of by a separate pass — the scores stay in registers, so the (rare, warp-uniform) case of
-        //      a row max more than 2^8 above its reference re-runs the pass after the exact online-softmax correction ---
-        float sum_t;
-#pragma unroll 1
-        for (int attempt = 0; attempt < 2; ++attempt) {
-          const float mb = m_ref * sl2;
-          const uint64_t sl2_2 = pk2(sl2, sl2), nmb_2 = pk2(-mb, -mb);
-          uint64_t sm2[4] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
-          float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            uint32_t pkc[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float x0 = __uint_as_float(v[c][i]), x1 = __uint_as_float(v[c][i + 1]);
-              const float x2 = __uint_as_float(v[c][i + 2]), x3 = __uint_as_float(v[c][i + 3]);
-              if (FUSE) {
-                mx0 = fmaxf(fmaxf(mx0, x0), x1);  // one 3-input FMNMX per pair
-                mx1 = fmaxf(fmaxf(mx1, x2), x3);
-              }
-              float t0, t1, t2, t3, e0, e1, e2, e3;
-              upk2(fma2(pk2(x0, x1), sl2_2, nmb_2), t0, t1);
-              upk2(fma2(pk2(x2, x3), sl2_2, nmb_2), t2, t3);
-              e0 = ex2f(t0);
-              e1 = ex2f(t1);
-              if (POLY && ((i >> 2) % POLY) == POLY - 1) {
-                ex2_poly2(t2, t3, e2, e3);  // this pair on the FMA pipe
-              } else {
-                e2 = ex2f(t2);
-                e3 = ex2f(t3);
-              }
-              sm2[(i >> 1) & 3] = add2(sm2[(i >> 1) & 3], pk2(e0, e1));
-              sm2[((i >> 1) + 1) & 3] = add2(sm2[((i >> 1) + 1) & 3], pk2(e2, e3));
-              pkc[i >> 1] = pack_h2(e0, e1);
-              pkc[(i >> 1) + 1] = pack_h2(e2, e3);
-            }
-            if (LATE && c == 0 && !pv_waited) {
-              // PV_{j-1} has read P_{j-1} and O is stable — waited for only after the first chunk's exponentials
-              mbar_wait(&pv_done[X], (gt - 1) & 1);
-              tc_fence_after();
-              pv_waited = true;
-            }
-            tmem_st_32x16(t_p + c * 16, pkc);  // row = lane, column k = keys (2k, 2k+1) as an fp16 pair (TS-mode A layout)
-          }
-          {
-            float s0, s1, s2, s3, s4, s5, s6, s7;
-            upk2(sm2[0], s0, s1);
-            upk2(sm2[1], s2, s3);
-            upk2(sm2[2], s4, s5);
-            upk2(sm2[3], s6, s7);
-            sum_t = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
-          }
-          const float m_t = fmaxf(mx0, mx1);
-          if (!FUSE || j == 0 || attempt == 1 || !__any_sync(0xffffffffu, (m_t - m_ref) * sl2 > LAZY_LOG2)) break;
-          // exact online-softmax step for this warp's rows: new reference, O and l rescaled, then the pass again
+        bool pv_waited = (j == 0);  // tile 0: the epilogue of the previous work item has waited for its last PV
+        if (j == 0) {
+          m_ref = m_t;
+        } else if (__any_sync(0xffffffffu, (m_t - m_ref) * sl2 > LAZY_LOG2)) {
+          // exact online-softmax step for this warp's rows: new reference, O and l rescaled (rare after the first tiles)
           const float m_new = fmaxf(m_ref, m_t);
           const float alpha = ex2f((m_ref - m_new) * sl2);
           m_ref = m_new;
           l_run *= alpha;
-          tmem_st_wait();
+          mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has completed: O is stable, the P columns are free
+          tc_fence_after();
+          pv_waited = true;
 #pragma unroll
           for (int c = 0; c < DVP / 16; ++c) {
             uint32_t o[16];
@@ -390,6 +317,50 @@ __global__ void __launch_bounds__(PPCfg<DVP>::THREADS, 1) attn_pp_kernel(const _
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tmem_st_32x16(t_o + c * 16, o);
           }
+          tmem_st_wait();
+        }
+        if (trace) ts3 = clock64();
+        // ---- exponentials against the reference max, P -> tensor memory chunk by chunk.  One pair in four goes through
+        //      the FMA pipe (POLY = 4): same box, batch 60: 4.18 M cycles against 4.43 M with every exponential on the
+        //      MUFU (profiles/r02_attn_softmax_loop_ab_same_box.txt) -------------------------------------------------
+        const float mb = m_ref * sl2;
+        const uint64_t sl2_2 = pk2(sl2, sl2), nmb_2 = pk2(-mb, -mb);
+        uint64_t sm2[4] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
+        if (!pv_waited) {
+          mbar_wait(&pv_done[X], (gt - 1) & 1);  // PV_{j-1} has read P_{j-1}: the P columns may be overwritten
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t pkc[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float t0, t1, t2, t3, e0, e1, e2, e3;
+            upk2(fma2(pk2(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])), sl2_2, nmb_2), t0, t1);
+            upk2(fma2(pk2(__uint_as_float(v[c][i + 2]), __uint_as_float(v[c][i + 3])), sl2_2, nmb_2), t2, t3);
+            e0 = ex2f(t0);
+            e1 = ex2f(t1);
+            if (POLY && ((i >> 2) % POLY) == POLY - 1) {
+              ex2_poly2(t2, t3, e2, e3);  // this pair on the FMA pipe
+            } else {
+              e2 = ex2f(t2);
+              e3 = ex2f(t3);
+            }
+            sm2[(i >> 1) & 3] = add2(sm2[(i >> 1) & 3], pk2(e0, e1));
+            sm2[((i >> 1) + 1) & 3] = add2(sm2[((i >> 1) + 1) & 3], pk2(e2, e3));
+            pkc[i >> 1] = pack_h2(e0, e1);
+            pkc[(i >> 1) + 1] = pack_h2(e2, e3);
+          }
+          tmem_st_32x16(t_p + c * 16, pkc);  // row = lane, column k = keys (2k, 2k+1) as an fp16 pair (TS-mode A layout)
+        }
+        float sum_t;
+        {
+          float s0, s1, s2, s3, s4, s5, s6, s7;
+          upk2(sm2[0], s0, s1);
+          upk2(sm2[1], s2, s3);
+          upk2(sm2[2], s4, s5);
+          upk2(sm2[3], s6, s7);
+          sum_t = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
         }
         l_run += sum_t;
         tmem_st_wait();
@@ -842,17 +813,16 @@ static int attn_set_attr() {
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<DKA, DVP, BKV, ST, SB, PT>::SMEM));
   return 0;
 }
-// instantiations: the shipped configuration for every head-dim class; the A/B grid (POLY x MODE) for head dim 40 only
-template <int DVP, int TRACE, int POLY, int MODE>
+template <int DVP, int TRACE, int POLY>
 static cudaError_t pp_launch_one(const AttnKParams& p, dim3 grid, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_pp_kernel<DVP, TRACE, POLY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_pp_kernel<DVP, TRACE, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          PPCfg<DVP>::SMEM);
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  return launch_pdl(attn_pp_kernel<DVP, TRACE, POLY, MODE>, grid, dim3(PPCfg<DVP>::THREADS), PPCfg<DVP>::SMEM, stream, p);
+  return launch_pdl(attn_pp_kernel<DVP, TRACE, POLY>, grid, dim3(PPCfg<DVP>::THREADS), PPCfg<DVP>::SMEM, stream, p);
 }
 
 static bool g_attn_init = false;
@@ -877,8 +847,9 @@ static int variant_for(int d, int Nk, int Nq) {
   // SDW_ATTN_PP=0: the one-query-tile kernel everywhere (A/B measurements)
   static const bool pp = [] { const char* e = std::getenv("SDW_ATTN_PP"); return !(e && e[0] == '0'); }();
   const int cls = d <= 16 ? 0 : (d <= 32 ? 1 : (d <= 48 ? 2 : 3));
-  // SDW_ATTN_PP_CROSS=1: single-KV-tile (cross) attention through the two-tile kernel as well (A/B switch)
-  static const bool pp_cross = [] { const char* e = std::getenv("SDW_ATTN_PP_CROSS"); return e && e[0] == '1'; }();
+  // single-KV-tile (cross) attention with >= 2 query tiles goes through the two-tile kernel as well: 64x64, 77 keys,
+  // batch 60: 155.6 us against 193.1 us for the query-tile loop of attn_fwd_kernel (same box); SDW_ATTN_PP_CROSS=0 = A/B
+  static const bool pp_cross = [] { const char* e = std::getenv("SDW_ATTN_PP_CROSS"); return !(e && e[0] == '0'); }();
   if (d <= 64) return (pp && (Nk > 128 || (pp_cross && Nq >= 256))) ? 8 + cls : cls;
   return d <= 80 ? 4 : 5;
 }
@@ -962,34 +933,16 @@ static cudaError_t launch_fwd(const AttnLaunchImpl* I, cudaStream_t stream) {
   return launch_pdl(attn_fwd_kernel<DKA, DVP, BKV, ST, SB, PT>, I->grid, dim3(ATT_THREADS),
                     AttnCfg<DKA, DVP, BKV, ST, SB, PT>::SMEM, stream, I->p);
 }
-static constexpr int PP_POLY = 0, PP_MODE = 0;  // shipped softmax-loop configuration
+static constexpr int PP_POLY = 4;  // shipped: one exponential pair in four on the FMA pipe
 template <int DVP>
 static cudaError_t launch_pp(const AttnLaunchImpl* I, cudaStream_t stream) {
   AttnKParams p = I->p;
   p.dbg = g_attn_dbg;
-  if (DVP == 48) {
-    // A/B grid for the dominant shape (head dim 40): SDW_ATTN_POLY = 0 | 4 (share of exponentials on the FMA pipe),
-    // SDW_ATTN_MODE bit 0 = row max fused into the exponential pass, bit 1 = PV_{j-1} awaited after the first chunk
-    static const int poly = [] { const char* e = std::getenv("SDW_ATTN_POLY"); return e ? std::atoi(e) : PP_POLY; }();
-    static const int mode = [] { const char* e = std::getenv("SDW_ATTN_MODE"); return e ? std::atoi(e) : PP_MODE; }();
-    const int key = (p.dbg ? 100 : 0) + (poly == 4 ? 10 : 0) + (mode & 3);
-    switch (key) {
-      case 0: return pp_launch_one<48, 0, 0, 0>(p, I->grid, stream);
-      case 1: return pp_launch_one<48, 0, 0, 1>(p, I->grid, stream);
-      case 2: return pp_launch_one<48, 0, 0, 2>(p, I->grid, stream);
-      case 3: return pp_launch_one<48, 0, 0, 3>(p, I->grid, stream);
-      case 10: return pp_launch_one<48, 0, 4, 0>(p, I->grid, stream);
-      case 11: return pp_launch_one<48, 0, 4, 1>(p, I->grid, stream);
-      case 12: return pp_launch_one<48, 0, 4, 2>(p, I->grid, stream);
-      case 13: return pp_launch_one<48, 0, 4, 3>(p, I->grid, stream);
-      case 100: return pp_launch_one<48, 1, 0, 0>(p, I->grid, stream);
-      case 101: return pp_launch_one<48, 1, 0, 1>(p, I->grid, stream);
-      case 110: return pp_launch_one<48, 1, 4, 0>(p, I->grid, stream);
-      case 111: return pp_launch_one<48, 1, 4, 1>(p, I->grid, stream);
-      default: return pp_launch_one<48, 1, PP_POLY, PP_MODE>(p, I->grid, stream);
-    }
-  }
-  return pp_launch_one<DVP, 0, PP_POLY, PP_MODE>(p, I->grid, stream);
+  // SDW_ATTN_POLY=0: every exponential on the MUFU (the A/B leg of tools/attn_bench.py)
+  static const int poly = [] { const char* e = std::getenv("SDW_ATTN_POLY"); return e ? std::atoi(e) : PP_POLY; }();
+  if (p.dbg) return pp_launch_one<DVP, 1, PP_POLY>(p, I->grid, stream);
+  if (poly == 0) return pp_launch_one<DVP, 0, 0>(p, I->grid, stream);
+  return pp_launch_one<DVP, 0, PP_POLY>(p, I->grid, stream);
 }
 
 int launch_attention(const AttnLaunch& L, cudaStream_t stream) {

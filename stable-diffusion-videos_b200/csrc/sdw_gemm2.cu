@@ -35,7 +35,10 @@ namespace sdw {
 
 // warpgroup 0: producer, MMA, residual producer (+1 idle warp); then EW warpgroups of epilogue warps
 template <int EW> struct G2Threads { static constexpr int value = 128 + 128 * EW; };
-static constexpr int G2_REGS_ROLE = 56, G2_REGS_EPI = 112;  // EW = 4: 128 * 56 + 512 * 112 = 64512 registers
+// EW = 4: the CTA's register pool is what it was launched with, 640 threads x 96 = 61440 (setmaxnreg.inc blocks until the
+// pool has room — asking for 112 hung the kernel): 128 * 56 + 512 * 104 = 60416
+static constexpr int G2_REGS_ROLE = 56, G2_REGS_EPI = 104;
+static_assert(128 * G2_REGS_ROLE + 512 * G2_REGS_EPI <= 640 * 96, "setmaxnreg budget of the 640-thread kernel");
 static constexpr int G2_A_STAGE = 128 * 64 * 2;
 
 // NSUB = accumulators per activation tile: NSUB = 2 computes a 256 x (2*BN) tile per CTA pair — the A tile is pulled

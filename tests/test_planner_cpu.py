@@ -115,19 +115,20 @@ def test_attention_variants_for_the_sd14_head_dims(native):
     assert _attn(native, 32, 1024, 1024, 8, 80)["variant"] == 4
     assert _attn(native, 32, 256, 256, 8, 160)["variant"] == 5
     assert _attn(native, 16, 9216, 9216, 5, 64)["variant"] == 11   # SD-2.1, 96x96 latent
-    assert _attn(native, 32, 4096, 77, 8, 40)["variant"] == 2       # single KV tile: the one-tile kernel with a query loop
+    assert _attn(native, 32, 4096, 77, 8, 40)["variant"] == 10      # single KV tile, >= 2 query tiles: the two-tile kernel too
+    assert _attn(native, 32, 128, 77, 8, 40)["variant"] == 2        # one query tile: the one-tile kernel
     p = _attn(native, 32, 4096, 4096, 8, 40)
     assert (p["qt"], p["gx"], p["gy"], p["gz"]) == (2, 148, 1, 1)   # persistent: 148 CTAs over 32 * 8 * 16 work items
     p = _attn(native, 1, 576, 576, 5, 64)                           # fewer work items than SMs
     assert (p["gx"], p["gy"], p["gz"]) == (15, 1, 1)
 
 
-def test_cross_attention_loops_over_query_tiles(native):
-    p = _attn(native, 32, 4096, 77, 8, 40)     # all 77 keys in one KV tile: 8 query tiles per CTA, K / V^T loaded once
-    assert p["qt"] == 8 and p["gx"] == 4 and p["gx"] * p["qt"] * 128 == 4096
-    p = _attn(native, 2, 4096, 77, 8, 40)      # small batch: keep >= ~3 waves of CTAs rather than long loops
-    assert p["qt"] < 8 and p["gx"] * p["qt"] * 128 >= 4096
-    p = _attn(native, 32, 300, 77, 8, 40)      # ragged query count
-    assert p["gx"] * p["qt"] * 128 >= 300
+def test_cross_attention_plans(native):
+    p = _attn(native, 32, 1024, 77, 8, 80)     # head dim 80: BKV = 64, so 77 keys are two KV tiles — no query-tile loop
+    assert p["variant"] == 4 and p["qt"] == 1 and p["gx"] == 8
+    p = _attn(native, 32, 128, 77, 8, 40)      # one query tile: attn_fwd_kernel, all keys in one KV tile
+    assert p["variant"] == 2 and p["gx"] * p["qt"] * 128 >= 128
+    p = _attn(native, 32, 4096, 77, 8, 40)     # head dim 40: persistent two-tile kernel, one work item = 256 queries
+    assert (p["variant"], p["qt"], p["gx"]) == (10, 2, 148)
     with pytest.raises(native.SdwError):
         _attn(native, 1, 64, 64, 1, 512)        # the VAE's d = 512 goes through the unfused path
