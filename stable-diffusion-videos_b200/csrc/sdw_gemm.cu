@@ -474,17 +474,19 @@ int plan_gemm(const GemmDesc& d, GemmLaunch* L) {
     const int epi_bytes = p.epi_tma ? G2_EPI_OUT + G2_EPI_BIAS + (d.resid ? G2_RES_STAGES * G2_RES_STAGE : 0) : G2_EPI_OLD;
     p.nstages = std::min(8, (G2_SMEM_USABLE - G2_BAR_BYTES - epi_bytes) / (a_stage + b_stage));
     SDW_REQUIRE(p.nstages >= 2, "no room for a two-stage operand pipeline");
-    // epilogue width: four warps per TMEM lane quarter where the epilogue, not the MMA, sets the tile time — the per-tap
-    // kernels up to 24 K blocks (every transformer linear / 1x1 conv of the UNet; profiles/r02_ncu_epilogue_shortk.md).
-    // SDW_GEMM_EW=2 keeps the 8-warp epilogue everywhere (A/B)
+    // epilogue width: four warps per TMEM lane quarter where the epilogue, not the MMA, sets the tile time — K <= 448
+    // (the 64x64-level transformer linears, K = 320: GEGLU 434 -> 383 us, QKV-like 218 -> 161 us, out-projection 99 ->
+    // 88 us at batch 60, same box; from K = 640 on the MMA is the longer leg and the wider epilogue loses 2-10 %:
+    // profiles/r02_epilogue_width_ab_same_box.txt).  SDW_GEMM_EW=2 | 4: 8-warp epilogue everywhere / 16 wherever eligible
     {
       static const int ew_env = [] { const char* e = std::getenv("SDW_GEMM_EW"); return e ? std::atoi(e) : 0; }();
       const bool can4 = p.epi_tma && nsub == 1 && !reuse;
       if (d.ew == 4) SDW_REQUIRE(can4, "the 16-warp epilogue needs the TMA epilogue, one accumulator and the per-tap mainloop");
-      const int want4 = d.ew ? d.ew == 4 : (ew_env ? ew_env == 4 : kblocks <= 24);
+      const int want4 = d.ew ? d.ew == 4 : (ew_env ? ew_env == 4 : kblocks <= 7);
       L->ew = can4 && want4 ? 4 : 2;
-      if (L->ew == 4) {  // 16 per-warp bias copies instead of 8
-        p.nstages = std::min(8, (G2_SMEM_USABLE - G2_BAR_BYTES - epi_bytes - G2_EPI_BIAS) / (a_stage + b_stage));
+      if (L->ew == 4) {  // 16 per-warp bias copies instead of 8, eight residual ring slots instead of four
+        const int extra = G2_EPI_BIAS + (d.resid ? G2_RES_STAGES * G2_RES_STAGE : 0);
+        p.nstages = std::min(8, (G2_SMEM_USABLE - G2_BAR_BYTES - epi_bytes - extra) / (a_stage + b_stage));
         SDW_REQUIRE(p.nstages >= 2, "no room for a two-stage operand pipeline");
       }
     }

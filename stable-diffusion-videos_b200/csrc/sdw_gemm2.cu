@@ -83,9 +83,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2Threads<EW>::value
   uint64_t* empty_bar = full_bar + Cfg::MAX_STAGES;
   uint64_t* tmem_full = empty_bar + Cfg::MAX_STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;               // [2]  (leader's copy is the one in use)
-  uint64_t* res_full = tmem_empty + 2;                // [G2_RES_STAGES]  residual ring (TMA epilogue)
-  uint64_t* res_empty = res_full + G2_RES_STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty + G2_RES_STAGES);
+  uint64_t* res_full = tmem_empty + 2;                // [8]  residual ring (TMA epilogue): 2 * EW slots in use
+  uint64_t* res_empty = res_full + 8;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty + 8);
   uint8_t* smem_a = smem + G2_BAR_BYTES;
   uint8_t* smem_b = smem_a + STAGES * A_STAGE;
   // epilogue buffers.  classic: 2 KB per warp; TMA: output slabs (EW = 2: two 2 KB slabs per warp, EW = 4: one),
@@ -115,9 +115,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2Threads<EW>::value
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 8 * EW);  // 4 * EW epilogue warps x 2 CTAs
     }
-    for (int r = 0; r < G2_RES_STAGES; ++r) {
+    for (int r = 0; r < 2 * EW; ++r) {
       mbar_init(&res_full[r], 1);
-      mbar_init(&res_empty[r], 4);  // the four warps (one per TMEM lane quarter) that own the chunk's parity
+      mbar_init(&res_empty[r], 4);  // the four warps (one per TMEM lane quarter) of the chunk's group
     }
     if (p.epi_tma) {
       tma_prefetch_desc(&p.mapOut);
@@ -265,18 +265,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2Threads<EW>::value
     }
   } else if (warp == 2) {
     // =========================== residual producer (TMA epilogue, both CTAs) =========
-    // [128 rows x 32 columns] chunks of this CTA's residual tile, in the order the epilogue consumes them; runs ahead
-    // of the epilogue by up to G2_RES_STAGES chunks, across tile boundaries
+    // [128 rows x 32 columns] chunks of this CTA's residual tile, in chunk order; runs ahead of the epilogue by up to two
+    // chunks per chunk group (2 * EW slots), across tile boundaries
     if (NSUB == 1 && p.epi_tma && p.resid && lane == 0) {
-      uint32_t gc = 0;
+      uint32_t kq = 0;  // fills issued per chunk group, mod 4, two bits each
       int t;
       for (int i = 0; tile_index(i, t); ++i) {
         int x0, y0, b0, n0;
         tile_coords(t, x0, y0, b0, n0);
         const int nch = (max(0, min(BN, p.N - n0)) + 31) >> 5;
-        for (int c = 0; c < nch; ++c, ++gc) {
-          const uint32_t slot = gc % G2_RES_STAGES;
-          mbar_wait(&res_empty[slot], ((gc / G2_RES_STAGES) & 1) ^ 1);
+        for (int c = 0; c < nch; ++c) {
+          const uint32_t g = static_cast<uint32_t>(c) & (EW - 1);  // chunk group: slots {g, g + EW}, filled alternately
+          const uint32_t k = (kq >> (2 * g)) & 3u;
+          kq = (kq & ~(3u << (2 * g))) | (((k + 1) & 3u) << (2 * g));
+          const uint32_t slot = g + EW * (k & 1);
+          mbar_wait(&res_empty[slot], ((k >> 1) & 1) ^ 1);
           mbar_expect_tx(&res_full[slot], G2_RES_STAGE);
           tma_load_4d(&p.mapRes, &res_full[slot], res_ring + slot * G2_RES_STAGE, n0 + c * 32, x0, y0, b0);
         }

@@ -363,14 +363,14 @@ __device__ __forceinline__ void gemm_epilogue(const GemmKParams& p, uint32_t tme
 // instruction.  With five K blocks per tile that chain, not the MMA, set the tile time (profiles/r01_ncu_epilogue_shortk.md:
 // 8.6 us per 256 x 160 tile against a 1.7 us operand-ingest floor).  Here
 //   * the bias slice of the tile is copied to shared memory once per tile (before the accumulator is awaited),
-//   * the residual tile arrives in a 4-deep ring of [128 rows x 32 columns] chunks filled by TMA from a producer
-//     thread that runs ahead across tiles (consumers: the 4 warps — one per lane quarter — that own this chunk),
+//   * the residual tile arrives in [128 rows x 32 columns] chunks filled by TMA from a producer thread that runs ahead
+//     across tiles: two ring slots per chunk group c % EW (consumers: the 4 warps — one per lane quarter — of the group),
 //   * each warp writes its 32-row x 32-column output slab to shared memory (64B-swizzled, conflict-free) and one lane
 //     hands it to a TMA store; rows / columns outside the tensor are clipped by the tensor map.
-// State carried across tiles: `res_chunk` (ring position at tile start) and `nstore` (output double-buffer position).
+// State carried across tiles: `res_k` (residual chunks consumed = ring position of the warp's group) and `nstore` (output slab).
 // ---------------------------------------------------------------------------------------------
 struct EpiTmaState {
-  uint32_t res_chunk = 0;
+  uint32_t res_k = 0;   // residual chunks this warp has consumed (its group's ring position)
   uint32_t nstore = 0;
 };
 
@@ -490,9 +490,13 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKParams& p, uint32_t
     const uint8_t* rs = nullptr;
     uint32_t slot = 0;
     if (p.resid) {
-      const uint32_t gc = st.res_chunk + c;
-      slot = gc % G2_RES_STAGES;
-      mbar_wait(&res_full[slot], (gc / G2_RES_STAGES) & 1);
+      // the chunk group c % EW (= cpar) owns ring slots {cpar, cpar + EW}, filled alternately: every fill of a slot is
+      // consumed by the same four warps in order, so the one-bit phase parity cannot alias.  (A ring indexed by the
+      // global chunk count lets a group that skips revolutions mistake fill f - 2 of a slot for fill f: it hung the
+      // 16-warp epilogue with five chunks per tile.)
+      slot = cpar + EW * (st.res_k & 1);
+      mbar_wait(&res_full[slot], (st.res_k >> 1) & 1);
+      ++st.res_k;
       rs = res_ring + slot * G2_RES_STAGE + (row0 + lane) * 64;
     }
 #pragma unroll
@@ -538,7 +542,6 @@ __device__ __forceinline__ void gemm_epilogue_tma(const GemmKParams& p, uint32_t
     }
     ++st.nstore;
   }
-  st.res_chunk += nch;
 }
 
 }  // namespace sdw

@@ -167,7 +167,7 @@ constexpr int G2_BAR_BYTES = 1024;
 constexpr int G2_EPI_OLD = 8 * 2048;                       // 2 KB store-coalescing buffer per epilogue warp
 constexpr int G2_EPI_OUT = 8 * 2 * 2048;                   // TMA epilogue: 32-row x 64-byte output slabs, two per warp (8 warps) or one (16)
 constexpr int G2_EPI_BIAS = 8 * 1024;                      //   per-warp bias copy (<= 256 fp32 columns); twice that for 16 warps
-constexpr int G2_RES_STAGES = 4, G2_RES_STAGE = 128 * 64;  //   residual ring: [128 rows x 32 columns] fp16 chunks
+constexpr int G2_RES_STAGES = 4, G2_RES_STAGE = 128 * 64;  //   residual ring: [128 rows x 32 columns] fp16 chunks, 4 slots (8 with 16 epilogue warps)
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                const uint32_t* box, int swizzle_bytes = 128);
 

@@ -84,7 +84,7 @@ def test_shared_memory_budget_bounds_the_pipeline_depth(native):
         p = _plan(native, 32, hw, hw, c, nn, conv, mode=mode, resid=resid)
         a = 20480 if p["tr"] else 16384
         b = (3 if p["tr"] else 1) * p["nsub"] * (p["bn"] // 2) * 128
-        epi = (32768 + (16384 if p["ew"] == 4 else 8192) + (32768 if resid else 0)) if p["epi_tma"] else 16384
+        epi = ((32768 + 16384 + (65536 if resid else 0)) if p["ew"] == 4 else (32768 + 8192 + (32768 if resid else 0))) if p["epi_tma"] else 16384
         assert 2 <= p["nstages"] <= 8 and p["nstages"] * (a + b) + epi + 1024 <= 227 * 1024 - 1024, p
 
 
