@@ -393,7 +393,10 @@ def main():
         if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
     k_ach = kern["flop_per_launch"] / (kern["us_per_launch"] * 1e-6) / 1e12
     attn_tf = attn_flop / (attn_us * 1e-6) / 1e12
-    sm_hz = (clk["sm_mhz"] if clk and clk.get("sm_mhz") else 1850) * 1e6
+    # exponential floor of the attention kernel: one ex2 per score at 16 / clk / SM.  The kernel is timed ALONE (it then
+    # runs near the maximum SM clock, not at the power-capped clock of the sampler), so the floor is taken at sm_max_mhz —
+    # the smallest floor, i.e. xu_frac is a lower bound of how close the kernel is to it
+    sm_hz = (clk["sm_max_mhz"] if clk and clk.get("sm_max_mhz") else 1965) * 1e6
     xu_floor_us = attn_exps / (16.0 * 148 * sm_hz) * 1e6
     tr_attn, tr_conv = _traffic("attention_self_64x64_d40", 2 * F), _traffic("conv3x3_64x64_320", 2 * F)
     achieved_tf = value * FLOP_PER_FRAME["sd14"] / 1e12 / world
@@ -413,7 +416,8 @@ def main():
             "kernel_batch": 2 * F, "us_per_launch": attn_us,
             "xu_floor_us": xu_floor_us, "xu_frac": xu_floor_us / attn_us,
             "note": f"timed alone, L2 flushed between launches, vs {peak_src} burst fp16/bf16 peak; this kernel is bound by "
-                    "one MUFU.EX2 per score (16/clk/SM): xu_frac = exponential floor at the sampled SM clock / time",
+                    "one exponential per score (MUFU.EX2, 16/clk/SM; the kernel moves a quarter of them to the FMA pipe): "
+                    "xu_frac = all-MUFU exponential floor at the maximum SM clock / time",
             "conv3x3": {"kernel": kern["name"], "kernel_batch": kern["batch"], "us_per_launch": kern["us_per_launch"],
                         "bound": "tensor", "achieved": k_ach, "peak": burst_tf, "unit": "TFLOP/s", "frac": k_ach / burst_tf,
                         "traffic": tr_conv["bytes"], "traffic_source": tr_conv["source"]},
