@@ -346,27 +346,40 @@ struct Engine {
       emit([L](cudaStream_t st, int) { return launch_attention(*L, st); });
       return 0;
     }
+    // S is materialised for a CHUNK of samples at a time (<= unfused_chunk(...) samples: about 64 MB of scores, which the
+    // 126 MB L2 keeps resident between the QK^T GEMM, the row softmax and the PV GEMM) — not for the whole batch, which at
+    // 30 frames of the VAE's 4096-token mid-block attention was 1 GB written once and read twice
     const int64_t Nkp = (Nk + 7) / 8 * 8;
-    GemmDesc g;
-    g.A = q; g.C = d; g.W = Nq; g.H = heads; g.B = Bq;
-    g.sW = q_ld; g.sH = d; g.sB = static_cast<int64_t>(Nq) * q_ld;
-    g.Wt = k; g.N = Nk; g.ldb = k_ld; g.Kb = d;
-    g.b_batched = 1; g.sBh = d; g.sBb = static_cast<int64_t>(Nk) * k_ld;
-    g.out = S; g.ldc = Nkp;
-    g.o_sW = Nkp; g.o_sH = static_cast<int64_t>(Nq) * Nkp; g.o_sB = static_cast<int64_t>(heads) * Nq * Nkp;
-    g.alpha = 1.f / std::sqrt(static_cast<float>(d));
-    if (int e = emit_gemm(g)) return e;
-    __half* Sp = S;
-    const int64_t rows = static_cast<int64_t>(Bq) * heads * Nq;
-    emit([=](cudaStream_t st, int) { return softmax_rows(Sp, Nkp, rows, Nk, st); });
-    GemmDesc h;
-    h.A = S; h.C = Nk; h.W = Nq; h.H = heads; h.B = Bq;
-    h.sW = Nkp; h.sH = static_cast<int64_t>(Nq) * Nkp; h.sB = static_cast<int64_t>(heads) * Nq * Nkp;
-    h.Wt = vt; h.N = d; h.ldb = vt_ld; h.Kb = Nk;
-    h.b_batched = 1; h.sBh = static_cast<int64_t>(d) * vt_ld; h.sBb = static_cast<int64_t>(heads) * d * vt_ld;
-    h.out = out.p; h.ldc = out.ld;
-    h.o_sW = out.ld; h.o_sH = d; h.o_sB = static_cast<int64_t>(Nq) * out.ld;
-    return emit_gemm(h);
+    const int chunk = unfused_chunk(Bq, heads, Nq, Nkp);
+    for (int b0 = 0; b0 < Bq; b0 += chunk) {
+      const int nb = std::min(chunk, Bq - b0);
+      GemmDesc g;
+      g.A = q ? q + static_cast<int64_t>(b0) * Nq * q_ld : nullptr; g.C = d; g.W = Nq; g.H = heads; g.B = nb;
+      g.sW = q_ld; g.sH = d; g.sB = static_cast<int64_t>(Nq) * q_ld;
+      g.Wt = k ? k + static_cast<int64_t>(b0) * Nk * k_ld : nullptr; g.N = Nk; g.ldb = k_ld; g.Kb = d;
+      g.b_batched = 1; g.sBh = d; g.sBb = static_cast<int64_t>(Nk) * k_ld;
+      g.out = S; g.ldc = Nkp;
+      g.o_sW = Nkp; g.o_sH = static_cast<int64_t>(Nq) * Nkp; g.o_sB = static_cast<int64_t>(heads) * Nq * Nkp;
+      g.alpha = 1.f / std::sqrt(static_cast<float>(d));
+      if (int e = emit_gemm(g)) return e;
+      __half* Sp = S;
+      const int64_t rows = static_cast<int64_t>(nb) * heads * Nq;
+      emit([=](cudaStream_t st, int) { return softmax_rows(Sp, Nkp, rows, Nk, st); });
+      GemmDesc h;
+      h.A = S; h.C = Nk; h.W = Nq; h.H = heads; h.B = nb;
+      h.sW = Nkp; h.sH = static_cast<int64_t>(Nq) * Nkp; h.sB = static_cast<int64_t>(heads) * Nq * Nkp;
+      h.Wt = vt ? vt + static_cast<int64_t>(b0) * heads * d * vt_ld : nullptr; h.N = d; h.ldb = vt_ld; h.Kb = Nk;
+      h.b_batched = 1; h.sBh = static_cast<int64_t>(d) * vt_ld; h.sBb = static_cast<int64_t>(heads) * d * vt_ld;
+      h.out = out.p ? out.p + static_cast<int64_t>(b0) * Nq * out.ld : nullptr; h.ldc = out.ld;
+      h.o_sW = out.ld; h.o_sH = d; h.o_sB = static_cast<int64_t>(Nq) * out.ld;
+      if (int e = emit_gemm(h)) return e;
+    }
+    return 0;
+  }
+  // samples per chunk of the unfused attention: as many as fit ~64 MB of fp16 scores, at least one
+  static int unfused_chunk(int Bq, int heads, int64_t Nq, int64_t Nkp) {
+    const int64_t per_sample = static_cast<int64_t>(heads) * Nq * Nkp * 2;
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(Bq, (int64_t(64) << 20) / std::max<int64_t>(1, per_sample))));
   }
 
   // ---- model pieces ----------------------------------------------------------
@@ -761,9 +774,11 @@ struct Engine {
         const int hl = std::max(1, cfg.attention_heads[l]);
         if (use_flash && attn_supported(cfg.block_out_channels[l] / hl)) continue;
         const int64_t nl = static_cast<int64_t>(H >> l) * (W >> l);
-        unet_s = std::max(unet_s, static_cast<int64_t>(Bn) * hl * nl * ((nl + 7) / 8 * 8));
+        const int64_t nlp = (nl + 7) / 8 * 8;
+        unet_s = std::max(unet_s, static_cast<int64_t>(unfused_chunk(Bn, hl, nl, nlp)) * hl * nl * nlp);
       }
-      int64_t vae_s = static_cast<int64_t>(F) * n0 * ((n0 + 7) / 8 * 8);
+      const int64_t n0p = (n0 + 7) / 8 * 8;
+      int64_t vae_s = static_cast<int64_t>(unfused_chunk(F, 1, n0, n0p)) * n0 * n0p;  // a chunk of samples, not the batch
       S_elems = static_cast<size_t>(std::max(unet_s, vae_s));
       S = static_cast<__half*>(alloc(S_elems * 2));
     }

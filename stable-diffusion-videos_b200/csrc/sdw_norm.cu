@@ -26,11 +26,15 @@ static constexpr int GN_MAX_GROUPS = 64;
 // per-thread partials go to shared memory and are reduced in index order (bit-reproducible).
 __global__ void __launch_bounds__(256) gn_partial_det_kernel(const __half* __restrict__ x, int64_t ld, int C, int G,
                                                              int64_t P, int pix_per_chunk,
-                                                             float2* __restrict__ part) {
+                                                             float2* __restrict__ part, int rev) {
   extern __shared__ float sm[];  // [rows][C] sums then [rows][C] squares
   pdl_wait();
   pdl_launch_dependents();
-  const int b = blockIdx.y, chunk = blockIdx.x;
+  // blocks walk the tensor from its END when `rev` is set: the producing GEMM wrote it front to back, so the tail is what
+  // the 126 MB L2 still holds (a front-to-back read of a 157 MB tensor evicts every line just before it is needed); this
+  // pass then ends at the front, which is where gn_apply starts
+  const int b = rev ? static_cast<int>(gridDim.y) - 1 - static_cast<int>(blockIdx.y) : static_cast<int>(blockIdx.y);
+  const int chunk = rev ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
   const int cg = C / G;
   const int vecs = C / 8;
   const int rows = max(1, min(min(static_cast<int>(blockDim.x) / vecs, 16), 6144 / C));
@@ -366,6 +370,12 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const __half* __r
   }
 }
 
+// back-to-front block order of the statistics / LayerNorm passes (L2 reuse of the producer's output); SDW_NORM_REV=0 = A/B
+int norm_reverse() {
+  static const int v = [] { const char* e = std::getenv("SDW_NORM_REV"); return e ? std::atoi(e) : 1; }();
+  return v;
+}
+
 // chunks per sample: enough blocks to fill the machine (B * nchunks >= ~4 waves) while keeping >= 16 pixels each
 int gn_chunks(int64_t P, int B) {
   int64_t want = (148 * 7 + B - 1) / B;  // 7 blocks of the stats kernel fit an SM (30 KB of shared memory each)
@@ -425,7 +435,8 @@ int groupnorm(const __half* x, int64_t ldx, int B, int64_t P, int C, int G, cons
   const size_t smem = static_cast<size_t>(2) * rows * C * sizeof(float);
   SDW_REQUIRE(smem <= 48 * 1024, "GroupNorm: channel count too large for the stats kernel");
   float2* stats = partial_ws + static_cast<size_t>(B) * nchunks * G;
-  SDW_CUDA_OK(launch_pdl(gn_partial_det_kernel, dim3(nchunks, B), dim3(256), smem, stream, x, ldx, C, G, P, ppc, partial_ws));
+  SDW_CUDA_OK(launch_pdl(gn_partial_det_kernel, dim3(nchunks, B), dim3(256), smem, stream, x, ldx, C, G, P, ppc, partial_ws,
+                         norm_reverse()));
   const int BG = B * G;
   SDW_CUDA_OK(launch_pdl(gn_finalize_kernel, dim3((BG + 7) / 8), dim3(256), 0, stream, partial_ws, nchunks, G, BG,
                          static_cast<float>(P) * (C / G), eps, stats));
@@ -446,10 +457,13 @@ template <int MAXV, int R>  // 16-byte vectors per lane per row, rows per warp (
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int64_t ldx, int64_t rows,
                                                         int C, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
-                                                        __half* __restrict__ y, int64_t ldy) {
+                                                        __half* __restrict__ y, int64_t ldy, int rev) {
   pdl_wait();
   pdl_launch_dependents();
-  const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  // `rev`: blocks walk the rows from the END — the tail of the tensor is what the L2 still holds of the producing GEMM's
+  // output, and the consumer GEMM then finds the head of the normalised tensor (written last) in L2
+  const int64_t blk = rev ? static_cast<int64_t>(gridDim.x) - 1 - blockIdx.x : static_cast<int64_t>(blockIdx.x);
+  const int64_t row0 = (blk * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
   if (row0 >= rows) return;
   const int lane = threadIdx.x & 31;
   const int vecs = C / 8;
@@ -525,15 +539,16 @@ int layernorm(const __half* x, int64_t ldx, int64_t rows, int C, const float* ga
               __half* y, int64_t ldy, cudaStream_t stream) {
   SDW_REQUIRE(C % 8 == 0 && C <= 8 * 32 * 8, "LayerNorm: C % 8 == 0 and C <= 2048");
   const int vecs = C / 8;
+  const int rev = norm_reverse();
   if (vecs <= 64) {
     const unsigned blocks = static_cast<unsigned>((rows + 31) / 32);
-    SDW_CUDA_OK(launch_pdl(layernorm_kernel<2, 4>, dim3(blocks), dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, y, ldy));
+    SDW_CUDA_OK(launch_pdl(layernorm_kernel<2, 4>, dim3(blocks), dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, y, ldy, rev));
   } else if (vecs <= 160) {
     const unsigned blocks = static_cast<unsigned>((rows + 15) / 16);
-    SDW_CUDA_OK(launch_pdl(layernorm_kernel<5, 2>, dim3(blocks), dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, y, ldy));
+    SDW_CUDA_OK(launch_pdl(layernorm_kernel<5, 2>, dim3(blocks), dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, y, ldy, rev));
   } else {
     const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
-    SDW_CUDA_OK(launch_pdl(layernorm_kernel<8, 1>, dim3(blocks), dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, y, ldy));
+    SDW_CUDA_OK(launch_pdl(layernorm_kernel<8, 1>, dim3(blocks), dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, y, ldy, rev));
   }
   SDW_CUDA_OK(cudaGetLastError());
   return 0;
