@@ -217,7 +217,7 @@ int pack_weight_up4(const void* w, int N, int C, void* out, cudaStream_t stream)
 // ---------------------------------------------------------------------------
 int gn_chunks(int64_t P, int B);
 size_t gn_workspace_bytes(int B);
-int groupnorm_launches();  // kernels per GroupNorm (1 fused cluster kernel, or 3 with SDW_GN_FUSED=0)
+int groupnorm_launches();  // kernels per GroupNorm (partial statistics, finalize, apply)
 int groupnorm(const __half* x, int64_t ldx, int B, int64_t P, int C, int G, const float* gamma, const float* beta,
               float eps, int silu, __half* y, int64_t ldy, float2* partial_ws, cudaStream_t stream);
 int layernorm(const __half* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,

@@ -7,11 +7,9 @@
 #include "sdw_internal.h"
 #include "sdw_ptx.cuh"
 
-#include <cooperative_groups.h>
 #include <cstdlib>
 
 namespace sdw {
-namespace cg = cooperative_groups;
 
 // =============================================================================================
 // GroupNorm: three small deterministic kernels.
@@ -222,153 +220,9 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __half* __restri
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Fused GroupNorm: one thread-block cluster per sample (looping over samples), statistics and normalisation in ONE
-// launch.  Each CTA sums its pixel slice (same fixed-order arithmetic as gn_partial_det_kernel), the per-CTA partials
-// are exchanged through distributed shared memory and reduced in rank order by every CTA, and the slice is normalised
-// right away — while it is still in L2, because only (clusters in flight) x (one sample) of the tensor is live at a
-// time.  It drops one HBM read of the tensor and two launches, but MEASURED SLOWER than the three-kernel version
-// (64x64x320, batch 32: 130 us vs 82 us; VAE 512x512x128: 2.1 ms vs 0.82 ms — 18 clusters of 8 CTAs keep too few
-// loads in flight and 32 samples need two rounds), so it is opt-in: SDW_GN_FUSED=1.  Tests cover both.
-// ---------------------------------------------------------------------------------------------
-static constexpr int GNF_THREADS = 512;
-
-__global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const __half* __restrict__ x, int64_t ldx, int B, int C,
-                                                               int G, int64_t P, const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta, float eps, int silu,
-                                                               __half* __restrict__ y, int64_t ldy) {
-  extern __shared__ float sm[];  // [rows][C] sums, [rows][C] squares
-  __shared__ float2 s_part[GN_MAX_GROUPS];
-  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
-  cg::cluster_group cluster = cg::this_cluster();
-  const int cs = static_cast<int>(cluster.num_blocks());
-  const int rank = static_cast<int>(cluster.block_rank());
-  const int cluster_id = blockIdx.x / cs, nclusters = gridDim.x / cs;
-  pdl_wait();
-  pdl_launch_dependents();
-  const int cg_ = C / G;
-  const int vecs = C / 8;
-  const int rows = max(1, min(min(GNF_THREADS / vecs, 16), 6144 / C));
-  float* ssum = sm;
-  float* ssq = sm + rows * C;
-  const int64_t ppc = (P + cs - 1) / cs;
-  const int64_t p0 = min(P, static_cast<int64_t>(rank) * ppc), p1 = min(P, p0 + ppc);
-  const float count = static_cast<float>(P) * cg_;
-
-  for (int b = cluster_id; b < B; b += nclusters) {
-    const __half* xb = x + static_cast<int64_t>(b) * P * ldx;
-    __half* yb = y + static_cast<int64_t>(b) * P * ldy;
-    // ---- phase 1: per-channel sums over this CTA's pixels ----
-    for (int item = threadIdx.x; item < rows * vecs; item += blockDim.x) {
-      const int v = item % vecs, prow = item / vecs;
-      float s[8], q[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-      auto acc8 = [&](const uint4& u) {
-        const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(h[j]);
-          s[2 * j] += f.x;
-          q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
-          s[2 * j + 1] += f.y;
-          q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
-        }
-      };
-      int64_t p = p0 + prow;
-      for (; p + 3 * rows < p1; p += 4 * rows) {
-        uint4 u[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (p + k * rows) * ldx + v * 8);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc8(u[k]);
-      }
-      for (; p < p1; p += rows) acc8(*reinterpret_cast<const uint4*>(xb + p * ldx + v * 8));
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        ssum[prow * C + v * 8 + j] = s[j];
-        ssq[prow * C + v * 8 + j] = q[j];
-      }
-    }
-    __syncthreads();
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-      float a = 0.f, c = 0.f;
-      for (int r = 0; r < rows; ++r)
-        for (int j = 0; j < cg_; ++j) {
-          a += ssum[r * C + g * cg_ + j];
-          c += ssq[r * C + g * cg_ + j];
-        }
-      s_part[g] = make_float2(a, c);
-    }
-    cluster.sync();  // every CTA's partials are visible cluster-wide
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-      float a = 0.f, c = 0.f;
-      for (int r = 0; r < cs; ++r) {  // rank order: bit-reproducible
-        const float2 pr = *cluster.map_shared_rank(&s_part[g], r);
-        a += pr.x;
-        c += pr.y;
-      }
-      const float mean = a / count;
-      const float var = fmaxf(c / count - mean * mean, 0.f);
-      s_mean[g] = mean;
-      s_rstd[g] = rsqrtf(var + eps);
-    }
-    cluster.sync();  // peers are done reading s_part (it is rewritten for the next sample); s_mean / s_rstd visible
-    // ---- phase 2: normalise this CTA's pixels (they are still in L2) ----
-    const int64_t items = (p1 - p0) * vecs;
-    auto apply8 = [&](const uint4& u, int v, int64_t p) {
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h[j]);
-        o[2 * j] = f.x;
-        o[2 * j + 1] = f.y;
-      }
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      int g = (v * 8) / cg_;
-      int rem = v * 8 - g * cg_;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t = (o[j] - s_mean[g]) * s_rstd[g] * gg[j] + bb[j];
-        if (silu) t = __fdividef(t, 1.f + __expf(-t));
-        o[j] = t;
-        if (++rem == cg_) {
-          rem = 0;
-          ++g;
-        }
-      }
-      *reinterpret_cast<uint4*>(yb + p * ldy + v * 8) =
-          make_uint4(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]), pack_h2(o[4], o[5]), pack_h2(o[6], o[7]));
-    };
-    int64_t it = threadIdx.x;
-    for (; it + 3 * blockDim.x < items; it += 4 * blockDim.x) {
-      uint4 u[4];
-      int vv[4];
-      int64_t pp[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int64_t i2 = it + k * blockDim.x;
-        vv[k] = static_cast<int>(i2 % vecs);
-        pp[k] = p0 + i2 / vecs;
-        u[k] = *reinterpret_cast<const uint4*>(xb + pp[k] * ldx + vv[k] * 8);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) apply8(u[k], vv[k], pp[k]);
-    }
-    for (; it < items; it += blockDim.x) {
-      const int v = static_cast<int>(it % vecs);
-      const int64_t p = p0 + it / vecs;
-      apply8(*reinterpret_cast<const uint4*>(xb + p * ldx + v * 8), v, p);
-    }
-    __syncthreads();  // ssum / ssq / s_mean are rewritten by the next sample
-  }
-}
+// (A single-launch variant — one thread-block cluster per sample, statistics exchanged through distributed shared memory,
+//  the slice normalised while still in L2 — was built, measured slower (64x64x320, batch 32: 130 us vs 82 us; VAE
+//  512x512x128: 2.1 ms vs 0.82 ms: 18 clusters of 8 CTAs keep too few loads in flight) and removed.)
 
 // back-to-front block order of the statistics / LayerNorm passes (L2 reuse of the producer's output); SDW_NORM_REV=0 = A/B
 int norm_reverse() {
@@ -388,46 +242,12 @@ int gn_chunks(int64_t P, int B) {
 // workspace: partials [B][nchunks][G] float2 followed by stats [B][G] float2
 size_t gn_workspace_bytes(int B) { return (static_cast<size_t>(B) * GN_MAX_CHUNKS * GN_MAX_GROUPS + B * GN_MAX_GROUPS) * sizeof(float2); }
 
-static bool gn_fused_enabled() {
-  static const int fused_env = [] { const char* e = std::getenv("SDW_GN_FUSED"); return e ? std::atoi(e) : 0; }();
-  return fused_env != 0;
-}
-int groupnorm_launches() { return gn_fused_enabled() ? 1 : 3; }
+int groupnorm_launches() { return 3; }
 
 int groupnorm(const __half* x, int64_t ldx, int B, int64_t P, int C, int G, const float* gamma, const float* beta,
               float eps, int silu, __half* y, int64_t ldy, float2* partial_ws, cudaStream_t stream) {
   SDW_REQUIRE(C % 8 == 0 && C % G == 0 && G <= GN_MAX_GROUPS, "GroupNorm: C % 8, C % G, G <= 64");
   SDW_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0, "GroupNorm: row pitch must be a multiple of 8");
-  if (gn_fused_enabled()) {
-    // clusters of 8 CTAs, one sample per cluster at a time; at most 18 clusters (148 SMs) so that the live part of the
-    // tensor (clusters x one sample) stays L2-resident between the two phases
-    const int cs = P >= 8 * 16 ? 8 : (P >= 2 * 16 ? 2 : 1);
-    const int nclusters = std::min(B, 148 / cs);
-    const int vecs = C / 8;
-    const int rows = std::max(1, std::min(std::min(GNF_THREADS / vecs, 16), 6144 / C));
-    const size_t smem = static_cast<size_t>(2) * rows * C * sizeof(float);
-    SDW_REQUIRE(smem <= 48 * 1024, "GroupNorm: channel count too large for the stats pass");
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(nclusters * cs);
-    cfg.blockDim = dim3(GNF_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    int nattr = 1;
-    if (pdl_enabled()) {
-      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[1].val.programmaticStreamSerializationAllowed = 1;
-      nattr = 2;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = nattr;
-    SDW_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel, x, ldx, B, C, G, P, gamma, beta, eps, silu, y, ldy));
-    return 0;
-  }
   const int nchunks = gn_chunks(P, B);
   const int ppc = static_cast<int>((P + nchunks - 1) / nchunks);
   const int vecs = C / 8;
@@ -535,11 +355,119 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   }
 }
 
+// Streaming form: a fixed grid (a few blocks per SM) whose warps walk the row groups with a stride, the loads of group
+// i + 1 in flight while group i is reduced, normalised and stored — no block turnover, and the HBM pipe never drains
+// between a warp's load and store phases.
+template <int MAXV, int R>
+__global__ void __launch_bounds__(256, 2) layernorm_stream_kernel(const __half* __restrict__ x, int64_t ldx, int64_t rows,
+                                                               int C, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float eps,
+                                                               __half* __restrict__ y, int64_t ldy, int rev) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int vecs = C / 8;
+  const int64_t ngroups = (rows + R - 1) / R;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  const int64_t w0 = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  auto group_row0 = [&](int64_t g) { return (rev ? ngroups - 1 - g : g) * R; };
+  auto load = [&](uint4 (&u)[R][MAXV], int64_t g) {
+    const int64_t row0 = group_row0(g);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < vecs && row0 + r < rows) u[r][i] = *reinterpret_cast<const uint4*>(x + (row0 + r) * ldx + vi * 8);
+      }
+  };
+  auto process = [&](const uint4 (&u)[R][MAXV], int64_t g) {
+    const int64_t row0 = group_row0(g);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r;
+      if (row >= rows) break;  // warp-uniform
+      float v[MAXV][8];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < vecs) {
+          const __half2* h = reinterpret_cast<const __half2*>(&u[r][i]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            v[i][2 * j] = f.x;
+            v[i][2 * j + 1] = f.y;
+            sum += f.x + f.y;
+          }
+        }
+      }
+      sum = warp_sum(sum);
+      const float mean = sum / C;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < vecs) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = v[i][j] - mean;
+            sq = fmaf(d, d, sq);
+          }
+        }
+      }
+      sq = warp_sum(sq);
+      const float rstd = rsqrtf(sq / C + eps);
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < vecs) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8) + 1);
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
+          *reinterpret_cast<uint4*>(y + row * ldy + vi * 8) =
+              make_uint4(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]), pack_h2(o[4], o[5]), pack_h2(o[6], o[7]));
+        }
+      }
+    }
+  };
+  uint4 ua[R][MAXV], ub[R][MAXV];
+  int64_t g = w0;
+  if (g < ngroups) load(ua, g);
+#pragma unroll 1
+  while (g < ngroups) {
+    const int64_t g1 = g + nwarps;
+    if (g1 < ngroups) load(ub, g1);
+    process(ua, g);
+    if (g1 >= ngroups) break;
+    const int64_t g2 = g1 + nwarps;
+    if (g2 < ngroups) load(ua, g2);
+    process(ub, g1);
+    g = g2;
+  }
+}
+
 int layernorm(const __half* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
               __half* y, int64_t ldy, cudaStream_t stream) {
   SDW_REQUIRE(C % 8 == 0 && C <= 8 * 32 * 8, "LayerNorm: C % 8 == 0 and C <= 2048");
   const int vecs = C / 8;
   const int rev = norm_reverse();
+  // SDW_LN_STREAM=1: the streaming kernel (fixed grid, next group's loads in flight) for C <= 512 — A/B switch
+  static const int stream_env = [] { const char* e = std::getenv("SDW_LN_STREAM"); return e ? std::atoi(e) : 0; }();
+  if (stream_env && vecs <= 64 && rows >= 148 * 8 * 4 * 4) {
+    const int per_sm = stream_env >= 2 ? stream_env : 4;
+    SDW_CUDA_OK(launch_pdl(layernorm_stream_kernel<2, 4>, dim3(148 * per_sm), dim3(256), 0, stream, x, ldx, rows, C, gamma, beta,
+                           eps, y, ldy, rev));
+    SDW_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (vecs <= 64) {
     const unsigned blocks = static_cast<unsigned>((rows + 31) / 32);
     SDW_CUDA_OK(launch_pdl(layernorm_kernel<2, 4>, dim3(blocks), dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, y, ldy, rev));
