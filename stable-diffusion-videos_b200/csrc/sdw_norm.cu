@@ -355,103 +355,106 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
   }
 }
 
-// Streaming form: a fixed grid (a few blocks per SM) whose warps walk the row groups with a stride, the loads of group
-// i + 1 in flight while group i is reduced, normalised and stored — no block turnover, and the HBM pipe never drains
-// between a warp's load and store phases.
-template <int MAXV, int R>
-__global__ void __launch_bounds__(256, 2) layernorm_stream_kernel(const __half* __restrict__ x, int64_t ldx, int64_t rows,
-                                                               int C, const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta, float eps,
-                                                               __half* __restrict__ y, int64_t ldy, int rev) {
+// LayerNorm for C = 40 * LPR (320 / 640 / 1280: every width of the SD UNets): LPR lanes share a row, five 16-byte vectors
+// per lane, so all 32 lanes carry data (the generic kernel runs its second vector slot 25 % full at C = 320), the
+// reductions stay inside LPR-lane groups, the arithmetic is packed fp32x2 and gamma / beta come from shared memory.
+// ncu on the generic kernel at C = 320: issue slots 65 % busy at 34 % occupancy and 37 % of the DRAM peak — it was bound
+// by its instruction count (~200 per 16-byte vector), not by HBM (profiles/r02_ncu_norms.txt).
+// (A persistent "streaming" form of the generic kernel — fixed grid, next row group's loads in flight — was measured
+//  SLOWER, 112 vs 87 us at C = 320, and dropped: the loads were never the problem.)
+template <int LPR, int ITER>
+__global__ void __launch_bounds__(256) layernorm_c40_kernel(const __half* __restrict__ x, int64_t ldx, int64_t rows,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps,
+                                                            __half* __restrict__ y, int64_t ldy, int rev) {
+  constexpr int C = 40 * LPR, RW = 32 / LPR;  // channels; rows per warp and iteration
+  extern __shared__ float ln_gb[];             // [C] gamma, [C] beta
   pdl_wait();
   pdl_launch_dependents();
-  const int lane = threadIdx.x & 31;
-  const int vecs = C / 8;
-  const int64_t ngroups = (rows + R - 1) / R;
-  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
-  const int64_t w0 = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  auto group_row0 = [&](int64_t g) { return (rev ? ngroups - 1 - g : g) * R; };
-  auto load = [&](uint4 (&u)[R][MAXV], int64_t g) {
-    const int64_t row0 = group_row0(g);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    ln_gb[c] = gamma[c];
+    ln_gb[C + c] = beta[c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % LPR, rsel = lane / LPR;  // position inside the row's lane group; which of the warp's rows
+  const int64_t blk = rev ? static_cast<int64_t>(gridDim.x) - 1 - blockIdx.x : static_cast<int64_t>(blockIdx.x);
+  const int64_t row_base = (blk * (blockDim.x >> 5) + warp) * (RW * ITER);
+  uint4 u[ITER][5];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+  for (int it = 0; it < ITER; ++it) {
+    const int64_t row = row_base + it * RW + rsel;
+    if (row < rows) {
 #pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int vi = lane + i * 32;
-        if (vi < vecs && row0 + r < rows) u[r][i] = *reinterpret_cast<const uint4*>(x + (row0 + r) * ldx + vi * 8);
-      }
-  };
-  auto process = [&](const uint4 (&u)[R][MAXV], int64_t g) {
-    const int64_t row0 = group_row0(g);
+      for (int i = 0; i < 5; ++i) u[it][i] = *reinterpret_cast<const uint4*>(x + row * ldx + (sub + i * LPR) * 8);
+    }
+  }
+  const float inv_c = 1.f / C;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int64_t row = row0 + r;
-      if (row >= rows) break;  // warp-uniform
-      float v[MAXV][8];
-      float sum = 0.f;
+  for (int it = 0; it < ITER; ++it) {
+    const int64_t row = row_base + it * RW + rsel;
+    const bool ok = row < rows;  // whole lane groups are in or out; the shuffles below stay inside a group
+    uint64_t v[5][4];
+    uint64_t s2 = pk2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int vi = lane + i * 32;
-        if (vi < vecs) {
-          const __half2* h = reinterpret_cast<const __half2*>(&u[r][i]);
+    for (int i = 0; i < 5; ++i) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u[it][i]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(h[j]);
-            v[i][2 * j] = f.x;
-            v[i][2 * j + 1] = f.y;
-            sum += f.x + f.y;
-          }
-        }
-      }
-      sum = warp_sum(sum);
-      const float mean = sum / C;
-      float sq = 0.f;
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int vi = lane + i * 32;
-        if (vi < vecs) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float d = v[i][j] - mean;
-            sq = fmaf(d, d, sq);
-          }
-        }
-      }
-      sq = warp_sum(sq);
-      const float rstd = rsqrtf(sq / C + eps);
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int vi = lane + i * 32;
-        if (vi < vecs) {
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
-          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8) + 1);
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8) + 1);
-          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
-          *reinterpret_cast<uint4*>(y + row * ldy + vi * 8) =
-              make_uint4(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]), pack_h2(o[4], o[5]), pack_h2(o[6], o[7]));
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = ok ? __half22float2(h[j]) : make_float2(0.f, 0.f);
+        v[i][j] = pk2(f.x, f.y);
+        s2 = add2(s2, v[i][j]);
       }
     }
-  };
-  uint4 ua[R][MAXV], ub[R][MAXV];
-  int64_t g = w0;
-  if (g < ngroups) load(ua, g);
-#pragma unroll 1
-  while (g < ngroups) {
-    const int64_t g1 = g + nwarps;
-    if (g1 < ngroups) load(ub, g1);
-    process(ua, g);
-    if (g1 >= ngroups) break;
-    const int64_t g2 = g1 + nwarps;
-    if (g2 < ngroups) load(ua, g2);
-    process(ub, g1);
-    g = g2;
+    float sa, sb;
+    upk2(s2, sa, sb);
+    float sum = sa + sb;
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    const uint64_t nm2 = pk2(-mean, -mean);
+    uint64_t q2 = pk2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[i][j] = add2(v[i][j], nm2);
+        q2 = fma2(v[i][j], v[i][j], q2);
+      }
+    upk2(q2, sa, sb);
+    float sq = sa + sb;
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_c + eps);
+    const uint64_t r2 = pk2(rstd, rstd);
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int c0 = (sub + i * LPR) * 8;
+        const float4 g0 = *reinterpret_cast<const float4*>(ln_gb + c0), g1 = *reinterpret_cast<const float4*>(ln_gb + c0 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(ln_gb + C + c0), b1 = *reinterpret_cast<const float4*>(ln_gb + C + c0 + 4);
+        float o0, o1, o2, o3, o4, o5, o6, o7;
+        upk2(fma2(mul2(v[i][0], r2), pk2(g0.x, g0.y), pk2(b0.x, b0.y)), o0, o1);
+        upk2(fma2(mul2(v[i][1], r2), pk2(g0.z, g0.w), pk2(b0.z, b0.w)), o2, o3);
+        upk2(fma2(mul2(v[i][2], r2), pk2(g1.x, g1.y), pk2(b1.x, b1.y)), o4, o5);
+        upk2(fma2(mul2(v[i][3], r2), pk2(g1.z, g1.w), pk2(b1.z, b1.w)), o6, o7);
+        *reinterpret_cast<uint4*>(y + row * ldy + c0) =
+            make_uint4(pack_h2(o0, o1), pack_h2(o2, o3), pack_h2(o4, o5), pack_h2(o6, o7));
+      }
+    }
   }
+}
+
+template <int LPR>
+static int launch_ln_c40(const __half* x, int64_t ldx, int64_t rows, const float* gamma, const float* beta, float eps,
+                         __half* y, int64_t ldy, int rev, cudaStream_t stream) {
+  constexpr int ITER = 2, C = 40 * LPR;
+  const int64_t rows_per_block = 8 * (32 / LPR) * ITER;
+  const unsigned blocks = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
+  SDW_CUDA_OK(launch_pdl(layernorm_c40_kernel<LPR, ITER>, dim3(blocks), dim3(256), static_cast<size_t>(2) * C * sizeof(float),
+                         stream, x, ldx, rows, gamma, beta, eps, y, ldy, rev));
+  SDW_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int layernorm(const __half* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
@@ -459,14 +462,14 @@ int layernorm(const __half* x, int64_t ldx, int64_t rows, int C, const float* ga
   SDW_REQUIRE(C % 8 == 0 && C <= 8 * 32 * 8, "LayerNorm: C % 8 == 0 and C <= 2048");
   const int vecs = C / 8;
   const int rev = norm_reverse();
-  // SDW_LN_STREAM=1: the streaming kernel (fixed grid, next group's loads in flight) for C <= 512 — A/B switch
-  static const int stream_env = [] { const char* e = std::getenv("SDW_LN_STREAM"); return e ? std::atoi(e) : 0; }();
-  if (stream_env && vecs <= 64 && rows >= 148 * 8 * 4 * 4) {
-    const int per_sm = stream_env >= 2 ? stream_env : 4;
-    SDW_CUDA_OK(launch_pdl(layernorm_stream_kernel<2, 4>, dim3(148 * per_sm), dim3(256), 0, stream, x, ldx, rows, C, gamma, beta,
-                           eps, y, ldy, rev));
-    SDW_CUDA_OK(cudaGetLastError());
-    return 0;
+  // the UNet widths take the lane-group kernel; SDW_LN_C40=0 keeps the generic one (A/B)
+  static const int c40_env = [] { const char* e = std::getenv("SDW_LN_C40"); return e ? std::atoi(e) : 1; }();
+  const bool vec_ok = (ldx % 8 == 0) && (ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+  if (c40_env && vec_ok) {
+    if (C == 320) return launch_ln_c40<8>(x, ldx, rows, gamma, beta, eps, y, ldy, rev, stream);
+    if (C == 640) return launch_ln_c40<16>(x, ldx, rows, gamma, beta, eps, y, ldy, rev, stream);
+    if (C == 1280) return launch_ln_c40<32>(x, ldx, rows, gamma, beta, eps, y, ldy, rev, stream);
   }
   if (vecs <= 64) {
     const unsigned blocks = static_cast<unsigned>((rows + 31) / 32);

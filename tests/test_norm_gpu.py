@@ -56,7 +56,7 @@ def test_groupnorm_strided_views_and_determinism():
     assert (outs[0].float() - ref).abs().max().item() <= 2 ** -9 * ref.abs().max().item() + 1e-3
 
 
-@pytest.mark.parametrize("rows,Cc", [(4096, 320), (1000, 640), (77, 1280), (5, 512)])
+@pytest.mark.parametrize("rows,Cc", [(4096, 320), (1000, 640), (77, 1280), (5, 512), (4099, 320), (3, 320), (1, 640), (129, 768)])
 def test_layernorm(rows, Cc):
     n = _native()
     x = _rand(rows, Cc, seed=5, scale=2.0, shift=-0.5)
@@ -65,5 +65,23 @@ def test_layernorm(rows, Cc):
     y = torch.full_like(x, float("nan"))
     n.layernorm(x, rows, Cc, gamma, beta, 1e-5, y)
     torch.cuda.synchronize()
+    ref = Fn.layer_norm(x.float(), (Cc,), gamma, beta, 1e-5)
+    assert (y.float() - ref).abs().max().item() <= 2 ** -9 * ref.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("Cc", [320, 640, 1280])
+def test_layernorm_strided_rows(Cc):
+    """input / output rows are slices of wider buffers (pitch != C): the lane-group kernel must honour both pitches"""
+    n = _native()
+    rows = 531
+    big = _rand(rows, Cc + 64, seed=8, scale=1.5, shift=0.25)
+    x = big[:, 32:32 + Cc]
+    gamma = _rand(Cc, seed=9).float() * 0.2 + 1.0
+    beta = _rand(Cc, seed=10).float() * 0.1
+    ybuf = torch.zeros(rows, Cc + 128, dtype=torch.float16, device="cuda")
+    y = ybuf[:, 64:64 + Cc]
+    n.layernorm(x, rows, Cc, gamma, beta, 1e-5, y)
+    torch.cuda.synchronize()
+    assert (ybuf[:, :64] == 0).all() and (ybuf[:, 64 + Cc:] == 0).all()
     ref = Fn.layer_norm(x.float(), (Cc,), gamma, beta, 1e-5)
     assert (y.float() - ref).abs().max().item() <= 2 ** -9 * ref.abs().max().item() + 1e-3
