@@ -233,6 +233,18 @@ class StableDiffusionWalkPipeline:
                                       f"rules only: {sorted(kinds)}); stochastic samplers (Euler ancestral, "
                                       "DPM-Solver SDE variants) are not implemented")
         kind = kinds[sc["_class_name"]]
+        # scheduler_config.json fields beyond the beta schedule: the reference itself forces steps_offset = 1 and
+        # clip_sample = False on whatever the checkpoint says (P:85-110), so those are applied, not read; anything this
+        # implementation cannot honour is an error, never silently ignored
+        if sc.get("trained_betas") is not None:
+            raise NotImplementedError("scheduler_config.json: trained_betas is not supported (scaled_linear schedule only)")
+        if sc.get("set_alpha_to_one", False):
+            raise NotImplementedError("scheduler_config.json: set_alpha_to_one=True is not supported (Stable Diffusion "
+                                      "checkpoints ship False; the final alpha is alphas_cumprod[0])")
+        if kind == "pndm" and not sc.get("skip_prk_steps", True):
+            raise NotImplementedError("PNDM with Runge-Kutta warm-up steps (skip_prk_steps=False) is not supported")
+        if sc.get("prediction_type", "epsilon") not in ("epsilon", "v_prediction"):
+            raise NotImplementedError(f"prediction_type {sc['prediction_type']!r} is not supported")
         ucfg.prediction_type = sc.get("prediction_type", "epsilon")
         sch = SCHEDULERS[kind](num_train_timesteps=sc.get("num_train_timesteps", 1000),
                                beta_start=sc.get("beta_start", 0.00085), beta_end=sc.get("beta_end", 0.012),
