@@ -234,17 +234,6 @@ __device__ __forceinline__ void tma_load_4d_2sm(const void* map, uint32_t bar_cl
       "r"(c3)
       : "memory");
 }
-// same, multicast: the box lands at the same smem offset in every CTA of `mask`, and the completion bytes are signalled
-// on the barrier at the same offset in the LEADER (even CTA) of each destination CTA's pair
-__device__ __forceinline__ void tma_load_4d_2sm_mc(const void* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
-                                                   int c2, int c3, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-      "[%0], [%1, {%4, %5, %6, %7}], [%2], %3;"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "h"(mask), "r"(c0), "r"(c1),
-      "r"(c2), "r"(c3)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols) {  // one warp in EACH CTA
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                "r"(ncols)
