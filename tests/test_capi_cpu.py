@@ -114,7 +114,7 @@ def test_launch_plans_validate_without_a_gpu():
         lib.sdw_debug_plan_only(0)
 
 
-@pytest.mark.parametrize("toggle", ["SDW_GEMM_EW=2", "SDW_EPI_TMA=0", "SDW_EPI_TMA=2", "SDW_GEMM_TR=0",
+@pytest.mark.parametrize("toggle", ["SDW_GEMM_EW=2", "SDW_GEMM_EW=4", "SDW_EPI_TMA=0", "SDW_EPI_TMA=2", "SDW_GEMM_TR=0",
                                     "SDW_NO_FLASH=1"])
 def test_launch_plans_validate_under_every_opt_in_switch(toggle):
     """the kernel A/B switches (8-warp epilogue everywhere, classic epilogue, per-tap conv loads, ...) must
