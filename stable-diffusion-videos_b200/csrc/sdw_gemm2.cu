@@ -11,9 +11,10 @@
 //                         signalled on the LEADER's full barrier (cta_group::2 TMA, mapa'd barrier address).
 //   warp 1 (leader)     : MMA issuer, 4 x UMMA(M=256, N=BN, K=16) per K block; tcgen05.commit multicast frees the
 //                         smem stage in both CTAs / publishes the accumulator to both epilogues.
-//   warp 2 (both CTAs)  : residual producer of the TMA epilogue (one thread; a 4-deep ring of [128 x 32] chunks).
-//   warps 4-11 (both)   : epilogue on the CTA's own 128 rows, two warps per TMEM lane quarter (sdw_gemm_epi.cuh), then a
-//                         remote arrive on the leader's tmem_empty barrier.
+//   warp 2 (both CTAs)  : residual producer of the TMA epilogue (one thread; [128 x 32] chunks, two ring slots per chunk
+//                         group c % EW).
+//   warps 4.. (both)    : epilogue on the CTA's own 128 rows, EW = 2 or 4 warps per TMEM lane quarter (sdw_gemm_epi.cuh),
+//                         then a remote arrive on the leader's tmem_empty barrier.
 //
 // Mainloop flavours (all in this kernel; chosen per GEMM by plan_gemm, sdw_gemm.cu):
 //   per-tap      one activation box per (tap, channel chunk)              every conv / linear (the original form)
@@ -26,7 +27,7 @@
 // spins on tmem_empty and the TMA producer on the full ring while two epilogue warps per scheduler run at 0.44 IPC
 // (profiles/r02_ncu_epilogue_shortk.md).
 // Shared memory is carved at run time: [barriers 1 KB | operand ring | epilogue buffers]; the planner sizes the ring
-// from what the chosen epilogue (classic: 16 KB, TMA: 40-72 KB) leaves of the 227 KB.
+// from what the chosen epilogue (classic: 16 KB, TMA: 40-72 KB, with 16 warps up to 112 KB) leaves of the 227 KB.
 #include "sdw_gemm_epi.cuh"
 #include "sdw_internal.h"
 #include "sdw_ptx.cuh"
